@@ -1,0 +1,196 @@
+/*
+ * b200cd.h — C ABI of the B200 (sm_100a) training-step kernels for multimodal siamese change detection.
+ *
+ * This is the drop-in boundary for ONE hot path of SebastianHafner/multimodal_siamese_cd: forward +
+ * backward of the U-Net family in utils/networks.py and the losses in utils/loss_functions.py.
+ * The reference is pure Python over torch ops; each entry point below replaces the torch op(s) cited
+ * next to it (file:line relative to the reference root). The Python host layer
+ * (multimodal_siamese_cd_b200/) binds these with ctypes and registers them as torch custom ops.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory (inputs, outputs,
+ *     workspaces); the library allocates nothing in steady state (one 4-byte error flag per device at
+ *     b200cd_init).
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
+ *   - activations are NHWC bf16 with an explicit element stride per pixel (`ld`, multiple of 8), so
+ *     channel slices of a concatenation buffer are addressed without copies; base pointers must be
+ *     16-byte aligned. Parameters, logits, targets, statistics and gradients of parameters are fp32 in
+ *     the reference layouts.
+ *   - return value: 0 = ok, otherwise a B200CD_ERR_* code; b200cd_last_error() gives the message
+ *     (thread-local). Nothing throws.
+ *   - sm_100a only: b200cd_init fails with B200CD_ERR_ARCH on anything else. There is no CPU path.
+ */
+#ifndef B200CD_H_
+#define B200CD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CD_OK 0
+#define B200CD_ERR_SHAPE 1
+#define B200CD_ERR_ALIGN 2
+#define B200CD_ERR_ARCH 3
+#define B200CD_ERR_CUDA 4
+#define B200CD_ERR_DEVICE 5 /* a kernel reported a pipeline time-out (see b200cd_device_status) */
+
+#define B200CD_ABI_VERSION 1
+
+int b200cd_abi_version(void);
+const char* b200cd_last_error(void);
+
+/* Binds the library to CUDA device `device` of the calling process: checks compute capability 10.x,
+ * resolves cuTensorMapEncodeTiled, allocates the per-device error flag. Idempotent. */
+int b200cd_init(int device);
+
+/* Synchronises `stream` and returns 0, or B200CD_ERR_DEVICE if any kernel launched so far on this device
+ * recorded a pipeline time-out (wrong descriptor / byte count); the flag is cleared. Test/debug aid. */
+int b200cd_device_status(int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Input packing — replaces torch.cat((x_t1, x_t2), 1) utils/networks.py:74,106,113, the modality
+ * slicing :105,112,233,246 and the implicit NCHW fp32 -> conv operand conversion of the first Conv2d
+ * (InConv, :405-412). Writes bf16 im2col rows [n_img*H*W][kpad], k = tap*Cin + ci (zero padded), so the
+ * first 3x3 conv is a plain GEMM.
+ *   cat_mode 0: images = [src0 batch ; src1 batch], Cin = nc (shared-weight t1 / t2 calls, :141-145)
+ *   cat_mode 1: channels = [src0 ; src1], Cin = 2*nc (early fusion, :74)
+ *   src0/src1: fp32 NCHW [B][csrc][H][W]; channels c_lo .. c_lo+nc-1 of each are used.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_pack_input(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B, int H,
+                      int W, int kpad, void* out_bf16, void* stream);
+
+/* Weight packing fp32 reference layouts -> bf16 GEMM operands (run every step: the optimizer owns the
+ * fp32 master weights, nn.Conv2d.weight / nn.ConvTranspose2d.weight utils/networks.py:392,395,433).
+ *   mode 0 conv3x3 forward   w[co=d0][ci=d1][3][3]  -> out[co][tap][ci]
+ *   mode 1 conv3x3 dgrad     out[ci][tap'][co] = w[co][ci][2-ky'][2-kx']
+ *   mode 2 first layer       out[co][kpad], k = tap*d1 + ci
+ *   mode 3 convT forward     w[ci=d0][co=d1][2][2]  -> out[tap*d1 + co][ci]
+ *   mode 4 convT dgrad       out[ci][tap*d1 + co] */
+int b200cd_pack_weights(int mode, const float* w, void* out_bf16, int d0, int d1, int kpad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * G1 — tcgen05 implicit GEMM, D[pixel, n] = sum_{tap,k} A_tap[pixel, k] * Bw[n, tap*ka + k].
+ *   mode 0: 3x3 same-conv, 9 taps — nn.Conv2d(in,out,3,padding=1) utils/networks.py:392,395 (forward;
+ *           with mode-1 packed weights also its input gradient).
+ *   mode 1: single tap — the im2col'ed first conv; with out_mode 1 the forward of
+ *           nn.ConvTranspose2d(c,c,2,stride=2) utils/networks.py:433 (N = 4*cout, scatter epilogue writes
+ *           straight into the channel slice of the concat buffer, replacing F.pad + torch.cat :443,449).
+ *   mode 2: 4 taps gathered at stride 2 from a (2H x 2W) tensor — input gradient of the transposed conv.
+ *   A: bf16 NHWC view [n_img][H][W][ka] (mode 2: [n_img][2H][2W][ka]) with stride a_ld per pixel.
+ *   Bw: bf16 [N][taps*ka] row-major.
+ *   out: bf16 NHWC view [n_img][H][W][N] (out_mode 1: [n_img][2H][2W][cout]) with stride out_ld.
+ *   bias: fp32 [N] (out_mode 1: [cout]) or NULL.
+ *   stats: NULL or fp32 [num_tiles][N][2] per-tile (sum, sum of squares) of the stored bf16 values — the
+ *          batch statistics nn.BatchNorm2d (utils/networks.py:393,396) needs; num_tiles from
+ *          b200cd_conv_gemm_tiles. A tile never spans two images.
+ *   requires ka % 64 == 0, N % 64 == 0, a_ld % 8 == 0, out_ld % 8 == 0.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                     const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
+                     void* stream);
+/* tiles_per_image for (H, W): stats has n_img * tiles_per_image rows. */
+int b200cd_conv_gemm_tiles(int H, int W);
+
+/* ---------------------------------------------------------------------------------------------------
+ * G2 — tcgen05 weight-gradient GEMM, ws[split][tap][m][n] = sum_{pixels in split} U[pixel, m] * V_tap[pixel, n]
+ * (the weight gradients autograd produces for nn.Conv2d / nn.ConvTranspose2d, utils/networks.py:392,395,433).
+ *   mode 0: 3x3 conv, 9 taps; V is read shifted by sign*(kx-1, ky-1) (sign=+1: U = dOut, V = input;
+ *           sign=-1: U = input, V = dOut).
+ *   mode 1: single tap (first layer on the im2col rows).
+ *   mode 2: transposed conv, 4 taps: U = low-res input [n_img][H][W][cu], V = full-res gradient
+ *           [n_img][2H][2W][cv] gathered at (2y+dy, 2x+dx).
+ *   ws element (split, tap, m, n) at split*split_stride + tap*tap_stride + m*m_stride + n*n_stride.
+ *   requires cv % 64 == 0, cu % 64 == 0; H, W arbitrary (out-of-image pixels read as zero).
+ *   halo: 1 = load the shifted operand once per pixel tile with a one-row halo (mode 0 only).
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
+                      int cv, int n_img, int H, int W, float* ws, int splits, int64_t split_stride, int64_t tap_stride,
+                      int64_t m_stride, int64_t n_stride, void* stream);
+/* number of 8x8 pixel tiles (upper bound for `splits`) */
+int b200cd_wgrad_tiles(int n_img, int H, int W);
+
+/* Fixed-order sum over splits into the reference parameter layout.
+ *   layout 0: ws[s][tap][d0][d1] -> grad[d0][d1][tap]  (Conv2d.weight [co][ci][3][3]; ConvTranspose2d.weight [ci][co][2][2])
+ *   layout 1: ws[s][d0][ld1], k = tap*d1 + i -> grad[d0][d1][tap], split_stride = d0*ld1 (first layer) */
+int b200cd_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int layout, int d0, int d1, int taps,
+                        float* grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * BatchNorm2d (train or eval), utils/networks.py:393,396 — statistics stage.
+ *   partial: the `stats` output of b200cd_conv_gemm, ld = its N; stat-group g owns tiles
+ *            [g*tiles_per_group, (g+1)*tiles_per_group) (a group = one reference module call, i.e. one
+ *            timestamp of the shared-weight encoder, SURVEY §0 finding 1).
+ *   count: elements per channel per group. ws: fp64 [spl][G][C][2].
+ *   train=1: batch statistics; running_mean/var are updated once per group in order 0..G-1
+ *            (order_rev=1: G-1..0, decoder_sem is called on t2 first, utils/networks.py:191-195) with the
+ *            unbiased variance; *nbt += G. train=0: running statistics are used, nothing is updated.
+ *   outputs fp32 [G][C]: mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_bn_stats(const float* partial, int ld, int C, int tiles_per_group, int G, double count, int spl, double* ws,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var, int64_t* nbt,
+                    float momentum, float eps, int train, int order_rev, float* mean, float* invstd, float* scale,
+                    float* shift, void* stream);
+
+/* BN-apply + nn.ReLU (utils/networks.py:394,397) fused with nn.MaxPool2d(2) (:420), torch.sub(f_t2, f_t1)
+ * (:147-150, 183-186, 223-228) and the skip half of torch.cat([x2, x1]) (:449).
+ *   r: conv output bf16 [n_img][H][W][C]; diff=1: images [0,n_img/2) are t1, the rest t2, and
+ *   dif[n] = a[n + n_img/2] - a[n]. Outputs (each nullable): a, a2 (second copy, e.g. a concat slice),
+ *   pool [n_img][H/2][W/2][C], dif [n_img/2][H][W][C]. */
+int b200cd_bn_apply(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
+                    int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
+                    void* dif, int64_t ld_d, void* stream);
+
+/* Gradient sources summed on the fly by the BN backward kernels. */
+typedef struct {
+  int32_t kind;     /* 0 none; 1 bf16 NHWC at this resolution; 2 bf16 NHWC at half resolution, routed to the
+                       arg-max of each 2x2 window (MaxPool2d backward); 3 fp32 dz[pixel] times w[channel]
+                       (OutConv backward, utils/networks.py:457) */
+  const void* ptr;
+  const float* w;   /* kind 3 */
+  int64_t ld;
+  int32_t n_mod;    /* > 0: source image = n % n_mod and scale = n < n_mod ? scale_lo : scale_hi
+                       (the t2 - t1 difference feeds +d to t2 and -d to t1) */
+  float scale_lo, scale_hi;
+} b200cd_grad_src;
+
+/* BatchNorm2d + ReLU backward: dr = scale*(dy - mean_g(dy) - xhat*mean_g(dy*xhat)), dy = (sum of sources)*[y>0];
+ * dgamma[C], dbeta[C] summed over groups. ws: fp32, b200cd_bn_bwd_ws_floats(...) floats. */
+int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                  const float* shift, const b200cd_grad_src* srcs /* [3] */, int n_img, int H, int W, int C, int G,
+                  float* ws, float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream);
+size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G);
+
+/* OutConv (nn.Conv2d(c, 1, 1), utils/networks.py:454-461) forward over one or two C-channel inputs
+ * (the fusion heads read torch.concat((x_stream1, x_stream2), 1), :118,255,302, without materialising it). */
+int b200cd_head_fwd(const void* a0, int64_t ld0, const void* a1, int64_t ld1, int C, const float* w, const float* b,
+                    int64_t npix, float* logits, void* stream);
+
+/* out[c] = sum_pixels wgt[pixel] * x[pixel][c]  (x == NULL: C = 1, out = sum wgt; wgt == NULL: plain column sum).
+ * OutConv weight/bias gradients and the ConvTranspose2d bias gradient. ws: fp32 [nblk*C]. */
+int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * power_jaccard_loss, utils/loss_functions.py:141-150. sums = (sum p*t, sum p^2, sum t^2) in fp64 over the
+ * selected rows (rowmask == NULL: all; else rows with (rowmask[row] != 0) == sel, the boolean row
+ * indexing of train_semisupervised.py:85-87,102-104). t_is_logit: the target is sigmoid(t) and receives
+ * a gradient (MMCR consistency term, :75-76,105). ws: fp64 [nblk*3].
+ * A data-parallel caller all-reduces `sums` (SUM) between b200cd_pj_fwd and b200cd_pj_loss / _bwd.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_pj_fwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel, int rows,
+                  int64_t per_row, int nblk, double* ws, double* sums, void* stream);
+int b200cd_pj_loss(const double* sums, float* loss, void* stream);
+/* dz (+)= g * dL/dz, dt (+)= g * dL/dt (dt nullable), g = gmul * (gptr ? *gptr : 1). accumulate=0 overwrites
+ * (unselected rows get 0). */
+int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel, int rows,
+                  int64_t per_row, const double* sums, const float* gptr, float gmul, int accumulate, float* dz,
+                  float* dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CD_H_ */

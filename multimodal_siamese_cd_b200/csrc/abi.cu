@@ -1,0 +1,425 @@
+// C-ABI layer (include/b200cd.h): argument validation, TMA tensor-map construction, error codes.
+// Everything exported is extern "C" with plain pointers and sizes; kernels live in the other .cu files.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/b200cd.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(B200CD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int kMaxDevices = 16;
+EncodeTiledFn g_encode = nullptr;
+int* g_err_flag[kMaxDevices] = {nullptr};
+
+int current_err_flag(int** out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || g_err_flag[dev] == nullptr)
+    return fail(B200CD_ERR_ARCH, "b200cd_init(%d) has not been called for the current device", dev);
+  *out = g_err_flag[dev];
+  return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// rank-2 or rank-5 bf16 tensor map with the 128-byte swizzle; dims/box innermost first, strides in bytes
+// for dims 1..rank-1.
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+  if (g_encode == nullptr) return fail(B200CD_ERR_ARCH, "b200cd_init has not been called");
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return fail(B200CD_ERR_SHAPE, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i < rank - 1; ++i) {
+    gs[i] = strides[i];
+    if (strides[i] % 16 != 0) return fail(B200CD_ERR_ALIGN, "TMA stride %d = %llu not a multiple of 16 bytes", i,
+                                          static_cast<unsigned long long>(strides[i]));
+  }
+  if (!aligned16(base)) return fail(B200CD_ERR_ALIGN, "TMA base pointer not 16-byte aligned");
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd,
+                        gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200CD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// NHWC view [n][h][w][c] with per-pixel stride ld (elements) as a rank-5 map (trailing unit dim).
+int make_nhwc_map(CUtensorMap* m, const void* base, int64_t ld, int c, int w, int h, int n, uint32_t bw, uint32_t bh) {
+  const uint64_t e = 2;
+  const uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+  const uint64_t strides[4] = {(uint64_t)ld * e, (uint64_t)w * ld * e, (uint64_t)h * w * ld * e,
+                               (uint64_t)n * h * w * ld * e};
+  const uint32_t box[5] = {64, bw, bh, 1, 1};
+  return make_map(m, base, 5, dims, strides, box);
+}
+
+// Full-resolution NHWC tensor [n][2h][2w][c] viewed as [n*h][dy][w][dx][c]: the 2x2/stride-2 gather/scatter
+// of the transposed convolution as one box per (dy, dx).
+int make_up2_map(CUtensorMap* m, const void* base, int64_t ld, int c, int w, int h, int n, uint32_t bw, uint32_t bh) {
+  const uint64_t e = 2;
+  const uint64_t dims[5] = {(uint64_t)c, 2, (uint64_t)w, 2, (uint64_t)n * h};
+  const uint64_t strides[4] = {(uint64_t)ld * e, 2 * (uint64_t)ld * e, 2 * (uint64_t)w * ld * e,
+                               4 * (uint64_t)w * ld * e};
+  const uint32_t box[5] = {64, 1, bw, 1, bh};
+  return make_map(m, base, 5, dims, strides, box);
+}
+
+void tile_shape(int W, int* tw, int* th) {
+  if (W >= 16) {
+    *tw = 16;
+    *th = 8;
+  } else {
+    *tw = 8;
+    *th = 16;
+  }
+}
+
+int bn_bwd_nblk(int n_img, int H, int W, int C, int G) {
+  const long long wins = static_cast<long long>(n_img / G) * ((H + 1) / 2) * ((W + 1) / 2);
+  const int lanes = 256 / (C / 8);
+  long long nblk = wins / (static_cast<long long>(lanes) * 4);
+  const long long cap = (148 * 4) / G;
+  if (nblk > cap) nblk = cap;
+  if (nblk < 1) nblk = 1;
+  return static_cast<int>(nblk);
+}
+
+bool chan_ok(int C) { return C >= 64 && C % 64 == 0 && 256 % (C / 8) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int b200cd_abi_version(void) { return B200CD_ABI_VERSION; }
+const char* b200cd_last_error(void) { return g_last_error.c_str(); }
+
+int b200cd_init(int device) {
+  if (device < 0 || device >= kMaxDevices) return fail(B200CD_ERR_SHAPE, "device index %d out of range", device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B200CD_ERR_ARCH, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (fn == nullptr || q != cudaDriverEntryPointSuccess)
+      return fail(B200CD_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  if (g_err_flag[device] == nullptr) {
+    int* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, sizeof(int)));
+    CUDA_TRY(cudaMemset(p, 0, sizeof(int)));
+    g_err_flag[device] = p;
+  }
+  return 0;
+}
+
+int b200cd_device_status(int device, void* stream) {
+  if (device < 0 || device >= kMaxDevices || g_err_flag[device] == nullptr)
+    return fail(B200CD_ERR_ARCH, "b200cd_init(%d) has not been called", device);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  int v = 0;
+  CUDA_TRY(cudaMemcpy(&v, g_err_flag[device], sizeof(int), cudaMemcpyDeviceToHost));
+  if (v != 0) {
+    CUDA_TRY(cudaMemset(g_err_flag[device], 0, sizeof(int)));
+    return fail(B200CD_ERR_DEVICE, "a tensor-core kernel timed out waiting on an mbarrier (device code %d)", v);
+  }
+  return 0;
+}
+
+int b200cd_pack_input(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B, int H,
+                      int W, int kpad, void* out, void* stream) {
+  const int cin = cat_mode ? 2 * nc : nc;
+  if (nc <= 0 || c_lo < 0 || c_lo + nc > csrc || B <= 0 || H <= 0 || W <= 0)
+    return fail(B200CD_ERR_SHAPE, "pack_input: bad channel/batch arguments");
+  if (kpad % 64 != 0 || 9 * cin > kpad || kpad > 256)
+    return fail(B200CD_ERR_SHAPE, "pack_input: kpad=%d must be a multiple of 64 holding 9*Cin=%d", kpad, 9 * cin);
+  if (!aligned16(out)) return fail(B200CD_ERR_ALIGN, "pack_input: output not 16-byte aligned");
+  CUDA_TRY(b200cd::launch_pack_input(src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad, out,
+                                     reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, void* stream) {
+  if (mode < 0 || mode > 4 || d0 <= 0 || d1 <= 0) return fail(B200CD_ERR_SHAPE, "pack_weights: bad arguments");
+  if (mode == 2 && (kpad % 64 != 0 || 9 * d1 > kpad)) return fail(B200CD_ERR_SHAPE, "pack_weights: bad kpad");
+  CUDA_TRY(b200cd::launch_pack_weights(mode, w, out, d0, d1, kpad, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_conv_gemm_tiles(int H, int W) {
+  int tw, th;
+  tile_shape(W, &tw, &th);
+  return ((W + tw - 1) / tw) * ((H + th - 1) / th);
+}
+
+int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                     const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
+                     void* stream) {
+  if (mode < 0 || mode > 2 || out_mode < 0 || out_mode > 1) return fail(B200CD_ERR_SHAPE, "conv_gemm: bad mode");
+  if (ka < 64 || ka % 64 != 0 || N < 64 || N % 64 != 0)
+    return fail(B200CD_ERR_SHAPE, "conv_gemm: ka=%d and N=%d must be multiples of 64", ka, N);
+  if (a_ld % 8 != 0 || out_ld % 8 != 0 || a_ld < ka) return fail(B200CD_ERR_ALIGN, "conv_gemm: ld must be a multiple of 8");
+  if (n_img <= 0 || H <= 0 || W <= 0) return fail(B200CD_ERR_SHAPE, "conv_gemm: empty problem");
+  if (out_mode == 1 && (cout < 64 || cout % 64 != 0 || N != 4 * cout))
+    return fail(B200CD_ERR_SHAPE, "conv_gemm: scatter epilogue needs N = 4*cout, cout %% 64 == 0");
+  if (out_mode == 1 && stats != nullptr) return fail(B200CD_ERR_SHAPE, "conv_gemm: no statistics with the scatter epilogue");
+  int* err = nullptr;
+  if (int rc = current_err_flag(&err)) return rc;
+
+  int tw, th;
+  tile_shape(W, &tw, &th);
+  b200cd::FpropParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode;
+  p.out_mode = out_mode;
+  p.taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
+  p.kchunks = ka / 64;
+  p.ka = ka;
+  p.tw = tw;
+  p.th = th;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
+  p.H = H;
+  p.W = W;
+  p.N = N;
+  p.cout = out_mode == 1 ? cout : N;
+  p.bias = bias;
+  p.stats = reinterpret_cast<float2*>(stats);
+  p.ragged = (H % th != 0 || W % tw != 0) ? 1 : 0;
+  p.err = err;
+  const int width = out_mode == 1 ? cout : N;
+  const int bn = (width % 128 == 0) ? 128 : 64;
+
+  CUtensorMap mapA, mapB, mapO;
+  int rc;
+  if (mode == 2) rc = make_up2_map(&mapA, A, a_ld, ka, W, H, n_img, tw, th);
+  else rc = make_nhwc_map(&mapA, A, a_ld, ka, W, H, n_img, tw, th);
+  if (rc) return rc;
+  {
+    const uint64_t ktot = static_cast<uint64_t>(p.taps) * ka;
+    const uint64_t dims[2] = {ktot, (uint64_t)N};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t box[2] = {64, (uint32_t)bn};
+    if ((rc = make_map(&mapB, Bw, 2, dims, strides, box))) return rc;
+  }
+  if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout, W, H, n_img, tw, th);
+  else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);
+  if (rc) return rc;
+  const int num_tiles = n_img * p.tiles_x * p.tiles_y;
+  CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_wgrad_tiles(int n_img, int H, int W) { return n_img * ((W + 7) / 8) * ((H + 7) / 8); }
+
+int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
+                      int cv, int n_img, int H, int W, float* ws, int splits, int64_t split_stride, int64_t tap_stride,
+                      int64_t m_stride, int64_t n_stride, void* stream) {
+  if (mode < 0 || mode > 2) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: bad mode");
+  if (cu < 64 || cu % 64 != 0 || cv < 64 || cv % 64 != 0)
+    return fail(B200CD_ERR_SHAPE, "wgrad_gemm: cu=%d, cv=%d must be multiples of 64", cu, cv);
+  if (u_ld % 8 != 0 || v_ld % 8 != 0) return fail(B200CD_ERR_ALIGN, "wgrad_gemm: ld must be a multiple of 8");
+  if (sign != 1 && sign != -1) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: sign must be +1 or -1");
+  if (n_stride == 1 && (!aligned16(ws) || split_stride % 4 != 0 || tap_stride % 4 != 0 || m_stride % 4 != 0))
+    return fail(B200CD_ERR_ALIGN, "wgrad_gemm: workspace strides must keep 16-byte alignment");
+  const int total = b200cd_wgrad_tiles(n_img, H, W);
+  if (splits < 1 || splits > total) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: splits=%d outside [1, %d]", splits, total);
+  int* err = nullptr;
+  if (int rc = current_err_flag(&err)) return rc;
+  if (mode != 0) halo = 0;
+
+  b200cd::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode;
+  p.sign = sign;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + 7) / 8;
+  p.tiles_y = (H + 7) / 8;
+  p.total_tiles = total;
+  p.splits = splits;
+  p.cu = cu;
+  p.cv = cv;
+  p.ws = ws;
+  p.split_stride = split_stride;
+  p.tap_stride = tap_stride;
+  p.m_stride = m_stride;
+  p.n_stride = n_stride;
+  p.err = err;
+  const int bn = (cv % 128 == 0) ? 128 : 64;
+
+  CUtensorMap mapU, mapV;
+  int rc;
+  if ((rc = make_nhwc_map(&mapU, U, u_ld, cu, W, H, n_img, 8, 8))) return rc;
+  if (mode == 2) rc = make_up2_map(&mapV, V, v_ld, cv, W, H, n_img, 8, 8);
+  else rc = make_nhwc_map(&mapV, V, v_ld, cv, W, H, n_img, 8, halo ? 10 : 8);
+  if (rc) return rc;
+  CUDA_TRY(b200cd::launch_wgrad(mapU, mapV, p, bn, halo, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int layout, int d0, int d1, int taps,
+                        float* grad, void* stream) {
+  if (splits < 1 || d0 <= 0 || d1 <= 0 || taps <= 0 || layout < 0 || layout > 1)
+    return fail(B200CD_ERR_SHAPE, "wgrad_reduce: bad arguments");
+  CUDA_TRY(b200cd::launch_wgrad_reduce(ws, splits, split_stride, layout, d0, d1, taps, grad,
+                                       reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_bn_stats(const float* partial, int ld, int C, int tiles_per_group, int G, double count, int spl, double* ws,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var, int64_t* nbt,
+                    float momentum, float eps, int train, int order_rev, float* mean, float* invstd, float* scale,
+                    float* shift, void* stream) {
+  if (C <= 0 || G <= 0) return fail(B200CD_ERR_SHAPE, "bn_stats: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (train) {
+    if (spl < 1 || tiles_per_group < 1 || partial == nullptr || ws == nullptr)
+      return fail(B200CD_ERR_SHAPE, "bn_stats: training mode needs partial statistics and a workspace");
+    if (spl > tiles_per_group) spl = tiles_per_group;
+    CUDA_TRY(b200cd::launch_bn_stats_reduce(reinterpret_cast<const float2*>(partial), ld, C, tiles_per_group, G, spl,
+                                            ws, st));
+  }
+  CUDA_TRY(b200cd::launch_bn_finalize(ws, spl, C, G, count, gamma, beta, running_mean, running_var,
+                                      reinterpret_cast<long long*>(nbt), momentum, eps, train, order_rev, mean, invstd,
+                                      scale, shift, st));
+  return 0;
+}
+
+int b200cd_bn_apply(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
+                    int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
+                    void* dif, int64_t ld_d, void* stream) {
+  if (C % 8 != 0 || n_img % G != 0 || (diff && (n_img % 2 != 0 || G != 2)))
+    return fail(B200CD_ERR_SHAPE, "bn_apply: bad C/G/diff combination");
+  if (ld_r % 8 || (a && ld_a % 8) || (a2 && ld_a2 % 8) || (pool && ld_p % 8) || (dif && ld_d % 8))
+    return fail(B200CD_ERR_ALIGN, "bn_apply: ld must be a multiple of 8");
+  if (!aligned16(r) || !aligned16(a) || !aligned16(a2) || !aligned16(pool) || !aligned16(dif))
+    return fail(B200CD_ERR_ALIGN, "bn_apply: pointers must be 16-byte aligned");
+  CUDA_TRY(b200cd::launch_bn_apply(r, ld_r, scale, shift, n_img, H, W, C, G, diff, a, ld_a, a2, ld_a2, pool, ld_p, dif,
+                                   ld_d, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G) {
+  if (!chan_ok(C) || G <= 0 || n_img % G != 0) return 0;
+  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
+  return static_cast<size_t>(2) * G * C * (nblk + 1);
+}
+
+int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                  const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
+                  float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream) {
+  if (!chan_ok(C)) return fail(B200CD_ERR_SHAPE, "bn_bwd: C=%d must be a multiple of 64 with 256 %% (C/8) == 0", C);
+  if (G <= 0 || n_img % G != 0) return fail(B200CD_ERR_SHAPE, "bn_bwd: n_img must be a multiple of G");
+  if (ld_r % 8 || ld_dr % 8 || !aligned16(r) || !aligned16(dr)) return fail(B200CD_ERR_ALIGN, "bn_bwd: alignment");
+  b200cd::GradSrcs gs;
+  memset(&gs, 0, sizeof(gs));
+  for (int i = 0; i < 3; ++i) {
+    gs.s[i].kind = srcs[i].kind;
+    gs.s[i].ptr = srcs[i].ptr;
+    gs.s[i].w = srcs[i].w;
+    gs.s[i].ld = srcs[i].ld;
+    gs.s[i].n_mod = srcs[i].n_mod;
+    gs.s[i].scale_lo = srcs[i].scale_lo;
+    gs.s[i].scale_hi = srcs[i].scale_hi;
+    if (srcs[i].kind < 0 || srcs[i].kind > 3) return fail(B200CD_ERR_SHAPE, "bn_bwd: bad gradient source kind");
+    if ((srcs[i].kind == 1 || srcs[i].kind == 2) && (srcs[i].ld % 8 != 0 || !aligned16(srcs[i].ptr)))
+      return fail(B200CD_ERR_ALIGN, "bn_bwd: gradient source %d alignment", i);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
+  float* partial = ws;
+  float* mdy = ws + static_cast<size_t>(2) * G * C * nblk;
+  float* mdyx = mdy + static_cast<size_t>(G) * C;
+  const double count = static_cast<double>(n_img / G) * H * W;
+  CUDA_TRY(b200cd::launch_bn_bwd_reduce(r, ld_r, mean, invstd, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, dgamma, dbeta, mdy, mdyx, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_dx(r, ld_r, mean, invstd, scale, shift, mdy, mdyx, gs, n_img, H, W, C, G, dr, ld_dr, st));
+  return 0;
+}
+
+int b200cd_head_fwd(const void* a0, int64_t ld0, const void* a1, int64_t ld1, int C, const float* w, const float* b,
+                    int64_t npix, float* logits, void* stream) {
+  if (C % 64 != 0 || C <= 0) return fail(B200CD_ERR_SHAPE, "head_fwd: C must be a multiple of 64");
+  if (ld0 % 8 || (a1 && ld1 % 8) || !aligned16(a0) || !aligned16(a1)) return fail(B200CD_ERR_ALIGN, "head_fwd: alignment");
+  CUDA_TRY(b200cd::launch_head_fwd(a0, ld0, a1, ld1, C, w, b, npix, logits, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
+                  void* stream) {
+  if (x != nullptr && !chan_ok(C)) return fail(B200CD_ERR_SHAPE, "colsum: unsupported C=%d", C);
+  if (x == nullptr && (C != 1 || wgt == nullptr)) return fail(B200CD_ERR_SHAPE, "colsum: x == NULL needs C == 1 and wgt");
+  if (nblk < 1 || npix < 1) return fail(B200CD_ERR_SHAPE, "colsum: empty");
+  if (x != nullptr && (ld % 8 || !aligned16(x))) return fail(B200CD_ERR_ALIGN, "colsum: alignment");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(b200cd::launch_colsum(x, ld, C, wgt, npix, nblk, ws, st));
+  CUDA_TRY(b200cd::launch_colsum_finalize(ws, nblk, C, out, st));
+  return 0;
+}
+
+int b200cd_pj_fwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel, int rows,
+                  int64_t per_row, int nblk, double* ws, double* sums, void* stream) {
+  if (rows < 1 || per_row < 4 || per_row % 4 != 0 || nblk < 1)
+    return fail(B200CD_ERR_SHAPE, "pj_fwd: per_row must be a positive multiple of 4");
+  if (!aligned16(z) || !aligned16(t)) return fail(B200CD_ERR_ALIGN, "pj_fwd: alignment");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(b200cd::launch_pj_reduce(z, t, t_is_logit, rowmask, sel, rows, per_row, nblk, ws, st));
+  CUDA_TRY(b200cd::launch_pj_finalize(ws, nblk, sums, st));
+  return 0;
+}
+
+int b200cd_pj_loss(const double* sums, float* loss, void* stream) {
+  CUDA_TRY(b200cd::launch_pj_loss(sums, loss, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel, int rows,
+                  int64_t per_row, const double* sums, const float* gptr, float gmul, int accumulate, float* dz,
+                  float* dt, void* stream) {
+  if (rows < 1 || per_row < 4 || per_row % 4 != 0) return fail(B200CD_ERR_SHAPE, "pj_bwd: per_row must be a multiple of 4");
+  if (!aligned16(z) || !aligned16(t) || !aligned16(dz) || !aligned16(dt)) return fail(B200CD_ERR_ALIGN, "pj_bwd: alignment");
+  CUDA_TRY(b200cd::launch_pj_bwd(z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr, gmul, accumulate, dz, dt,
+                                 reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

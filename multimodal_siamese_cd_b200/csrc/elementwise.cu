@@ -1,0 +1,933 @@
+// Memory-bound kernels of the training step (sm_100a): everything that is not a tensor-core contraction.
+// All activations are NHWC bf16 with an explicit element stride per pixel ("ld"), so producers can write
+// into channel slices of a concatenation buffer and consumers can read them without copy kernels.
+// Vector width is 8 channels = 16 bytes per thread access; reductions are two-stage (per-block partials,
+// then a fixed-order fp64 finalize) so results are run-to-run deterministic.
+//
+// Reference ops replaced (file:line in /root/reference):
+//   BatchNorm2d + ReLU (+ MaxPool2d, + torch.sub(t2, t1))   utils/networks.py:393-397, 420, 147-150
+//   torch.cat / slicing of the inputs                         utils/networks.py:74, 105-113, 233-246
+//   OutConv 1x1 heads                                         utils/networks.py:454-461
+//   power_jaccard_loss                                        utils/loss_functions.py:141-150
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200cd {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// Input packing: fp32 NCHW inputs -> bf16 im2col rows [pixel][kpad], k = tap*Cin + ci, zero padded.
+// The first-layer 3x3 conv (Cin in {2..8}) then runs as a plain GEMM on the tensor cores.
+//   cat_mode 0: images = [src0 batch ; src1 batch] (shared-weight t1/t2 call), Cin = nc
+//   cat_mode 1: channels = [src0 channels ; src1 channels] (early fusion), Cin = 2*nc
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pack_input_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                         int csrc, int c_lo, int nc, int cat_mode, int B, int H, int W,
+                                                         int kpad, __nv_bfloat16* __restrict__ out, long long npix) {
+  extern __shared__ uint32_t sm32[];
+  const int rowwords = kpad / 2 + 1;  // odd word stride -> conflict-free
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(sm32);
+  const int t = threadIdx.x;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * 128;
+  const long long pix = pix0 + t;
+  const int cin = cat_mode ? 2 * nc : nc;
+  __nv_bfloat16* myrow = sm + static_cast<size_t>(t) * rowwords * 2;
+  for (int k = 0; k < kpad; ++k) myrow[k] = __float2bfloat16_rn(0.f);
+  if (pix < npix) {
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src;
+      int b, c;
+      if (cat_mode == 0) {
+        src = n < B ? src0 : src1;
+        b = n < B ? n : n - B;
+        c = c_lo + ci;
+      } else {
+        src = ci < nc ? src0 : src1;
+        b = n;
+        c = c_lo + (ci < nc ? ci : ci - nc);
+      }
+      const float* plane = src + (static_cast<long long>(b) * csrc + c) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + kx - 1;
+          float v = 0.f;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(plane + static_cast<long long>(yy) * W + xx);
+          myrow[(ky * 3 + kx) * cin + ci] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int words = kpad / 2;
+  uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
+  for (int w = t; w < 128 * words; w += 128) {
+    const int row = w / words, col = w - row * words;
+    if (pix0 + row < npix) out32[(pix0 + row) * words + col] = sm32[row * rowwords + col];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing fp32 (reference layouts) -> bf16 GEMM operands.
+//   mode 0: conv3x3 forward   w[d0=co][d1=ci][3][3] -> out[co][tap][ci]
+//   mode 1: conv3x3 dgrad     out[ci][tap'][co] = w[co][ci][2-ky'][2-kx']
+//   mode 2: first layer       out[co][kpad], k = tap*ci_count + ci
+//   mode 3: convT forward     w[d0=ci][d1=co][2][2] -> out[tap*co_count + co][ci]
+//   mode 4: convT dgrad       out[ci][tap*co_count + co]
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
+                                    int d1, int kpad, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float v = 0.f;
+  if (mode == 0) {
+    const int ci = static_cast<int>(i % d1);
+    const int tap = static_cast<int>((i / d1) % 9);
+    const int co = static_cast<int>(i / (9ll * d1));
+    v = w[(static_cast<long long>(co) * d1 + ci) * 9 + tap];
+  } else if (mode == 1) {
+    const int co = static_cast<int>(i % d0);
+    const int tap = static_cast<int>((i / d0) % 9);
+    const int ci = static_cast<int>(i / (9ll * d0));
+    v = w[(static_cast<long long>(co) * d1 + ci) * 9 + (8 - tap)];
+  } else if (mode == 2) {
+    const int k = static_cast<int>(i % kpad);
+    const int co = static_cast<int>(i / kpad);
+    if (k < 9 * d1) {
+      const int tap = k / d1, ci = k - tap * d1;
+      v = w[(static_cast<long long>(co) * d1 + ci) * 9 + tap];
+    }
+  } else if (mode == 3) {
+    const int ci = static_cast<int>(i % d0);
+    const int n = static_cast<int>(i / d0);
+    const int tap = n / d1, co = n - tap * d1;
+    v = w[(static_cast<long long>(ci) * d1 + co) * 4 + tap];
+  } else {
+    const int n = static_cast<int>(i % (4ll * d1));
+    const int ci = static_cast<int>(i / (4ll * d1));
+    const int tap = n / d1, co = n - tap * d1;
+    v = w[(static_cast<long long>(ci) * d1 + co) * 4 + tap];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics: stage 1 reduces the conv epilogue's per-tile (sum, sumsq) partials over a
+// slice of the tiles of one stat-group in fp64; stage 2 finishes, produces mean / invstd and the
+// affine (scale, shift) the apply kernel uses, and updates the running statistics group by group.
+// Stat-group = one reference module call (timestamp t1 or t2 of the shared-weight encoder).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float2* __restrict__ partial, int ld, int C,
+                                                              int tiles_per_group, int spl,
+                                                              double* __restrict__ partial2) {
+  __shared__ double sh[8][32][2];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int l = threadIdx.x >> 5;
+  const int g = blockIdx.y, sp = blockIdx.z;
+  const int tb = static_cast<int>(static_cast<long long>(tiles_per_group) * sp / spl);
+  const int te = static_cast<int>(static_cast<long long>(tiles_per_group) * (sp + 1) / spl);
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const float2* base = partial + static_cast<long long>(g) * tiles_per_group * ld + c;
+    for (int t = tb + l; t < te; t += 8) {
+      const float2 v = __ldg(base + static_cast<long long>(t) * ld);
+      s += v.x;
+      q += v.y;
+    }
+  }
+  sh[l][threadIdx.x & 31][0] = s;
+  sh[l][threadIdx.x & 31][1] = q;
+  __syncthreads();
+  if (l == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) {
+      s += sh[i][threadIdx.x][0];
+      q += sh[i][threadIdx.x][1];
+    }
+    double* o = partial2 + ((static_cast<long long>(sp) * gridDim.y + g) * C + c) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ partial2, int spl, int C, int G, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps, int train, int order_rev,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (!train) {
+    // eval: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta for every group
+    const float is = 1.0f / sqrtf(running_var[c] + eps);
+    for (int g = 0; g < G; ++g) {
+      mean[g * C + c] = running_mean[c];
+      invstd[g * C + c] = is;
+      const float sc = gamma[c] * is;
+      scale[g * C + c] = sc;
+      shift[g * C + c] = beta[c] - running_mean[c] * sc;
+    }
+    return;
+  }
+  float rm = running_mean[c], rv = running_var[c];
+  for (int gi = 0; gi < G; ++gi) {
+    const int g = order_rev ? G - 1 - gi : gi;
+    double s = 0.0, q = 0.0;
+    for (int sp = 0; sp < spl; ++sp) {
+      const double* o = partial2 + ((static_cast<long long>(sp) * G + g) * C + c) * 2;
+      s += o[0];
+      q += o[1];
+    }
+    const double mu = s / count;
+    double var = q / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float muf = static_cast<float>(mu);
+    mean[g * C + c] = muf;
+    invstd[g * C + c] = is;
+    const float sc = gamma[c] * is;
+    scale[g * C + c] = sc;
+    shift[g * C + c] = beta[c] - muf * sc;
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * muf;
+    rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
+  }
+  running_mean[c] = rm;
+  running_var[c] = rv;
+  if (c == 0 && nbt != nullptr) *nbt += G;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN-apply + ReLU, fused with MaxPool2d(2), the t2 - t1 feature difference and a second copy into a
+// concat slice. One thread = one 2x2 pixel window x 8 channels (x both timestamps when diff).
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const __nv_bfloat16* r;
+  long long ld_r;
+  const float* scale;
+  const float* shift;
+  int n_img, H, W, C, G, diff;
+  __nv_bfloat16 *a, *a2, *pool, *dif;
+  long long ld_a, ld_a2, ld_p, ld_d;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
+  const int cvecs = p.C >> 3;
+  const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+  const int n_units = p.diff ? p.n_img / 2 : p.n_img;
+  const long long total = static_cast<long long>(n_units) * H2 * W2 * cvecs;
+  const int per_group = p.n_img / p.G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvecs);
+    long long w = i / cvecs;
+    const int x2 = static_cast<int>(w % W2);
+    w /= W2;
+    const int y2 = static_cast<int>(w % H2);
+    const int n = static_cast<int>(w / H2);
+    const int c = cv << 3;
+    float amax[2][8];
+    float av[2][4][8];
+    const int reps = p.diff ? 2 : 1;
+    const bool full = (2 * y2 + 1 < p.H) && (2 * x2 + 1 < p.W);
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      if (rep >= reps) break;
+      const int nn = n + rep * n_units;
+      const int g = nn / per_group;
+      float sc[8], sh[8];
+      load8f(p.scale + g * p.C + c, sc);
+      load8f(p.shift + g * p.C + c, sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) amax[rep][j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+        if (y < p.H && x < p.W) {
+          const long long pix = (static_cast<long long>(nn) * p.H + y) * p.W + x;
+          float rv[8];
+          unpack8(ldg16(p.r + pix * p.ld_r + c), rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v = fmaxf(fmaf(rv[j], sc[j], sh[j]), 0.f);
+            av[rep][k][j] = v;
+            amax[rep][j] = fmaxf(amax[rep][j], v);
+          }
+          const uint4 o = pack8(av[rep][k]);
+          if (p.a) *reinterpret_cast<uint4*>(p.a + pix * p.ld_a + c) = o;
+          if (p.a2) *reinterpret_cast<uint4*>(p.a2 + pix * p.ld_a2 + c) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) av[rep][k][j] = 0.f;
+        }
+      }
+      if (p.pool && full) {
+        const long long ppix = (static_cast<long long>(nn) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
+        *reinterpret_cast<uint4*>(p.pool + ppix * p.ld_p + c) = pack8(amax[rep]);
+      }
+    }
+    if (p.diff && p.dif) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+        if (y < p.H && x < p.W) {
+          const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+          float d[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = av[1][k][j] - av[0][k][j];
+          *reinterpret_cast<uint4*>(p.dif + pix * p.ld_d + c) = pack8(d);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward. dy = (sum of gradient sources) * [y > 0]; pass 1 reduces (sum dy, sum dy*xhat) per
+// (stat-group, channel); pass 2 writes dr = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)).
+// Gradient sources are gathered on the fly (skip connections with sign, max-pool routing, 1x1 head).
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const __nv_bfloat16* r;
+  long long ld_r;
+  const float *mean, *invstd, *scale, *shift;  // per (group, channel); scale = gamma*invstd, shift = beta - mean*scale
+  GradSrcs srcs;
+  int n_img, H, W, C, G;
+};
+
+// dy for the 4 pixels of window (n, y2, x2), channels c..c+7; xhat returned as well.
+__device__ __forceinline__ void window_dy(const BwdArgs& p, int n, int y2, int x2, int c, int g, float (&dy)[4][8],
+                                          float (&xh)[4][8], bool (&valid)[4]) {
+  float mu[8], is[8], sc[8], sh[8];
+  load8f(p.mean + g * p.C + c, mu);
+  load8f(p.invstd + g * p.C + c, is);
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
+  float aq[4][8];
+  bool pos[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+    valid[k] = (y < p.H) && (x < p.W);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dy[k][j] = 0.f;
+      xh[k][j] = 0.f;
+      aq[k][j] = 0.f;
+      pos[k][j] = false;
+    }
+    if (valid[k]) {
+      const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      float rv[8];
+      unpack8(ldg16(p.r + pix * p.ld_r + c), rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[k][j] = (rv[j] - mu[j]) * is[j];
+        // bit-identical to the forward apply kernel: same (scale, shift) arrays, same fma
+        const float yv = fmaf(rv[j], sc[j], sh[j]);
+        pos[k][j] = yv > 0.f;
+        aq[k][j] = round_bf16(fmaxf(yv, 0.f));
+      }
+    }
+  }
+#pragma unroll
+  for (int si = 0; si < 3; ++si) {
+    const GradSrc& s = p.srcs.s[si];
+    if (s.kind == 0) continue;
+    int ns = n;
+    float scale = 1.f;
+    if (s.n_mod > 0) {
+      scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
+      ns = n % s.n_mod;
+    }
+    if (s.kind == 1) {
+      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!valid[k]) continue;
+        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+        const long long pix = (static_cast<long long>(ns) * p.H + y) * p.W + x;
+        float gv[8];
+        unpack8(ldg16(gp + pix * s.ld + c), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[k][j] = fmaf(scale, gv[j], dy[k][j]);
+      }
+    } else if (s.kind == 2) {
+      if (valid[3]) {  // complete window only (MaxPool2d floors)
+        const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
+        const long long ppix = (static_cast<long long>(ns) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
+        float gv[8];
+        unpack8(ldg16(gp + ppix * s.ld + c), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // first maximum in row-major order, as ATen's max_pool2d_with_indices
+          int arg = 0;
+          float best = aq[0][j];
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (aq[k][j] > best) {
+              best = aq[k][j];
+              arg = k;
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k == arg) dy[k][j] = fmaf(scale, gv[j], dy[k][j]);
+        }
+      }
+    } else {
+      const float* dz = reinterpret_cast<const float*>(s.ptr);
+      float wv[8];
+      load8f(s.w + c, wv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!valid[k]) continue;
+        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+        const long long pix = (static_cast<long long>(ns) * p.H + y) * p.W + x;
+        const float d = scale * __ldg(dz + pix);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[k][j] = fmaf(d, wv[j], dy[k][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dy[k][j] = pos[k][j] ? dy[k][j] : 0.f;
+}
+
+// grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) window lanes
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
+  extern __shared__ float shred[];  // [lanes][C][2]
+  const int cvecs = p.C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int g = blockIdx.y;
+  const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+  const int per_group = p.n_img / p.G;
+  const long long wins = static_cast<long long>(per_group) * H2 * W2;
+  const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int c = cv << 3;
+  for (long long w = wb + l; w < we; w += lanes) {
+    const int x2 = static_cast<int>(w % W2);
+    const int y2 = static_cast<int>((w / W2) % H2);
+    const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
+    float dy[4][8], xh[4][8];
+    bool valid[4];
+    window_dy(p, n, y2, x2, c, g, dy, xh, valid);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += dy[k][j];
+        s2[j] = fmaf(dy[k][j], xh[k][j], s2[j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    shred[(l * p.C + c + j) * 2] = s1[j];
+    shred[(l * p.C + c + j) * 2 + 1] = s2[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < p.C; ch += 256) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < lanes; ++i) {
+      a += shred[(i * p.C + ch) * 2];
+      b += shred[(i * p.C + ch) * 2 + 1];
+    }
+    float* o = partial + ((static_cast<long long>(g) * gridDim.x + blockIdx.x) * p.C + ch) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int G, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ mdy,
+                                       float* __restrict__ mdyx) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double tg = 0.0, tb = 0.0;
+  for (int g = 0; g < G; ++g) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblk; ++i) {
+      const float* o = partial + ((static_cast<long long>(g) * nblk + i) * C + c) * 2;
+      a += o[0];
+      b += o[1];
+    }
+    mdy[g * C + c] = static_cast<float>(a / count);
+    mdyx[g * C + c] = static_cast<float>(b / count);
+    tb += a;
+    tg += b;
+  }
+  dgamma[c] = static_cast<float>(tg);
+  dbeta[c] = static_cast<float>(tb);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ mdy,
+                                                        const float* __restrict__ mdyx, __nv_bfloat16* __restrict__ dr,
+                                                        long long ld_dr) {
+  const int cvecs = p.C >> 3;
+  const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+  const long long total = static_cast<long long>(p.n_img) * H2 * W2 * cvecs;
+  const int per_group = p.n_img / p.G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvecs);
+    long long w = i / cvecs;
+    const int x2 = static_cast<int>(w % W2);
+    w /= W2;
+    const int y2 = static_cast<int>(w % H2);
+    const int n = static_cast<int>(w / H2);
+    const int g = n / per_group;
+    const int c = cv << 3;
+    float dy[4][8], xh[4][8];
+    bool valid[4];
+    window_dy(p, n, y2, x2, c, g, dy, xh, valid);
+    float m1[8], m2[8], sc[8];
+    load8f(mdy + g * p.C + c, m1);
+    load8f(mdyx + g * p.C + c, m2);
+    load8f(p.scale + g * p.C + c, sc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+      const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dy[k][j] - m1[j] - xh[k][j] * m2[j]);
+      *reinterpret_cast<uint4*>(dr + pix * ld_dr + c) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 head (OutConv, C -> 1) over one or two 64..128-channel inputs; 8 lanes per pixel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ a0, long long ld0,
+                                                       const __nv_bfloat16* __restrict__ a1, long long ld1, int C,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       long long npix, float* __restrict__ logits) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long pix = gid >> 3;
+  const int sub = static_cast<int>(gid & 7);
+  float acc = 0.f;
+  if (pix < npix) {
+    for (int c = sub * 8; c < C; c += 64) {
+      float av[8], wv[8];
+      unpack8(ldg16(a0 + pix * ld0 + c), av);
+      load8f(w + c, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(av[j], wv[j], acc);
+    }
+    if (a1 != nullptr) {
+      for (int c = sub * 8; c < C; c += 64) {
+        float av[8], wv[8];
+        unpack8(ldg16(a1 + pix * ld1 + c), av);
+        load8f(w + C + c, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(av[j], wv[j], acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (sub == 0 && pix < npix) logits[pix] = acc + __ldg(b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weighted column sums out[c] = sum_pixels wgt[pixel] * x[pixel, c]  (x bf16 or absent):
+//   transposed-conv bias gradient (wgt = null), head weight gradient (wgt = dz), head bias gradient
+//   (x = null, C = 1). Two-stage: partial[nblk][C] then fixed-order finalize.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int C,
+                                                     const float* __restrict__ wgt, long long npix,
+                                                     float* __restrict__ partial) {
+  extern __shared__ float shred[];
+  const long long pb = npix * blockIdx.x / gridDim.x, pe = npix * (blockIdx.x + 1) / gridDim.x;
+  if (x == nullptr) {
+    float s = 0.f;
+    for (long long i = pb + threadIdx.x; i < pe; i += 256) s += __ldg(wgt + i);
+    shred[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) shred[threadIdx.x] += shred[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = shred[0];
+    return;
+  }
+  const int cvecs = C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs, l = threadIdx.x / cvecs;
+  const int c = cv << 3;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (l < lanes) {
+    for (long long i = pb + l; i < pe; i += lanes) {
+      float v[8];
+      unpack8(ldg16(x + i * ld + c), v);
+      const float wg = wgt ? __ldg(wgt + i) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = fmaf(wg, v[j], s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) shred[l * C + c + j] = s[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += 256) {
+    float a = 0.f;
+    for (int i = 0; i < lanes; ++i) a += shred[i * C + ch];
+    partial[static_cast<long long>(blockIdx.x) * C + ch] = a;
+  }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0;
+  for (int i = 0; i < nblk; ++i) a += partial[static_cast<long long>(i) * C + c];
+  out[c] = static_cast<float>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split reduction of the weight-gradient workspace into the reference parameter layouts.
+//   layout 0: ws[s][tap][d0][d1]          -> grad[d0][d1][tap]   (conv3x3: [co][ci][3][3]; convT: [ci][co][2][2])
+//   layout 1: ws[s][d0][ld1 >= taps*d1], k = tap*d1 + i -> grad[d0][d1][tap]  (first layer; split_stride = d0*ld1)
+// ------------------------------------------------------------------------------------------------
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int layout,
+                                    int d0, int d1, int taps, float* __restrict__ grad, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i enumerates the workspace order (coalesced reads); writes are the strided side
+  long long src, dst;
+  if (layout == 0) {
+    const int b = static_cast<int>(i % d1);
+    const int a = static_cast<int>((i / d1) % d0);
+    const int tap = static_cast<int>(i / (static_cast<long long>(d1) * d0));
+    src = i;
+    dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
+  } else {
+    const int k = static_cast<int>(i % (taps * d1));
+    const int a = static_cast<int>(i / (taps * d1));
+    const int tap = k / d1, b = k - tap * d1;
+    const long long ld1 = split_stride / d0;
+    src = static_cast<long long>(a) * ld1 + k;
+    dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
+  }
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += ws[static_cast<long long>(s) * split_stride + src];
+  grad[dst] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Power-Jaccard loss (utils/loss_functions.py:141-150): p = sigmoid(z); I = sum p*t;
+// D = sum p^2 + sum t^2 - I + 1e-6; L = 1 - I/D, over all selected batch rows at once.
+// The target may itself be a logit (MMCR consistency term, train_semisupervised.py:75-105) and then
+// receives a gradient too. sums = (I, sum p^2, sum t^2) in fp64 so that a data-parallel run can
+// all-reduce them between the forward and backward kernels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + __expf(-z)); }
+
+__global__ void __launch_bounds__(256) pj_reduce_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                        int t_is_logit, const unsigned char* __restrict__ rowmask,
+                                                        int sel, int rows, long long per_row,
+                                                        double* __restrict__ partial) {
+  __shared__ float sh[3][256];
+  const long long total = static_cast<long long>(rows) * per_row;
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    const int row = static_cast<int>(i / per_row);
+    if (rowmask != nullptr && (rowmask[row] != 0) != (sel != 0)) continue;
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(z + i));
+    const float4 tv = __ldg(reinterpret_cast<const float4*>(t + i));
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float pp = sigmoidf_(zz[j]);
+      const float tg = t_is_logit ? sigmoidf_(tt[j]) : tt[j];
+      a = fmaf(pp, tg, a);
+      b = fmaf(pp, pp, b);
+      c = fmaf(tg, tg, c);
+    }
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  sh[2][threadIdx.x] = c;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+      sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x * 3 + 0] = sh[0][0];
+    partial[blockIdx.x * 3 + 1] = sh[1][0];
+    partial[blockIdx.x * 3 + 2] = sh[2][0];
+  }
+}
+
+__global__ void pj_finalize_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ sums) {
+  if (threadIdx.x < 3) {
+    double a = 0.0;
+    for (int i = 0; i < nblk; ++i) a += partial[i * 3 + threadIdx.x];
+    sums[threadIdx.x] = a;
+  }
+}
+
+__global__ void pj_loss_kernel(const double* __restrict__ sums, float* __restrict__ loss) {
+  const double I = sums[0];
+  const double D = sums[1] + sums[2] - I + 1e-6;
+  *loss = static_cast<float>(1.0 - I / D);
+}
+
+__global__ void __launch_bounds__(256) pj_bwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                     int t_is_logit, const unsigned char* __restrict__ rowmask, int sel,
+                                                     int rows, long long per_row, const double* __restrict__ sums,
+                                                     const float* __restrict__ gptr, float gmul, int accumulate,
+                                                     float* __restrict__ dz, float* __restrict__ dt) {
+  const long long total = static_cast<long long>(rows) * per_row;
+  const float I = static_cast<float>(sums[0]);
+  const float D = static_cast<float>(sums[1] + sums[2] - sums[0] + 1e-6);
+  const float g = gmul * (gptr ? __ldg(gptr) : 1.f);
+  const float invD2 = g / (D * D);
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    const int row = static_cast<int>(i / per_row);
+    const bool on = !(rowmask != nullptr && (rowmask[row] != 0) != (sel != 0));
+    float4 oz = make_float4(0.f, 0.f, 0.f, 0.f), ot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      const float4 zv = __ldg(reinterpret_cast<const float4*>(z + i));
+      const float4 tv = __ldg(reinterpret_cast<const float4*>(t + i));
+      const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+      const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+      float rz[4], rt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pp = sigmoidf_(zz[j]);
+        const float tg = t_is_logit ? sigmoidf_(tt[j]) : tt[j];
+        // dL/dp = -(t*D - I*(2p - t)) / D^2 ; dL/dt = -(p*D - I*(2t - p)) / D^2
+        rz[j] = -(tg * D - I * (2.f * pp - tg)) * invD2 * pp * (1.f - pp);
+        rt[j] = -(pp * D - I * (2.f * tg - pp)) * invD2 * (t_is_logit ? tg * (1.f - tg) : 1.f);
+      }
+      oz = make_float4(rz[0], rz[1], rz[2], rz[3]);
+      ot = make_float4(rt[0], rt[1], rt[2], rt[3]);
+    }
+    if (accumulate) {
+      if (on) {
+        float4* pz = reinterpret_cast<float4*>(dz + i);
+        float4 c = *pz;
+        c.x += oz.x; c.y += oz.y; c.z += oz.z; c.w += oz.w;
+        *pz = c;
+        if (dt != nullptr) {
+          float4* pt = reinterpret_cast<float4*>(dt + i);
+          float4 d = *pt;
+          d.x += ot.x; d.y += ot.y; d.z += ot.z; d.w += ot.w;
+          *pt = d;
+        }
+      }
+    } else {
+      *reinterpret_cast<float4*>(dz + i) = oz;
+      if (dt != nullptr) *reinterpret_cast<float4*>(dt + i) = ot;
+    }
+  }
+}
+
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B,
+                              int H, int W, int kpad, void* out, cudaStream_t st) {
+  const int n_img = cat_mode ? B : 2 * B;
+  const long long npix = static_cast<long long>(n_img) * H * W;
+  const int grid = static_cast<int>((npix + 127) / 128);
+  const size_t smem = 128 * (kpad / 2 + 1) * 4;
+  pack_input_kernel<<<grid, 128, smem, st>>>(src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad,
+                                             reinterpret_cast<__nv_bfloat16*>(out), npix);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, cudaStream_t st) {
+  long long total;
+  if (mode == 0 || mode == 1) total = 9ll * d0 * d1;
+  else if (mode == 2) total = static_cast<long long>(d0) * kpad;
+  else total = 4ll * d0 * d1;
+  pack_weights_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(
+      mode, w, reinterpret_cast<__nv_bfloat16*>(out), d0, d1, kpad, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
+                                   double* partial2, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, G, spl);
+  bn_stats_reduce_kernel<<<grid, 256, 0, st>>>(partial, ld, C, tiles_per_group, spl, partial2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, double count, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, long long* nbt,
+                               float momentum, float eps, int train, int order_rev, float* mean, float* invstd,
+                               float* scale, float* shift, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial2, spl, C, G, count, gamma, beta, running_mean,
+                                                      running_var, nbt, momentum, eps, train, order_rev, mean, invstd,
+                                                      scale, shift);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
+                            int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
+                            void* pool, long long ld_p, void* dif, long long ld_d, cudaStream_t st) {
+  ApplyArgs p;
+  p.r = reinterpret_cast<const __nv_bfloat16*>(r);
+  p.ld_r = ld_r;
+  p.scale = scale;
+  p.shift = shift;
+  p.n_img = n_img; p.H = H; p.W = W; p.C = C; p.G = G; p.diff = diff;
+  p.a = reinterpret_cast<__nv_bfloat16*>(a);
+  p.a2 = reinterpret_cast<__nv_bfloat16*>(a2);
+  p.pool = reinterpret_cast<__nv_bfloat16*>(pool);
+  p.dif = reinterpret_cast<__nv_bfloat16*>(dif);
+  p.ld_a = ld_a; p.ld_a2 = ld_a2; p.ld_p = ld_p; p.ld_d = ld_d;
+  const long long total = static_cast<long long>(diff ? n_img / 2 : n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+static BwdArgs make_bwd_args(const void* r, long long ld_r, const float* mean, const float* invstd, const float* scale,
+                             const float* shift, const GradSrcs& srcs, int n_img, int H, int W, int C, int G) {
+  BwdArgs p;
+  p.r = reinterpret_cast<const __nv_bfloat16*>(r);
+  p.ld_r = ld_r;
+  p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift;
+  p.srcs = srcs;
+  p.n_img = n_img; p.H = H; p.W = W; p.C = C; p.G = G;
+  return p;
+}
+
+cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* mean, const float* invstd,
+                                 const float* scale, const float* shift, const GradSrcs& srcs, int n_img, int H, int W,
+                                 int C, int G, int nblk, float* partial, cudaStream_t st) {
+  const BwdArgs p = make_bwd_args(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G);
+  const int lanes = 256 / (C / 8);
+  const size_t smem = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
+  dim3 grid(nblk, G);
+  bn_bwd_reduce_kernel<<<grid, 256, smem, st>>>(p, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, float* dgamma,
+                                   float* dbeta, float* mdy, float* mdyx, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, G, count, dgamma, dbeta, mdy, mdyx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* mean, const float* invstd,
+                             const float* scale, const float* shift, const float* mdy, const float* mdyx,
+                             const GradSrcs& srcs, int n_img, int H, int W, int C, int G, void* dr, long long ld_dr,
+                             cudaStream_t st) {
+  const BwdArgs p = make_bwd_args(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G);
+  const long long total = static_cast<long long>(n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  bn_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, mdy, mdyx, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
+                            const float* b, long long npix, float* logits, cudaStream_t st) {
+  const long long threads = npix * 8;
+  head_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a0), ld0, reinterpret_cast<const __nv_bfloat16*>(a1), ld1, C, w, b, npix,
+      logits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,
+                          float* partial, cudaStream_t st) {
+  size_t smem = 256 * sizeof(float);
+  if (x != nullptr) smem = static_cast<size_t>(256 / (C / 8)) * C * sizeof(float);
+  colsum_kernel<<<nblk, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, C, wgt, npix, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float* out, cudaStream_t st) {
+  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_reduce(const float* ws, int splits, long long split_stride, int layout, int d0, int d1,
+                                int taps, float* grad, cudaStream_t st) {
+  const long long total = static_cast<long long>(d0) * d1 * taps;
+  wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
+                                                                             taps, grad, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pj_reduce(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel,
+                             int rows, long long per_row, int nblk, double* partial, cudaStream_t st) {
+  pj_reduce_kernel<<<nblk, 256, 0, st>>>(z, t, t_is_logit, rowmask, sel, rows, per_row, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pj_finalize(const double* partial, int nblk, double* sums, cudaStream_t st) {
+  pj_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, sums);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pj_loss(const double* sums, float* loss, cudaStream_t st) {
+  pj_loss_kernel<<<1, 1, 0, st>>>(sums, loss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel,
+                          int rows, long long per_row, const double* sums, const float* gptr, float gmul,
+                          int accumulate, float* dz, float* dt, cudaStream_t st) {
+  const long long total = static_cast<long long>(rows) * per_row;
+  pj_bwd_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr,
+                                                          gmul, accumulate, dz, dt);
+  return cudaGetLastError();
+}
+
+}  // namespace b200cd

@@ -1,0 +1,263 @@
+// G1 — implicit-GEMM convolution on tcgen05 / TMEM, fed by TMA (sm_100a only).
+//
+// One CTA computes a 128-pixel x BN-channel output tile. The pixel tile is a tw x th rectangle of one
+// image, so the A operand of every filter tap is ONE TMA box load from the NHWC activation tensor at
+// a shifted coordinate; zero padding is the TMA out-of-bounds fill. The box lands in shared memory as
+// 128 rows of 128 bytes with the 128-byte swizzle = the canonical K-major UMMA operand, no im2col.
+// K loop = taps x (channels / 64); accumulators live in TMEM; the epilogue adds the bias, rounds to
+// bf16, stages the tile in (swizzled) shared memory, reduces the BatchNorm partial statistics of the
+// rounded values and stores the tile with TMA.
+//
+// Replaces (reference): nn.Conv2d(.,.,3,padding=1) utils/networks.py:392,395 (forward and, with
+// flipped/transposed weights, its input gradient), nn.ConvTranspose2d(c,c,2,stride=2)
+// utils/networks.py:433 (forward: out_mode 1; input gradient: mode 2).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200cd {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN, int STAGES>
+struct FpropSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kTmemSlotOff = kBarOff + 8 * (2 * STAGES + 1);
+  static constexpr int kBiasOff = kTmemSlotOff + 16;
+  static constexpr int kRedOff = kBiasOff + BN * 4;
+  static constexpr int kTotal = kRedOff + 4 * BN * 2 * 4;
+  static constexpr int kDynamic = kTotal + 1024;  // slack for the manual 1024-byte alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                         const __grid_constant__ CUtensorMap mapB,
+                                                         const __grid_constant__ CUtensorMap mapO,
+                                                         const FpropParams p) {
+  using L = FpropSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accbar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOff);
+  float* red = reinterpret_cast<float*>(smem + L::kRedOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const int tx = tile % p.tiles_x;
+  const int ty = (tile / p.tiles_x) % p.tiles_y;
+  const int img = tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.tw, y0 = ty * p.th;
+  const int iters = p.taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapO);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64) {
+    const int t = threadIdx.x - 64;
+    if (t < BN) {
+      float b = 0.f;
+      if (p.bias) b = p.bias[p.out_mode == 1 ? (n0 + t) % p.cout : (n0 + t)];
+      bias_s[t] = b;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err, DEV_ERR_EMPTY_TIMEOUT);
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        const int tap = it / p.kchunks;
+        const int kc = it - tap * p.kchunks;
+        mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+        if (p.mode == 0) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, img, 0);
+        } else if (p.mode == 1) {
+          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0, y0, img, 0);
+        } else {
+          const int dy = tap >> 1, dx = tap & 1;
+          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, dx, x0, dy, img * p.H + y0);
+        }
+        tma_load_2d(b_dst, &mapB, &full[s], tap * p.ka + kc * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row: +2 in the >>4 address field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accbar);
+    }
+  } else {
+    // ---------------- epilogue (128 threads) ----------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // row of the tile = pixel (m / tw, m % tw)
+    uint8_t* stg = smem;          // staging aliases stage 0: slab 0 = its A region, slab 1 = its B region
+    mbar_wait(accbar, 0, p.err, DEV_ERR_ACC_TIMEOUT);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c32 = 0; c32 < BN / 32; ++c32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c32 * 32, v);
+      tmem_ld_wait();
+      const int slab = (c32 * 32) >> 6;
+      const int chunk0 = ((c32 * 32) & 63) >> 3;
+      uint8_t* row = stg + slab * kABytes + m * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[cc * 8 + j]) + bias_s[c32 * 32 + cc * 8 + j];
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        const int phys = (chunk0 + cc) ^ (m & 7);
+        *reinterpret_cast<uint4*>(row + phys * 16) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    named_barrier_sync(1, 128);
+
+    const int t = threadIdx.x - 64;
+    if (t == 0) {
+#pragma unroll
+      for (int slab = 0; slab < BN / 64; ++slab) {
+        const int n = n0 + slab * 64;
+        if (p.out_mode == 0) {
+          tma_store_5d(&mapO, stg + slab * kABytes, n, x0, y0, img, 0);
+        } else {
+          const int tap = n / p.cout, co = n - tap * p.cout;
+          tma_store_5d(&mapO, stg + slab * kABytes, co, tap & 1, x0, tap >> 1, img * p.H + y0);
+        }
+      }
+      tma_store_commit();
+    }
+
+    if (p.stats != nullptr) {
+      // per-channel partial sums over the 128 staged (bf16-rounded) rows; conflict-free swizzled reads
+      const int cp = t & 31;  // channel pair inside a 64-channel slab
+      const int rq = t >> 5;  // row quarter
+#pragma unroll
+      for (int slab = 0; slab < BN / 64; ++slab) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int r = rq * 32; r < rq * 32 + 32; ++r) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + slab * kABytes + r * 128 +
+                                                                (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+          float lo = bf16_lo(w), hi = bf16_hi(w);
+          if (p.ragged) {
+            const bool ok = (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
+            lo = ok ? lo : 0.f;
+            hi = ok ? hi : 0.f;
+          }
+          s0 += lo;
+          q0 += lo * lo;
+          s1 += hi;
+          q1 += hi * hi;
+        }
+        float* dst = red + ((rq * BN) + slab * 64 + 2 * cp) * 2;
+        dst[0] = s0;
+        dst[1] = q0;
+        dst[2] = s1;
+        dst[3] = q1;
+      }
+      named_barrier_sync(2, 128);
+      if (t < BN) {
+        float s = 0.f, qq = 0.f;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          s += red[((r4 * BN) + t) * 2];
+          qq += red[((r4 * BN) + t) * 2 + 1];
+        }
+        p.stats[static_cast<size_t>(tile) * p.N + n0 + t] = make_float2(s, qq);
+      }
+    }
+    if (t == 0) tma_store_wait_read0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int STAGES>
+cudaError_t launch_one(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
+                       const FpropParams& p, int num_tiles, cudaStream_t stream) {
+  using L = FpropSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kDynamic);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(num_tiles, p.N / BN, 1);
+  fprop_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, stream>>>(mapA, mapB, mapO, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
+                         const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
+  // 3 stages of (16 KB A + BN*128 B) keep two CTAs resident per SM, so one CTA's epilogue overlaps the
+  // other's main loop.
+  if (bn == 128) return launch_one<128, 3>(mapA, mapB, mapO, p, num_tiles, stream);
+  if (bn == 64) return launch_one<64, 4>(mapA, mapB, mapO, p, num_tiles, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b200cd

@@ -1,0 +1,236 @@
+// G2 — weight-gradient GEMM on tcgen05 / TMEM (sm_100a only).
+//
+// dW_tap[m, n] = sum over pixels of U[pixel, m] * V_tap[pixel, n].  The reduction dimension is the pixel
+// index, and in NHWC memory the channel index is the contiguous one, so both operands are "MN-major":
+// a TMA box of 64 pixels x 64 channels lands in shared memory as 64 rows of 128 bytes (128-byte swizzle)
+// and is consumed as-is by tcgen05.mma with the MN-major bits set in the instruction descriptor.
+// One CTA owns a 128 x BN block of the weight gradient for a group of taps (one accumulator per tap in
+// TMEM) and a contiguous range of 8x8 pixel tiles (split over the pixel dimension); per-split results go
+// to a workspace that wgrad_reduce sums in a fixed order (deterministic, no float atomics).
+//
+// For 3x3 convolutions a CTA handles the three ky taps of one kx. With HALO the shifted operand is
+// loaded once per pixel tile as an 8 x 10 box (one halo row above and below); since a shift by one image
+// row is a shift by 8 shared-memory rows = one 1024-byte swizzle atom, the three ky operands are plain
+// address offsets into that box.
+//
+// Replaces (reference): the weight gradients autograd computes for nn.Conv2d utils/networks.py:392,395
+// and nn.ConvTranspose2d utils/networks.py:433.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200cd {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kUBytes = 2 * 64 * 128;  // 64 pixels x 128 channels (two 64-channel slabs)
+
+template <int BN, int MODE, bool HALO>
+struct WgradCfg {
+  static constexpr int kTaps = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+  static constexpr int kVRows = HALO ? 80 : 64;
+  static constexpr int kVSlab = kVRows * 128;
+  static constexpr int kVTiles = HALO ? 1 : kTaps;  // separately loaded tap tiles
+  static constexpr int kVBytes = kVTiles * (BN / 64) * kVSlab;
+  static constexpr int kStageBytes = kUBytes + kVBytes;
+  static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kCols = kTaps * BN;
+  static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTmemSlotOff = kBarOff + 8 * (2 * kStages + 1);
+  static constexpr int kTotal = kTmemSlotOff + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+  static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert(kCols <= 512, "accumulators exceed TMEM");
+};
+
+template <int BN, int MODE, bool HALO>
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ CUtensorMap mapU,
+                                                         const __grid_constant__ CUtensorMap mapV,
+                                                         const WgradParams p) {
+  using C = WgradCfg<BN, MODE, HALO>;
+  constexpr int STAGES = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accbar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kTmemSlotOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int split = blockIdx.z % p.splits;
+  const int kx = blockIdx.z / p.splits;  // mode 0 only (0..2)
+  const int t_begin = static_cast<int>(static_cast<long long>(p.total_tiles) * split / p.splits);
+  const int t_end = static_cast<int>(static_cast<long long>(p.total_tiles) * (split + 1) / p.splits);
+  const int iters = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapU);
+    tma_prefetch_desc(&mapV);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err, DEV_ERR_EMPTY_TIMEOUT);
+        const int tile = t_begin + it;
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int img = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * 8, y0 = ty * 8;
+        uint8_t* u_dst = smem + s * C::kStageBytes;
+        uint8_t* v_dst = u_dst + kUBytes;
+        mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+#pragma unroll
+        for (int slab = 0; slab < 2; ++slab)
+          tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
+        if (MODE == 0) {
+          const int sx = p.sign * (kx - 1);
+          if (HALO) {
+#pragma unroll
+            for (int slab = 0; slab < BN / 64; ++slab)
+              tma_load_5d(v_dst + slab * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx, y0 - 1, img, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int slab = 0; slab < BN / 64; ++slab)
+                tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx,
+                            y0 + j - 1, img, 0);
+          }
+        } else if (MODE == 1) {
+#pragma unroll
+          for (int slab = 0; slab < BN / 64; ++slab)
+            tma_load_5d(v_dst + slab * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0, y0, img, 0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int slab = 0; slab < BN / 64; ++slab)
+              tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, j & 1, x0,
+                          j >> 1, img * p.H + y0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
+        tc_fence_after();
+        const uint32_t u_addr = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t v_addr = u_addr + kUBytes;
+#pragma unroll
+        for (int j = 0; j < C::kTaps; ++j) {
+          // HALO: tap j = rows [8j, 8j+64) of the 80-row box (whole 1024-byte swizzle atoms)
+          const uint32_t vj = HALO ? v_addr + j * 1024 : v_addr + j * (BN / 64) * C::kVSlab;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // 16 pixels (K) per MMA = 16 rows of 128 bytes
+            const uint64_t adesc = make_smem_desc(u_addr + k * 2048, 8192, 1024);
+            const uint64_t bdesc = make_smem_desc(vj + k * 2048, C::kVSlab, 1024);
+            umma_bf16(tmem_base + j * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accbar);
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> fp32 workspace ----------------
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(accbar, 0, p.err, DEV_ERR_ACC_TIMEOUT);
+    tc_fence_after();
+    float* base = p.ws + static_cast<long long>(split) * p.split_stride;
+#pragma unroll 1
+    for (int j = 0; j < C::kTaps; ++j) {
+      int tap = j;
+      if (MODE == 0) tap = (p.sign > 0 ? j : 2 - j) * 3 + kx;
+      float* tbase = base + tap * p.tap_stride + static_cast<long long>(m) * p.m_stride;
+#pragma unroll 1
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN + c32 * 32, v);
+        tmem_ld_wait();
+        if (m < p.cu) {
+          if (p.n_stride == 1) {
+            float4* dst = reinterpret_cast<float4*>(tbase + n0 + c32 * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tbase[static_cast<long long>(n0 + c32 * 32 + i) * p.n_stride] = __uint_as_float(v[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BN, int MODE, bool HALO>
+cudaError_t launch_one(const CUtensorMap& mapU, const CUtensorMap& mapV, const WgradParams& p, cudaStream_t stream) {
+  using C = WgradCfg<BN, MODE, HALO>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kDynamic);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p.cu + 127) / 128, p.cv / BN, (MODE == 0 ? 3 : 1) * p.splits);
+  wgrad_kernel<BN, MODE, HALO><<<grid, kThreads, C::kDynamic, stream>>>(mapU, mapV, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const WgradParams& p, int bn, int halo,
+                         cudaStream_t stream) {
+  if (p.mode == 0) {
+    if (bn == 128) return halo ? launch_one<128, 0, true>(mapU, mapV, p, stream) : launch_one<128, 0, false>(mapU, mapV, p, stream);
+    if (bn == 64) return halo ? launch_one<64, 0, true>(mapU, mapV, p, stream) : launch_one<64, 0, false>(mapU, mapV, p, stream);
+  } else if (p.mode == 1) {
+    if (bn == 128) return launch_one<128, 1, false>(mapU, mapV, p, stream);
+    if (bn == 64) return launch_one<64, 1, false>(mapU, mapV, p, stream);
+  } else if (p.mode == 2) {
+    if (bn == 128) return launch_one<128, 2, false>(mapU, mapV, p, stream);
+    if (bn == 64) return launch_one<64, 2, false>(mapU, mapV, p, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b200cd

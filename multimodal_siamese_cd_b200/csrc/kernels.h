@@ -1,0 +1,101 @@
+// Internal (C++) launch interface between the C-ABI layer (abi.cu) and the kernel translation units.
+// Nothing here is exported; the exported surface is include/b200cd.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200cd {
+
+// ----------------------------------------------------------------------------------------------
+// G1: implicit-GEMM "fprop-like" kernel.  D[pixel, n] = sum_{tap, k} A_tap[pixel, k] * B[n, tap*ka + k]
+//   mode 0: 3x3 same-convolution (9 taps, zero padding through TMA out-of-bounds fill)
+//   mode 1: single tap (plain row GEMM: transposed-conv forward, im2col'ed first layer)
+//   mode 2: 4 taps gathered with stride 2 (transposed-conv input gradient)
+//   out_mode 0: NHWC tile store at the GEMM's own resolution
+//   out_mode 1: 2x2/stride-2 scatter (transposed-conv forward), N = 4*cout, tap = n / cout
+// ----------------------------------------------------------------------------------------------
+struct FpropParams {
+  int mode, out_mode;
+  int taps, kchunks, ka;  // K loop = taps * kchunks chunks of 64 channels; ka = channels per tap
+  int tw, th, tiles_x, tiles_y;
+  int H, W;               // pixel grid of the GEMM rows
+  int N, cout;
+  const float* bias;      // nullable
+  float2* stats;          // nullable: per (tile, n) partial (sum, sum of squares) of the bf16-rounded output
+  int ragged;             // 1 when H % th or W % tw != 0 (mask rows in the statistics)
+  int* err;
+};
+cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
+                         const FpropParams& p, int bn, int num_tiles, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// G2: weight-gradient kernel. D_tap[m, n] = sum_pixels U[pixel, m] * V_tap[pixel, n]
+//   (both operands MN-major straight out of NHWC memory), split over pixel ranges.
+//   mode 0: 3x3 conv (CTA = one kx, three ky taps; V shifted by sign*(kx-1, ky-1))
+//   mode 1: single tap
+//   mode 2: transposed conv (4 taps, V gathered with stride 2 from the full-resolution gradient)
+// ----------------------------------------------------------------------------------------------
+struct WgradParams {
+  int mode, sign;
+  int H, W, tiles_x, tiles_y, total_tiles, splits;
+  int cu, cv;
+  float* ws;
+  long long split_stride, tap_stride, m_stride, n_stride;
+  int* err;
+};
+cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const WgradParams& p, int bn, int halo,
+                         cudaStream_t stream);
+
+// ----------------------------------------------------------------------------------------------
+// Memory-bound kernels (elementwise.cu)
+// ----------------------------------------------------------------------------------------------
+struct GradSrc {
+  int kind;          // 0 none, 1 direct bf16 NHWC, 2 pooled bf16 (half resolution, routed to the arg-max), 3 head (dz*w)
+  const void* ptr;   // bf16 tensor (kinds 1, 2) or fp32 dz[pixel] (kind 3)
+  const float* w;    // kind 3: 1x1 head weights for these channels
+  long long ld;      // elements per pixel
+  int n_mod;         // > 0: source image = n % n_mod, scale = (n < n_mod) ? scale_lo : scale_hi
+  float scale_lo, scale_hi;
+};
+struct GradSrcs {
+  GradSrc s[3];
+};
+
+cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B,
+                              int H, int W, int kpad, void* out, cudaStream_t st);
+cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, cudaStream_t st);
+cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
+                                   double* partial2, cudaStream_t st);
+cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, double count, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var, long long* nbt,
+                               float momentum, float eps, int train, int order_rev, float* mean, float* invstd,
+                               float* scale, float* shift, cudaStream_t st);
+cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
+                            int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
+                            void* pool, long long ld_p, void* dif, long long ld_d, cudaStream_t st);
+cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* mean, const float* invstd,
+                                 const float* scale, const float* shift, const GradSrcs& srcs, int n_img, int H, int W,
+                                 int C, int G, int nblk, float* partial, cudaStream_t st);
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, float* dgamma,
+                                   float* dbeta, float* mdy, float* mdyx, cudaStream_t st);
+cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* mean, const float* invstd,
+                             const float* scale, const float* shift, const float* mdy, const float* mdyx,
+                             const GradSrcs& srcs, int n_img, int H, int W, int C, int G, void* dr, long long ld_dr,
+                             cudaStream_t st);
+cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
+                            const float* b, long long npix, float* logits, cudaStream_t st);
+cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,
+                          float* partial, cudaStream_t st);
+cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float* out, cudaStream_t st);
+cudaError_t launch_wgrad_reduce(const float* ws, int splits, long long split_stride, int layout, int d0, int d1,
+                                int taps, float* grad, cudaStream_t st);
+cudaError_t launch_pj_reduce(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel,
+                             int rows, long long per_row, int nblk, double* partial, cudaStream_t st);
+cudaError_t launch_pj_finalize(const double* partial, int nblk, double* sums, cudaStream_t st);
+cudaError_t launch_pj_loss(const double* sums, float* loss, cudaStream_t st);
+cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel,
+                          int rows, long long per_row, const double* sums, const float* gptr, float gmul,
+                          int accumulate, float* dz, float* dt, cudaStream_t st);
+
+}  // namespace b200cd

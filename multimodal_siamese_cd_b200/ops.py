@@ -1,0 +1,238 @@
+"""Tensor-level wrappers over the C ABI (include/b200cd.h).
+
+Activations are torch bf16 tensors of logical shape [n, H, W, C] whose last dim is contiguous and whose
+pixel stride `ld = t.stride(2)` may exceed C (a channel slice of a concat buffer). These functions only
+extract pointers/strides and launch on torch's current CUDA stream; they never compute on the CPU and
+raise on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GradSrc
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> int:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.B200CDError("b200cd ops run on CUDA tensors only (there is no CPU path)")
+        dev = t.device.index if dev is None else dev
+    if dev is None:
+        raise _lib.B200CDError("no tensor given")
+    _lib.init(dev)
+    return dev
+
+
+def _nhwc(t: torch.Tensor) -> tuple[int, int, int, int, int]:
+    """(n, H, W, C, ld) of an NHWC view."""
+    assert t.dim() == 4 and t.dtype == torch.bfloat16 and t.stride(3) == 1, "expected an NHWC bf16 view"
+    n, H, W, Cc = t.shape
+    ld = t.stride(2)
+    assert t.stride(1) == W * ld and (n == 1 or t.stride(0) == H * W * ld), "pixel stride must be uniform"
+    return n, H, W, Cc, ld
+
+
+def device_status(dev: Optional[int] = None) -> None:
+    """Synchronise and raise if any tensor-core kernel reported a pipeline time-out."""
+    dev = torch.cuda.current_device() if dev is None else dev
+    _lib.init(dev)
+    _lib.device_status(dev, _stream())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def pack_input(x0: torch.Tensor, x1: torch.Tensor, c_lo: int, nc: int, cat_mode: int, kpad: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x0, x1)
+    assert x0.dtype == torch.float32 and x0.is_contiguous() and x1.is_contiguous() and x0.shape == x1.shape
+    B, cs, H, W = x0.shape
+    n_img = B if cat_mode else 2 * B
+    if out is None:
+        out = torch.empty((n_img, H, W, kpad), device=x0.device, dtype=torch.bfloat16)
+    _lib.check(_lib.load().b200cd_pack_input(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad,
+                                             out.data_ptr(), _stream()))
+    return out
+
+
+def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(w)
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    d0, d1 = w.shape[0], w.shape[1]
+    if mode == 0:
+        shape = (d0, 9 * d1)
+    elif mode == 1:
+        shape = (d1, 9 * d0)
+    elif mode == 2:
+        shape = (d0, kpad)
+    elif mode == 3:
+        shape = (4 * d1, d0)
+    else:
+        shape = (d0, 4 * d1)
+    if out is None:
+        out = torch.empty(shape, device=w.device, dtype=torch.bfloat16)
+    assert tuple(out.shape) == shape and out.is_contiguous()
+    _lib.check(_lib.load().b200cd_pack_weights(mode, w.data_ptr(), out.data_ptr(), d0, d1, kpad, _stream()))
+    return out
+
+
+def conv_gemm_tiles(H: int, W: int) -> int:
+    return _lib.load().b200cd_conv_gemm_tiles(H, W)
+
+
+def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
+              bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
+    """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x)."""
+    _require_cuda(A, Bw, out)
+    n, Ha, Wa, ka, a_ld = _nhwc(A)
+    H, W = (Ha // 2, Wa // 2) if mode == 2 else (Ha, Wa)
+    no, Ho, Wo, Co, o_ld = _nhwc(out)
+    N = Bw.shape[0]
+    taps = 9 if mode == 0 else (1 if mode == 1 else 4)
+    assert Bw.dtype == torch.bfloat16 and Bw.is_contiguous() and Bw.shape[1] == taps * ka
+    if out_mode == 1:
+        assert (no, Ho, Wo) == (n, 2 * H, 2 * W) and N == 4 * Co
+        cout = Co
+    else:
+        assert (no, Ho, Wo, Co) == (n, H, W, N)
+        cout = 0
+    _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
+                                            out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
+
+
+def wgrad_tiles(n: int, H: int, W: int) -> int:
+    return _lib.load().b200cd_wgrad_tiles(n, H, W)
+
+
+def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor, ws: torch.Tensor, splits: int,
+               split_stride: int, tap_stride: int, m_stride: int, n_stride: int) -> None:
+    """G2. U: NHWC view at the GEMM resolution; V: NHWC view (mode 2: at 2x)."""
+    _require_cuda(U, V, ws)
+    n, H, W, cu, u_ld = _nhwc(U)
+    nv, Hv, Wv, cv, v_ld = _nhwc(V)
+    assert nv == n and ((Hv, Wv) == (2 * H, 2 * W) if mode == 2 else (Hv, Wv) == (H, W))
+    assert ws.dtype == torch.float32
+    _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
+                                             ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
+                                             _stream()))
+
+
+def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, d0: int, d1: int, taps: int,
+                 grad: torch.Tensor) -> None:
+    _require_cuda(ws, grad)
+    assert grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == d0 * d1 * taps
+    _lib.check(_lib.load().b200cd_wgrad_reduce(ws.data_ptr(), splits, split_stride, layout, d0, d1, taps,
+                                               grad.data_ptr(), _stream()))
+
+
+def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group: int, G: int, count: float, spl: int,
+             ws: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, running_mean: torch.Tensor,
+             running_var: torch.Tensor, nbt: Optional[torch.Tensor], momentum: float, eps: float, train: bool,
+             order_rev: bool, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> None:
+    _require_cuda(gamma, beta, running_mean, running_var, mean)
+    _lib.check(_lib.load().b200cd_bn_stats(_ptr(partial), ld, C_, tiles_per_group, G, float(count), spl, _ptr(ws),
+                                           gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                           running_var.data_ptr(), _ptr(nbt), momentum, eps, int(train), int(order_rev),
+                                           mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                           _stream()))
+
+
+def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, diff: bool,
+             a: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
+             dif: Optional[torch.Tensor] = None) -> None:
+    _require_cuda(r, scale, shift)
+    n, H, W, Cc, ld_r = _nhwc(r)
+
+    def ld(t):
+        return 0 if t is None else _nhwc(t)[4]
+
+    _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
+                                           int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool), _ptr(dif),
+                                           ld(dif), _stream()))
+
+
+def make_srcs(srcs: Sequence[dict]) -> C.Array:
+    """Build the b200cd_grad_src[3] array. Each dict: kind, t (tensor), w (tensor, kind 3), n_mod, scale_lo, scale_hi."""
+    arr = (GradSrc * 3)()
+    assert len(srcs) <= 3
+    for i, s in enumerate(srcs):
+        t = s["t"]
+        arr[i].kind = s["kind"]
+        arr[i].ptr = t.data_ptr()
+        arr[i].w = s["w"].data_ptr() if s.get("w") is not None else None
+        arr[i].ld = t.stride(2) if s["kind"] in (1, 2) else 0
+        arr[i].n_mod = s.get("n_mod", 0)
+        arr[i].scale_lo = s.get("scale_lo", 1.0)
+        arr[i].scale_hi = s.get("scale_hi", 1.0)
+    return arr
+
+
+def bn_bwd_ws_floats(n: int, H: int, W: int, C_: int, G: int) -> int:
+    return _lib.load().b200cd_bn_bwd_ws_floats(n, H, W, C_, G)
+
+
+def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+           srcs: C.Array, G: int, ws: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, dr: torch.Tensor) -> None:
+    _require_cuda(r, dr, ws)
+    n, H, W, Cc, ld_r = _nhwc(r)
+    _lib.check(_lib.load().b200cd_bn_bwd(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                         shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(), dgamma.data_ptr(),
+                                         dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))
+
+
+def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: torch.Tensor,
+             logits: torch.Tensor) -> None:
+    _require_cuda(a0, w, b, logits)
+    n, H, W, Cc, ld0 = _nhwc(a0)
+    ld1 = 0 if a1 is None else _nhwc(a1)[4]
+    _lib.check(_lib.load().b200cd_head_fwd(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(), n * H * W,
+                                           logits.data_ptr(), _stream()))
+
+
+def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nblk: int, ws: torch.Tensor,
+           out: torch.Tensor) -> None:
+    _require_cuda(ws, out)
+    if x is None:
+        Cc, ld = 1, 0
+    else:
+        Cc, ld = x.shape[3], x.stride(2)
+    _lib.check(_lib.load().b200cd_colsum(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(),
+                                         _stream()))
+
+
+def pj_fwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional[torch.Tensor], sel: int, nblk: int,
+           ws: torch.Tensor, sums: torch.Tensor) -> None:
+    _require_cuda(z, t, ws, sums)
+    rows = z.shape[0]
+    per_row = z.numel() // rows
+    _lib.check(_lib.load().b200cd_pj_fwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
+                                         nblk, ws.data_ptr(), sums.data_ptr(), _stream()))
+
+
+def pj_loss(sums: torch.Tensor, loss: torch.Tensor) -> None:
+    _require_cuda(sums, loss)
+    _lib.check(_lib.load().b200cd_pj_loss(sums.data_ptr(), loss.data_ptr(), _stream()))
+
+
+def pj_bwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional[torch.Tensor], sel: int,
+           sums: torch.Tensor, gptr: Optional[torch.Tensor], gmul: float, accumulate: bool, dz: torch.Tensor,
+           dt: Optional[torch.Tensor]) -> None:
+    _require_cuda(z, t, dz)
+    rows = z.shape[0]
+    per_row = z.numel() // rows
+    _lib.check(_lib.load().b200cd_pj_bwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
+                                         sums.data_ptr(), _ptr(gptr), gmul, int(accumulate), dz.data_ptr(), _ptr(dt),
+                                         _stream()))

@@ -1,0 +1,542 @@
+"""Per-kernel parity checks of the CUDA path (through the C ABI) against plain torch fp32 on the same
+bf16-rounded inputs. Imported by tests/test_gpu_ops.py (pytest -m gpu) and tools/gpu_probe.py.
+
+Each check returns a dict of metrics; `ok` says whether the tolerance written next to it was met.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from multimodal_siamese_cd_b200 import ops
+
+DEV = "cuda"
+
+
+def bf16r(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc(x_nchw: torch.Tensor) -> torch.Tensor:
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc: torch.Tensor) -> torch.Tensor:
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+def err(got: torch.Tensor, ref: torch.Tensor) -> dict:
+    got = got.double()
+    ref = ref.double()
+    d = (got - ref)
+    return {
+        "max_abs": d.abs().max().item(),
+        "rel_l2": (d.norm() / ref.norm().clamp_min(1e-30)).item(),
+        "ref_absmax": ref.abs().max().item(),
+        "finite": bool(torch.isfinite(got).all().item()),
+    }
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device=DEV)
+    g.manual_seed(seed)
+    return g
+
+
+# ----------------------------------------------------------------------------------------------------
+def check_pack_weights() -> dict:
+    g = _gen(1)
+    w = torch.randn(128, 64, 3, 3, device=DEV, generator=g)
+    wt = torch.randn(128, 64, 2, 2, device=DEV, generator=g)  # convT: [ci][co][2][2]
+    w1 = torch.randn(64, 6, 3, 3, device=DEV, generator=g)
+    out = {}
+    p0 = ops.pack_weights(0, w)
+    ref0 = w.permute(0, 2, 3, 1).reshape(128, 9 * 64).to(torch.bfloat16)
+    out["m0"] = bool(torch.equal(p0, ref0))
+    p1 = ops.pack_weights(1, w)
+    ref1 = w.flip(2, 3).permute(1, 2, 3, 0).reshape(64, 9 * 128).to(torch.bfloat16)
+    out["m1"] = bool(torch.equal(p1, ref1))
+    p2 = ops.pack_weights(2, w1, kpad=64)
+    ref2 = torch.zeros(64, 64, device=DEV)
+    ref2[:, :54] = w1.permute(0, 2, 3, 1).reshape(64, 54)
+    out["m2"] = bool(torch.equal(p2, ref2.to(torch.bfloat16)))
+    p3 = ops.pack_weights(3, wt)
+    ref3 = wt.permute(2, 3, 1, 0).reshape(4 * 64, 128).to(torch.bfloat16)
+    out["m3"] = bool(torch.equal(p3, ref3))
+    p4 = ops.pack_weights(4, wt)
+    ref4 = wt.permute(0, 2, 3, 1).reshape(128, 4 * 64).to(torch.bfloat16)
+    out["m4"] = bool(torch.equal(p4, ref4))
+    out["ok"] = all(out.values())
+    return out
+
+
+def im2col_ref(x: torch.Tensor, kpad: int) -> torch.Tensor:
+    """x: [n, C, H, W] fp32 -> [n, H, W, kpad] with k = tap*C + c."""
+    n, Cc, H, W = x.shape
+    cols = F.unfold(x, 3, padding=1).view(n, Cc, 9, H, W)  # [n, c, tap, H, W]
+    cols = cols.permute(0, 3, 4, 2, 1).reshape(n, H, W, 9 * Cc)
+    out = torch.zeros(n, H, W, kpad, device=x.device)
+    out[..., : 9 * Cc] = cols
+    return out.to(torch.bfloat16)
+
+
+def check_pack_input() -> dict:
+    g = _gen(2)
+    x1 = torch.rand(2, 6, 24, 40, device=DEV, generator=g)
+    x2 = torch.rand(2, 6, 24, 40, device=DEV, generator=g)
+    out = {}
+    got = ops.pack_input(x1, x2, 2, 4, 0, 64)  # siamese on the S2 bands
+    ref = im2col_ref(torch.cat([x1[:, 2:6], x2[:, 2:6]], 0), 64)
+    out["cat_batch"] = bool(torch.equal(got, ref))
+    got = ops.pack_input(x1, x2, 0, 2, 1, 64)  # early fusion of the S1 bands
+    ref = im2col_ref(torch.cat([x1[:, 0:2], x2[:, 0:2]], 1), 64)
+    out["cat_chan"] = bool(torch.equal(got, ref))
+    got = ops.pack_input(x1, x2, 2, 4, 1, 128)  # 8 channels -> K = 72 -> kpad 128
+    ref = im2col_ref(torch.cat([x1[:, 2:6], x2[:, 2:6]], 1), 128)
+    out["cat_chan8"] = bool(torch.equal(got, ref))
+    out["ok"] = all(out.values())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, slice_out=False, seed=3,
+                  tol=6e-3) -> dict:
+    """conv_gemm mode 0 vs F.conv2d (fp32 math on the bf16-rounded operands); output is bf16 so the bound is
+    one bf16 ulp (2^-8 relative) plus accumulation-order noise."""
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, cin, H, W, device=DEV, generator=g))
+    w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cin ** 0.5))
+    b = torch.randn(cout, device=DEV, generator=g) if bias else None
+    if slice_in:
+        buf = torch.zeros(n, H, W, cin + 64, device=DEV, dtype=torch.bfloat16)
+        A = buf[..., 64:]
+        A.copy_(nhwc(x))
+    else:
+        A = nhwc(x).to(torch.bfloat16)
+    if slice_out:
+        obuf = torch.full((n, H, W, cout + 64), 7.0, device=DEV, dtype=torch.bfloat16)
+        out = obuf[..., :cout]
+    else:
+        obuf = None
+        out = torch.empty(n, H, W, cout, device=DEV, dtype=torch.bfloat16)
+    tiles = ops.conv_gemm_tiles(H, W)
+    stats = torch.zeros(n * tiles, cout, 2, device=DEV)
+    Bw = ops.pack_weights(0, w)
+    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats)
+    ops.device_status()
+    ref = F.conv2d(x, w, b, padding=1)
+    res = err(nchw(out.float()), ref)
+    got_sum = stats[..., 0].sum(0)
+    got_sq = stats[..., 1].sum(0)
+    o32 = out.float()
+    res["stats_sum_rel"] = ((got_sum - o32.sum((0, 1, 2))).norm() / o32.sum((0, 1, 2)).norm().clamp_min(1e-6)).item()
+    res["stats_sq_rel"] = ((got_sq - (o32 * o32).sum((0, 1, 2))).norm() / (o32 * o32).sum((0, 1, 2)).norm()).item()
+    if obuf is not None:
+        res["untouched"] = bool((obuf[..., cout:] == 7.0).all().item())
+    res["ok"] = res["finite"] and res["rel_l2"] < tol and res["stats_sum_rel"] < 1e-3 and res["stats_sq_rel"] < 1e-3 \
+        and res.get("untouched", True)
+    return res
+
+
+def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> dict:
+    g = _gen(seed)
+    w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cout ** 0.5))
+    dr = bf16r(torch.randn(n, cout, H, W, device=DEV, generator=g))
+    Bd = ops.pack_weights(1, w)  # [cin][9*cout]
+    out = torch.empty(n, H, W, cin, device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm(0, 0, nhwc(dr).to(torch.bfloat16), Bd, out)
+    ops.device_status()
+    ref = F.conv_transpose2d(dr, w, padding=1)  # = input gradient of conv2d(x, w, padding=1)
+    res = err(nchw(out.float()), ref)
+    res["ok"] = res["finite"] and res["rel_l2"] < tol
+    return res
+
+
+def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3) -> dict:
+    """ConvTranspose2d(c, c, 2, stride=2) forward, scattered into the second half of a 2c concat buffer."""
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, c, h, w_, device=DEV, generator=g))
+    wt = bf16r(torch.randn(c, c, 2, 2, device=DEV, generator=g) / (c ** 0.5))
+    b = torch.randn(c, device=DEV, generator=g)
+    cat = torch.full((n, 2 * h, 2 * w_, 2 * c), 3.0, device=DEV, dtype=torch.bfloat16)
+    Bw = ops.pack_weights(3, wt)  # [4c][c]
+    ops.conv_gemm(1, 1, nhwc(x).to(torch.bfloat16), Bw, cat[..., c:], bias=b)
+    ops.device_status()
+    ref = F.conv_transpose2d(x, wt, b, stride=2)
+    res = err(nchw(cat[..., c:].float()), ref)
+    res["untouched"] = bool((cat[..., :c] == 3.0).all().item())
+    res["ok"] = res["finite"] and res["rel_l2"] < tol and res["untouched"]
+    return res
+
+
+def check_convt_dgrad(n=2, h=16, w_=16, c=128, seed=6, tol=6e-3) -> dict:
+    g = _gen(seed)
+    wt = bf16r(torch.randn(c, c, 2, 2, device=DEV, generator=g) / (2.0 * c ** 0.5))
+    dcat = torch.zeros(n, 2 * h, 2 * w_, 2 * c, device=DEV, dtype=torch.bfloat16)
+    dout = bf16r(torch.randn(n, c, 2 * h, 2 * w_, device=DEV, generator=g))
+    dcat[..., c:] = nhwc(dout).to(torch.bfloat16)
+    Bd = ops.pack_weights(4, wt)  # [c][4c]
+    out = torch.empty(n, h, w_, c, device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm(2, 0, dcat[..., c:], Bd, out)
+    ops.device_status()
+    ref = F.conv2d(dout, wt, stride=2)  # input gradient of conv_transpose2d(x, wt, stride=2)
+    res = err(nchw(out.float()), ref)
+    res["ok"] = res["finite"] and res["rel_l2"] < tol
+    return res
+
+
+def _splits_for(total: int, want: int) -> int:
+    return max(1, min(total, want))
+
+
+def check_wgrad3x3(n=2, H=32, W=32, cin=64, cout=128, sign=1, halo=0, splits=5, seed=7, tol=2e-3) -> dict:
+    """wgrad_gemm mode 0 + wgrad_reduce vs autograd's weight gradient (fp32 accumulation on both sides)."""
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, cin, H, W, device=DEV, generator=g))
+    dr = bf16r(torch.randn(n, cout, H, W, device=DEV, generator=g))
+    xa = nhwc(x).to(torch.bfloat16)
+    da = nhwc(dr).to(torch.bfloat16)
+    splits = _splits_for(ops.wgrad_tiles(n, H, W), splits)
+    ws = torch.full((splits, 9, cout, cin), float("nan"), device=DEV)
+    if sign == 1:   # M <-> cout (U = dOut), N <-> cin (V = input, shifted)
+        ops.wgrad_gemm(0, 1, halo, da, xa, ws, splits, 9 * cout * cin, cout * cin, cin, 1)
+    else:           # M <-> cin (U = input), N <-> cout (V = dOut, shifted the other way)
+        ops.wgrad_gemm(0, -1, halo, xa, da, ws, splits, 9 * cout * cin, cout * cin, 1, cin)
+    grad = torch.empty(cout, cin, 3, 3, device=DEV)
+    ops.wgrad_reduce(ws, splits, 9 * cout * cin, 0, cout, cin, 9, grad)
+    ops.device_status()
+    ref = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), dr, padding=1)
+    res = err(grad, ref)
+    res["ok"] = res["finite"] and res["rel_l2"] < tol
+    return res
+
+
+def check_wgrad_convt(n=2, h=16, w_=16, c=128, splits=3, seed=8, tol=2e-3) -> dict:
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, c, h, w_, device=DEV, generator=g))
+    dout = bf16r(torch.randn(n, c, 2 * h, 2 * w_, device=DEV, generator=g))
+    dcat = torch.zeros(n, 2 * h, 2 * w_, 2 * c, device=DEV, dtype=torch.bfloat16)
+    dcat[..., c:] = nhwc(dout).to(torch.bfloat16)
+    splits = _splits_for(ops.wgrad_tiles(n, h, w_), splits)
+    ws = torch.full((splits, 4, c, c), float("nan"), device=DEV)  # [s][tap][ci][co]
+    ops.wgrad_gemm(2, 1, 0, nhwc(x).to(torch.bfloat16), dcat[..., c:], ws, splits, 4 * c * c, c * c, c, 1)
+    grad = torch.empty(c, c, 2, 2, device=DEV)
+    ops.wgrad_reduce(ws, splits, 4 * c * c, 0, c, c, 4, grad)
+    ops.device_status()
+    xr = x.clone().requires_grad_(False)
+    wt = torch.zeros(c, c, 2, 2, device=DEV, requires_grad=True)
+    F.conv_transpose2d(xr, wt, stride=2).backward(dout)
+    res = err(grad, wt.grad)
+    res["ok"] = res["finite"] and res["rel_l2"] < tol
+    return res
+
+
+def check_wgrad_first(n=2, H=32, W=32, cin=6, splits=4, seed=9, tol=2e-3) -> dict:
+    """First-layer conv: forward as a 1-tap GEMM over im2col rows, weight gradient with mode 1."""
+    g = _gen(seed)
+    x1 = torch.rand(n, cin, H, W, device=DEV, generator=g)
+    x2 = torch.rand(n, cin, H, W, device=DEV, generator=g)
+    w = bf16r(torch.randn(64, cin, 3, 3, device=DEV, generator=g) / (3.0 * cin ** 0.5))
+    b = torch.randn(64, device=DEV, generator=g)
+    cols = ops.pack_input(x1, x2, 0, cin, 0, 64)  # [2n, H, W, 64]
+    Bw = ops.pack_weights(2, w, kpad=64)
+    out = torch.empty(2 * n, H, W, 64, device=DEV, dtype=torch.bfloat16)
+    ops.conv_gemm(1, 0, cols, Bw, out, bias=b)
+    xcat = bf16r(torch.cat([x1, x2], 0))
+    ref = F.conv2d(xcat, w, b, padding=1)
+    res = {"fwd": err(nchw(out.float()), ref)}
+    dr = bf16r(torch.randn(2 * n, 64, H, W, device=DEV, generator=g))
+    splits = _splits_for(ops.wgrad_tiles(2 * n, H, W), splits)
+    ws = torch.full((splits, 64, 64), float("nan"), device=DEV)  # [s][co][kpad]
+    ops.wgrad_gemm(1, 1, 0, nhwc(dr).to(torch.bfloat16), cols, ws, splits, 64 * 64, 0, 64, 1)
+    grad = torch.empty(64, cin, 3, 3, device=DEV)
+    ops.wgrad_reduce(ws, splits, 64 * 64, 1, 64, cin, 9, grad)
+    ops.device_status()
+    refg = torch.nn.grad.conv2d_weight(xcat, (64, cin, 3, 3), dr, padding=1)
+    res["wgrad"] = err(grad, refg)
+    res["ok"] = res["fwd"]["finite"] and res["fwd"]["rel_l2"] < 6e-3 and res["wgrad"]["finite"] and \
+        res["wgrad"]["rel_l2"] < tol
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------
+def _bn_setup(n, H, W, Cc, G, seed):
+    g = _gen(seed)
+    r = (torch.randn(n, H, W, Cc, device=DEV, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(Cc, device=DEV, generator=g) + 0.5
+    beta = torch.randn(Cc, device=DEV, generator=g) * 0.2
+    return g, r, gamma, beta
+
+
+def _bn_forward_cuda(r, gamma, beta, G, train=True, rm=None, rv=None, order_rev=False):
+    """Statistics from a pass-through conv_gemm is overkill here: emulate the epilogue partials with torch
+    (per 128-pixel tile sums), then run the CUDA stats/finalize kernels."""
+    n, H, W, Cc = r.shape
+    tiles = ops.conv_gemm_tiles(H, W)
+    tw, th = (16, 8) if W >= 16 else (8, 16)
+    r32 = r.float()
+    # [n, ty, th, tx, tw, C] -> per tile sums
+    rt = r32.view(n, H // th, th, W // tw, tw, Cc)
+    part = torch.stack([rt.sum((2, 4)), (rt * rt).sum((2, 4))], -1).reshape(n * tiles, Cc, 2).contiguous()
+    mean = torch.empty(G, Cc, device=DEV)
+    invstd = torch.empty_like(mean)
+    scale = torch.empty_like(mean)
+    shift = torch.empty_like(mean)
+    spl = 4
+    ws = torch.empty(spl, G, Cc, 2, device=DEV, dtype=torch.float64)
+    rm = torch.zeros(Cc, device=DEV) if rm is None else rm
+    rv = torch.ones(Cc, device=DEV) if rv is None else rv
+    nbt = torch.zeros((), device=DEV, dtype=torch.int64)
+    ops.bn_stats(part, Cc, Cc, (n // G) * tiles, G, (n // G) * H * W, spl, ws, gamma, beta, rm, rv, nbt, 0.1, 1e-5,
+                 train, order_rev, mean, invstd, scale, shift)
+    return mean, invstd, scale, shift, rm, rv, nbt
+
+
+def check_bn_apply(n=4, H=16, W=32, Cc=64, seed=10) -> dict:
+    G = 2
+    g, r, gamma, beta = _bn_setup(n, H, W, Cc, G, seed)
+    mean, invstd, scale, shift, rm, rv, nbt = _bn_forward_cuda(r, gamma, beta, G)
+    a = torch.empty(n, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+    cat = torch.zeros(n // 2, H, W, 2 * Cc, device=DEV, dtype=torch.bfloat16)
+    pool = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.bn_apply(r, scale, shift, G, True, a=a, pool=pool, dif=cat[..., :Cc])
+    torch.cuda.synchronize()
+    res = {}
+    bn = torch.nn.BatchNorm2d(Cc).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    bn.train()
+    x = nchw(r.float())
+    h = n // 2
+    y1 = F.relu(bn(x[:h]))  # two calls, separate statistics, two running-stat updates (SURVEY §0 finding 1)
+    y2 = F.relu(bn(x[h:]))
+    ref_a = torch.cat([y1, y2], 0)
+    res["a"] = err(nchw(a.float()), ref_a)
+    res["pool"] = err(nchw(pool.float()), F.max_pool2d(ref_a, 2))
+    res["diff"] = err(nchw(cat[..., :Cc].float()), y2 - y1)
+    res["running_mean"] = err(rm, bn.running_mean)
+    res["running_var"] = err(rv, bn.running_var)
+    res["nbt"] = int(nbt.item())
+    res["ok"] = (res["a"]["rel_l2"] < 4e-3 and res["pool"]["rel_l2"] < 4e-3 and res["diff"]["rel_l2"] < 6e-3 and
+                 res["running_mean"]["max_abs"] < 1e-5 and res["running_var"]["max_abs"] < 1e-4 and res["nbt"] == 2)
+    return res
+
+
+def check_bn_bwd(n=4, H=16, W=32, Cc=64, seed=11) -> dict:
+    """BN+ReLU backward with three gradient sources: skip (+/- by timestamp), max-pool routing, direct."""
+    G = 2
+    g, r, gamma, beta = _bn_setup(n, H, W, Cc, G, seed)
+    mean, invstd, scale, shift, *_ = _bn_forward_cuda(r, gamma, beta, G)
+    h = n // 2
+    d_skip = bf16r(torch.randn(h, H, W, 2 * Cc, device=DEV, generator=g))  # concat-buffer gradient, first C = skip
+    d_pool = bf16r(torch.randn(n, H // 2, W // 2, Cc, device=DEV, generator=g))
+    d_dir = bf16r(torch.randn(n, H, W, Cc, device=DEV, generator=g))
+    d_skip_b = d_skip.to(torch.bfloat16)
+    srcs = ops.make_srcs([
+        {"kind": 1, "t": d_skip_b[..., :Cc], "n_mod": h, "scale_lo": -1.0, "scale_hi": 1.0},
+        {"kind": 2, "t": d_pool.to(torch.bfloat16)},
+        {"kind": 1, "t": d_dir.to(torch.bfloat16)},
+    ])
+    ws = torch.empty(ops.bn_bwd_ws_floats(n, H, W, Cc, G), device=DEV)
+    dgamma = torch.empty(Cc, device=DEV)
+    dbeta = torch.empty(Cc, device=DEV)
+    dr = torch.empty(n, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.bn_bwd(r, mean, invstd, scale, shift, srcs, G, ws, dgamma, dbeta, dr)
+    torch.cuda.synchronize()
+    # torch reference: same graph in fp32
+    x = nchw(r.float()).requires_grad_(True)
+    ga = gamma.clone().requires_grad_(True)
+    be = beta.clone().requires_grad_(True)
+    ys = []
+    for gi in range(2):
+        xs = x[gi * h:(gi + 1) * h]
+        ys.append(F.relu(F.batch_norm(xs, None, None, ga, be, True, 0.1, 1e-5)))
+    aa = torch.cat(ys, 0)
+    # forward stores a in bf16 and pools the rounded values: route through the same rounding for the arg-max
+    aq = aa + (bf16r(aa.detach()) - aa.detach())
+    loss = ((aa[h:] - aa[:h]) * nchw(d_skip[..., :Cc])).sum() + (F.max_pool2d(aq, 2) * nchw(d_pool)).sum() + \
+        (aa * nchw(d_dir)).sum()
+    loss.backward()
+    res = {"dr": err(nchw(dr.float()), x.grad), "dgamma": err(dgamma, ga.grad), "dbeta": err(dbeta, be.grad)}
+    res["ok"] = res["dr"]["rel_l2"] < 8e-3 and res["dgamma"]["rel_l2"] < 2e-3 and res["dbeta"]["rel_l2"] < 2e-3
+    return res
+
+
+def check_head(n=2, H=16, W=16, seed=12) -> dict:
+    g = _gen(seed)
+    a0 = bf16r(torch.randn(n, H, W, 64, device=DEV, generator=g))
+    a1 = bf16r(torch.randn(n, H, W, 64, device=DEV, generator=g))
+    w = torch.randn(128, device=DEV, generator=g)
+    b = torch.randn(1, device=DEV, generator=g)
+    logits = torch.empty(n, 1, H, W, device=DEV)
+    ops.head_fwd(a0.to(torch.bfloat16), a1.to(torch.bfloat16), w, b, logits)
+    ref = (torch.cat([a0, a1], -1) * w).sum(-1) + b
+    res = {"fusion": err(logits.view(n, H, W), ref)}
+    ops.head_fwd(a0.to(torch.bfloat16), None, w[:64].contiguous(), b, logits)
+    res["single"] = err(logits.view(n, H, W), (a0 * w[:64]).sum(-1) + b)
+    # weight / bias gradient through colsum
+    dz = torch.randn(n * H * W, device=DEV, generator=g)
+    nblk = 8
+    ws = torch.empty(nblk * 64, device=DEV)
+    dw = torch.empty(64, device=DEV)
+    ops.colsum(a0.to(torch.bfloat16), dz, n * H * W, nblk, ws, dw)
+    res["dw"] = err(dw, (a0.view(-1, 64) * dz[:, None]).sum(0))
+    db = torch.empty(1, device=DEV)
+    ops.colsum(None, dz, n * H * W, nblk, ws, db)
+    res["db"] = err(db, dz.sum().view(1))
+    cs = torch.empty(64, device=DEV)
+    ops.colsum(a1.to(torch.bfloat16), None, n * H * W, nblk, ws, cs)
+    res["colsum"] = err(cs, a1.view(-1, 64).sum(0))
+    torch.cuda.synchronize()
+    res["ok"] = all(res[k]["rel_l2"] < 1e-5 for k in ("fusion", "single", "dw", "colsum")) and res["db"]["max_abs"] < 1e-3
+    return res
+
+
+def power_jaccard_ref(z, t):
+    p = torch.sigmoid(z)
+    i = (p.flatten() * t.flatten()).sum()
+    d = (p.flatten() ** 2 + t.flatten() ** 2).sum() - i + 1e-6
+    return 1 - i / d
+
+
+def check_pj(B=6, H=32, W=32, seed=13) -> dict:
+    g = _gen(seed)
+    z = torch.randn(B, 1, H, W, device=DEV, generator=g) * 2
+    t = (torch.rand(B, 1, H, W, device=DEV, generator=g) > 0.9).float()
+    z2 = torch.randn(B, 1, H, W, device=DEV, generator=g)
+    mask = torch.tensor([1, 1, 0, 1, 1, 0], device=DEV, dtype=torch.uint8)
+    nblk = 16
+    ws = torch.empty(nblk * 3, device=DEV, dtype=torch.float64)
+    sums = torch.empty(3, device=DEV, dtype=torch.float64)
+    loss = torch.empty((), device=DEV)
+    res = {}
+    # (1) plain, all rows
+    ops.pj_fwd(z, t, False, None, 0, nblk, ws, sums)
+    ops.pj_loss(sums, loss)
+    dz = torch.empty_like(z)
+    gout = torch.tensor(0.5, device=DEV)
+    ops.pj_bwd(z, t, False, None, 0, sums, gout, 2.0, False, dz, None)
+    zr = z.clone().requires_grad_(True)
+    lr = power_jaccard_ref(zr, t)
+    lr.backward()
+    res["loss"] = abs(loss.item() - lr.item())
+    res["dz"] = err(dz, zr.grad)  # g = 0.5 * 2.0 = 1
+    # (2) labeled rows only
+    ops.pj_fwd(z, t, False, mask, 1, nblk, ws, sums)
+    ops.pj_loss(sums, loss)
+    ops.pj_bwd(z, t, False, mask, 1, sums, None, 1.0, False, dz, None)
+    zr = z.clone().requires_grad_(True)
+    mb = mask.bool()
+    lr = power_jaccard_ref(zr[mb], t[mb])
+    lr.backward()
+    res["loss_masked"] = abs(loss.item() - lr.item())
+    res["dz_masked"] = err(dz, zr.grad)
+    # (3) consistency term on the unlabeled rows: target = sigmoid(z2), gradient to both
+    ops.pj_fwd(z, z2, True, mask, 0, nblk, ws, sums)
+    ops.pj_loss(sums, loss)
+    dz2 = torch.empty_like(z2)
+    ops.pj_bwd(z, z2, True, mask, 0, sums, None, 1.0, False, dz, dz2)
+    zr = z.clone().requires_grad_(True)
+    z2r = z2.clone().requires_grad_(True)
+    lr = power_jaccard_ref(zr[~mb], torch.sigmoid(z2r)[~mb])
+    lr.backward()
+    res["loss_cons"] = abs(loss.item() - lr.item())
+    res["dz_cons"] = err(dz, zr.grad)
+    res["dz2_cons"] = err(dz2, z2r.grad)
+    # known answers: pj(0, 1) = 1/3 ; pj(z, 0) = 1 with zero gradient
+    z0 = torch.zeros(2, 1, 8, 8, device=DEV)
+    ops.pj_fwd(z0, torch.ones_like(z0), False, None, 0, 4, ws, sums)
+    ops.pj_loss(sums, loss)
+    res["ka_third"] = abs(loss.item() - 1.0 / 3.0)
+    ops.pj_fwd(z[:2], torch.zeros_like(z[:2]), False, None, 0, 4, ws, sums)
+    ops.pj_loss(sums, loss)
+    dzz = torch.empty_like(z[:2])
+    ops.pj_bwd(z[:2].contiguous(), torch.zeros_like(z[:2]), False, None, 0, sums, None, 1.0, False, dzz, None)
+    res["ka_one"] = abs(loss.item() - 1.0)
+    res["ka_zero_grad"] = dzz.abs().max().item()
+    torch.cuda.synchronize()
+    res["ok"] = (res["loss"] < 1e-6 and res["loss_masked"] < 1e-6 and res["loss_cons"] < 1e-6 and
+                 res["dz"]["rel_l2"] < 1e-4 and res["dz_masked"]["rel_l2"] < 1e-4 and res["dz_cons"]["rel_l2"] < 1e-4 and
+                 res["dz2_cons"]["rel_l2"] < 1e-4 and res["ka_third"] < 1e-6 and res["ka_one"] < 1e-7 and
+                 res["ka_zero_grad"] == 0.0)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------
+# Layout decoders: structured operands that reveal which (row, k) element each output used. Run by the
+# probe when a GEMM check fails (blind debugging aid; not part of the pytest suite).
+def decode_fprop() -> dict:
+    n, H, W = 1, 8, 16  # exactly one 128-pixel tile (tw=16, th=8)
+    A = torch.zeros(n, H, W, 64, device=DEV)
+    pix = torch.arange(H * W, device=DEV)
+    A.view(-1, 64)[pix, pix % 64] = 1.0  # pixel p selects k = p % 64
+    out = {}
+    for name, fn in (("n", lambda nn, kk: nn), ("k", lambda nn, kk: kk)):
+        nn, kk = torch.meshgrid(torch.arange(64, device=DEV), torch.arange(64, device=DEV), indexing="ij")
+        Bw = fn(nn, kk).float().to(torch.bfloat16).contiguous()  # [N=64][K=64]
+        o = torch.empty(n, H, W, 64, device=DEV, dtype=torch.bfloat16)
+        ops.conv_gemm(1, 0, A.to(torch.bfloat16), Bw, o)
+        ops.device_status()
+        out[name] = o.float().view(128, 64)[:, :].cpu()
+    # expected: out["n"][p][c] = c ; out["k"][p][c] = p % 64
+    exp_n = torch.arange(64).float().expand(128, 64)
+    exp_k = (torch.arange(128) % 64).float().view(128, 1).expand(128, 64)
+    return {"n_ok": bool(torch.equal(out["n"], exp_n)), "k_ok": bool(torch.equal(out["k"], exp_k)),
+            "n_sample": out["n"][:10, :10].tolist(), "k_sample": out["k"][:10, :10].tolist(),
+            "k_col0": out["k"][:, 0].tolist()}
+
+
+def decode_wgrad() -> dict:
+    n, H, W = 1, 8, 8  # one 64-pixel tile
+    U = torch.zeros(n, H, W, 128, device=DEV)
+    pix = torch.arange(64, device=DEV)
+    U.view(-1, 128)[pix, pix] = 1.0  # pixel p selects m = p
+    res = {}
+    for name in ("p", "n"):
+        V = torch.zeros(64, 64, device=DEV)
+        if name == "p":
+            V[:] = torch.arange(64, device=DEV).float().view(64, 1)
+        else:
+            V[:] = torch.arange(64, device=DEV).float().view(1, 64)
+        ws = torch.full((1, 1, 128, 64), float("nan"), device=DEV)
+        ops.wgrad_gemm(1, 1, 0, U.to(torch.bfloat16), V.view(1, 8, 8, 64).to(torch.bfloat16), ws, 1, 128 * 64, 0, 64, 1)
+        ops.device_status()
+        res[name] = ws[0, 0].cpu()
+    exp_p = torch.zeros(128, 64)
+    exp_p[:64] = torch.arange(64).float().view(64, 1)
+    exp_n = torch.zeros(128, 64)
+    exp_n[:64] = torch.arange(64).float().view(1, 64)
+    return {"p_ok": bool(torch.equal(res["p"], exp_p)), "n_ok": bool(torch.equal(res["n"], exp_n)),
+            "p_sample": res["p"][:10, :10].tolist(), "n_sample": res["n"][:10, :10].tolist(),
+            "p_col0": res["p"][:, 0].tolist()}
+
+
+ALL_CHECKS = {
+    "pack_weights": check_pack_weights,
+    "pack_input": check_pack_input,
+    "pj": check_pj,
+    "head": check_head,
+    "bn_apply": check_bn_apply,
+    "bn_bwd": check_bn_bwd,
+    "conv3x3_64_64": lambda: check_conv3x3(2, 32, 32, 64, 64),
+    "conv3x3_128_128_16": lambda: check_conv3x3(2, 16, 16, 128, 128, seed=31),
+    "conv3x3_64_128_64": lambda: check_conv3x3(1, 64, 64, 64, 128, bias=False, seed=32),
+    "conv3x3_slices": lambda: check_conv3x3(2, 32, 32, 192, 256, slice_in=True, slice_out=True, seed=33),
+    "conv3x3_512_512_16": lambda: check_conv3x3(2, 16, 16, 512, 512, seed=34),
+    "conv3x3_dgrad": check_conv3x3_dgrad,
+    "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),
+    "convt_fwd": check_convt_fwd,
+    "convt_fwd_64": lambda: check_convt_fwd(2, 16, 32, 64, seed=51),
+    "convt_dgrad": check_convt_dgrad,
+    "convt_dgrad_64": lambda: check_convt_dgrad(2, 16, 32, 64, seed=61),
+    "wgrad3x3_pos": lambda: check_wgrad3x3(sign=1, halo=0),
+    "wgrad3x3_pos_halo": lambda: check_wgrad3x3(sign=1, halo=1),
+    "wgrad3x3_neg": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=0, seed=71),
+    "wgrad3x3_neg_halo": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=1, seed=71),
+    "wgrad3x3_64_64_halo": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, seed=72),
+    "wgrad3x3_512_512_halo": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=8, seed=73),
+    "wgrad_convt": check_wgrad_convt,
+    "wgrad_convt_64": lambda: check_wgrad_convt(2, 16, 32, 64, seed=81),
+    "wgrad_first": check_wgrad_first,
+}
