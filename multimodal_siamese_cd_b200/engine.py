@@ -1,0 +1,586 @@
+"""Static execution plan of one training (or inference) step of a U-Net-family network on one B200.
+
+The plan is built once per (network, batch, H, W, train/eval): every activation, gradient and workspace
+buffer is allocated up front (NHWC bf16, torch's caching allocator owns the memory), every kernel launch is
+a closure over those buffers calling the C ABI (include/b200cd.h) on the current stream, and after one eager
+run forward and backward are captured into CUDA graphs and replayed. The t1/t2 calls of a shared-weight
+encoder (utils/networks.py:141-145) are ONE launch over 2B images with two BatchNorm stat-groups; skip
+connections, the t2 - t1 difference, max-pool and the transposed-conv output are written straight into the
+buffers their consumers read (no cat / pad / sub kernels).
+
+Reference semantics preserved: separate batch statistics and two sequential running-stat
+updates per shared BatchNorm (decoder_sem: t2 first), pre-BN conv biases get exact-zero gradients,
+`outc_sem_change` gets no gradient at all.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+def _kpad(cin: int) -> int:
+    k = 9 * cin
+    return 64 * ((k + 63) // 64)
+
+
+@dataclass
+class Stage:
+    """conv3x3 (+bias) -> BatchNorm -> ReLU, the unit DoubleConv is made of (utils/networks.py:391-398)."""
+    name: str
+    conv: nn.Conv2d
+    bn: nn.BatchNorm2d
+    n_img: int
+    H: int
+    W: int
+    G: int
+    order_rev: bool
+    first: bool
+    in_view: torch.Tensor
+    r: torch.Tensor = None
+    outs: dict = field(default_factory=dict)
+    srcs: list = field(default_factory=list)
+    d_in: Optional[torch.Tensor] = None
+    dr: Optional[torch.Tensor] = None
+    Wf: torch.Tensor = None
+    Wd: Optional[torch.Tensor] = None
+    mean: torch.Tensor = None
+    invstd: torch.Tensor = None
+    scale: torch.Tensor = None
+    shift: torch.Tensor = None
+
+    @property
+    def cin(self) -> int:
+        return self.conv.in_channels
+
+    @property
+    def cout(self) -> int:
+        return self.conv.out_channels
+
+
+@dataclass
+class UpConv:
+    """ConvTranspose2d(c, c, 2, stride=2) writing into the upper half of a concat buffer (utils/networks.py:433-449)."""
+    name: str
+    up: nn.ConvTranspose2d
+    x: torch.Tensor          # [nb, h, w, c] input (dense)
+    out: torch.Tensor        # cat[..., c:] view at 2x resolution
+    d_out: Optional[torch.Tensor] = None   # d_cat[..., c:] view
+    d_x: Optional[torch.Tensor] = None     # [nb, h, w, c]
+    Wf: torch.Tensor = None
+    Wd: Optional[torch.Tensor] = None
+
+
+@dataclass
+class Head:
+    """OutConv 1x1 (utils/networks.py:454-461) over one or two decoder outputs."""
+    name: str
+    conv: nn.Conv2d
+    inputs: list            # one or two [nb, H, W, 64] tensors
+    logits: torch.Tensor    # [nb, 1, H, W] fp32
+    dz: Optional[torch.Tensor] = None
+
+
+class GradArena:
+    """One flat fp32 buffer holding every parameter gradient, laid out in reverse registration order (heads and
+    decoders first, encoder last) so a data-parallel caller can all-reduce it in buckets as backward proceeds."""
+
+    def __init__(self, module: nn.Module, device: torch.device, skip: set):
+        self.params = [(n, p) for n, p in module.named_parameters()]
+        order = [(n, p) for n, p in reversed(self.params) if n not in skip]
+        total = 0
+        self.offsets = {}
+        for n, p in order:
+            self.offsets[n] = total
+            total += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
+        self.flat = torch.zeros(total, device=device, dtype=torch.float32)
+        self.views = {n: self.flat[o:o + p.numel()].view(p.shape) for (n, p), o in
+                      zip(order, self.offsets.values())}
+        self.skip = skip
+
+    def view_of(self, p: nn.Parameter) -> torch.Tensor:
+        for n, q in self.params:
+            if q is p:
+                return self.views[n]
+        raise KeyError("parameter not in arena")
+
+
+class StepEngine:
+    """Builds and runs the plan for `net` (one of the drop-in classes in networks.py)."""
+
+    def __init__(self, net: nn.Module, B: int, H: int, W: int, train: bool, device: torch.device,
+                 use_graphs: bool = True):
+        if H % 16 != 0 or W % 16 != 0:
+            raise ValueError(f"b200cd engine: H and W must be multiples of 16 (got {H}x{W})")
+        self.net, self.B, self.H, self.W, self.train, self.device = net, B, H, W, train, device
+        self.use_graphs = use_graphs
+        self.stages: list[Stage] = []
+        self.upconvs: list[UpConv] = []
+        self.heads: list[Head] = []
+        self.fwd_ops: list[Callable[[], None]] = []
+        self.bwd_ops: list[Callable[[], None]] = []
+        self.pack_fwd: list[Callable[[], None]] = []
+        self.pack_bwd: list[Callable[[], None]] = []
+        self.bwd_marks: list[tuple[int, int]] = []  # (index into bwd_ops, flat-grad offset completed so far)
+        self.mem_bytes = 0
+        cin_total = self._input_channels()
+        self.x_t1 = torch.zeros(B, cin_total, H, W, device=device)
+        self.x_t2 = torch.zeros(B, cin_total, H, W, device=device)
+        skip = {n for n, _ in net.named_parameters() if n.startswith("outc_sem_change")}
+        self.grads = GradArena(net, device, skip) if train else None
+        self._ws_need = {"stats": 0, "stats2": 0, "wgrad": 0, "bnbwd": 0, "colsum": 0}
+        self._build()
+        self._alloc_ws()
+        self._param_ptrs = self._ptr_signature()
+        self._g_fwd = None
+        self._g_bwd = None
+        self._runs = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _input_channels(self) -> int:
+        cfg = self.net.cfg
+        t = cfg.MODEL.TYPE
+        if t in ("dualstreamunet", "whatevernet", "whatevernet2"):
+            return len(cfg.DATALOADER.S1_BANDS) + len(cfg.DATALOADER.S2_BANDS)
+        return cfg.MODEL.IN_CHANNELS
+
+    def _ptr_signature(self):
+        return tuple(p.data_ptr() for p in self.net.parameters()) + tuple(b.data_ptr() for b in self.net.buffers())
+
+    def params_moved(self) -> bool:
+        return self._ptr_signature() != self._param_ptrs
+
+    def _new(self, *shape, dtype=BF16, zero=False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(*shape, device=self.device, dtype=dtype)
+        self.mem_bytes += t.numel() * t.element_size()
+        return t
+
+    # ------------------------------------------------------------------------------------------------
+    # building blocks
+    # ------------------------------------------------------------------------------------------------
+    def _stage(self, name, conv, bn, in_view, n_img, H, W, G, order_rev=False, first=False) -> Stage:
+        st = Stage(name, conv, bn, n_img, H, W, G, order_rev, first, in_view)
+        C = conv.out_channels
+        if C % 64 != 0 or (not first and conv.in_channels % 64 != 0):
+            raise ValueError(f"b200cd engine: channel counts must be multiples of 64 ({name}: {conv.in_channels}->{C})")
+        st.r = self._new(n_img, H, W, C)
+        for k in ("mean", "invstd", "scale", "shift"):
+            setattr(st, k, self._new(G, C, dtype=torch.float32))
+        if first:
+            st.Wf = self._new(C, in_view.shape[3])
+        else:
+            st.Wf = self._new(C, 9 * conv.in_channels)
+            if self.train:
+                st.Wd = self._new(conv.in_channels, 9 * C)
+        if self.train:
+            st.dr = self._new(n_img, H, W, C)
+        tiles = ops.conv_gemm_tiles(H, W)
+        self._ws_need["stats"] = max(self._ws_need["stats"], n_img * tiles * C * 2)
+        self._ws_need["stats2"] = max(self._ws_need["stats2"], 32 * G * C * 2)
+        if self.train:
+            self._ws_need["bnbwd"] = max(self._ws_need["bnbwd"], ops.bn_bwd_ws_floats(n_img, H, W, C, G))
+        self.stages.append(st)
+        return st
+
+    def _double_conv(self, name, dc: nn.Module, in_view, n_img, H, W, G, order_rev=False, first=False):
+        """dc.conv = Sequential(conv, bn, relu, conv, bn, relu). Returns (stage1, stage2); stage2.outs is set by the caller."""
+        seq = dc.conv
+        s1 = self._stage(f"{name}.0", seq[0], seq[1], in_view, n_img, H, W, G, order_rev, first)
+        a1 = self._new(n_img, H, W, s1.cout)
+        s1.outs = {"a": a1}
+        s2 = self._stage(f"{name}.3", seq[3], seq[4], a1, n_img, H, W, G, order_rev)
+        if self.train:
+            s2.d_in = self._new(n_img, H, W, s1.cout)
+            s1.srcs = [{"kind": 1, "t": s2.d_in}]
+        return s1, s2
+
+    def _encoder(self, tag: str, inc: nn.Module, encoder: nn.Module, c_lo: int, nc: int, siamese: bool):
+        """inc + encoder (utils/networks.py:405-412, 313-343). Returns the list of second stages per level
+        (their apply outputs / gradient sources are wired by the decoders) and the level geometry."""
+        B, H, W = self.B, self.H, self.W
+        n_img, G = (2 * B, 2) if siamese else (B, 1)
+        cin = nc if siamese else 2 * nc
+        assert inc.conv.conv[0].in_channels == cin, f"{tag}: first conv expects {inc.conv.conv[0].in_channels} channels, data has {cin}"
+        kpad = _kpad(cin)
+        cols = self._new(n_img, H, W, kpad)
+        self.fwd_ops.append(lambda: ops.pack_input(self.x_t1, self.x_t2, c_lo, nc, 0 if siamese else 1, kpad, out=cols))
+        levels = []
+        s1, s2 = self._double_conv(f"{tag}.inc", inc.conv, cols, n_img, H, W, G, first=True)
+        levels.append(s2)
+        h, w = H, W
+        prev = s2
+        for lname, down in encoder.down_seq.items():
+            pool = self._new(n_img, h // 2, w // 2, prev.cout)
+            prev.outs["pool"] = pool
+            h, w = h // 2, w // 2
+            d1, d2 = self._double_conv(f"{tag}.{lname}", down.mpconv[1], pool, n_img, h, w, G)
+            if self.train:
+                d1.d_in = self._new(n_img, h, w, prev.cout)  # gradient w.r.t. the pooled tensor
+                prev.srcs.append({"kind": 2, "t": d1.d_in})
+            levels.append(d2)
+            prev = d2
+        return levels
+
+    def _decoder(self, tag: str, decoder: nn.Module, levels: list, mode: str, order_rev: bool = False):
+        """Decoder (utils/networks.py:346-382) over encoder `levels`.
+        mode: 'plain' (skip = encoder activation, same batch), 'diff' (skip = t2 - t1, batch B from a 2B encoder),
+              'copy' (skip = encoder activation of a 2B shared-weight encoder, e.g. decoder_sem)."""
+        enc_n = levels[0].n_img
+        nb = enc_n // 2 if mode == "diff" else enc_n
+        G = 2 if mode == "copy" else 1
+        deep = levels[-1]
+        # x entering the first Up: deepest feature (or its difference)
+        if mode == "diff":
+            x = self._new(nb, deep.H, deep.W, deep.cout)
+            deep.outs["dif"] = x
+            deep.outs["diff"] = True
+            deep.outs.setdefault("a", None)
+        else:
+            x = deep.outs.get("a")
+            if x is None:
+                x = self._new(enc_n, deep.H, deep.W, deep.cout)
+                deep.outs["a"] = x
+        last = None
+        d_x_prev_consumer = None  # (stage whose srcs receive d_x)
+        producer = ("enc", deep)
+        ups = list(decoder.up_seq.items())
+        for i, (uname, up) in enumerate(ups):
+            skip_stage = levels[len(levels) - 2 - i]
+            c = up.up.in_channels
+            assert skip_stage.cout == c, f"{tag}.{uname}: skip has {skip_stage.cout} channels, Up expects {c}"
+            Hs, Ws = skip_stage.H, skip_stage.W
+            cat = self._new(nb, Hs, Ws, 2 * c)
+            # skip half of the concat buffer, written by the encoder's apply kernel
+            if mode == "diff":
+                skip_stage.outs["dif"] = cat[..., :c]
+                skip_stage.outs["diff"] = True
+                if "a" not in skip_stage.outs:
+                    skip_stage.outs["a"] = self._new(enc_n, Hs, Ws, c)
+            elif mode == "copy":
+                if "a" not in skip_stage.outs or skip_stage.outs["a"] is None:
+                    skip_stage.outs["a"] = self._new(enc_n, Hs, Ws, c)
+                skip_stage.outs["a2"] = cat[..., :c]
+            else:
+                assert "a" not in skip_stage.outs, "plain skip is written straight into the concat buffer"
+                skip_stage.outs["a"] = cat[..., :c]
+            uc = UpConv(f"{tag}.{uname}.up", up.up, x, cat[..., c:])
+            uc.Wf = self._new(4 * c, c)
+            self.upconvs.append(uc)
+            d_cat = None
+            if self.train:
+                d_cat = self._new(nb, Hs, Ws, 2 * c)
+                uc.Wd = self._new(c, 4 * c)
+                uc.d_out = d_cat[..., c:]
+                uc.d_x = self._new(nb, Hs // 2, Ws // 2, c)
+                # gradient of the skip half flows back into the encoder stage
+                if mode == "diff":
+                    skip_stage.srcs.append({"kind": 1, "t": d_cat[..., :c], "n_mod": nb, "scale_lo": -1.0, "scale_hi": 1.0})
+                else:
+                    skip_stage.srcs.append({"kind": 1, "t": d_cat[..., :c]})
+                # gradient w.r.t. x flows into whoever produced x
+                kind, pst = producer
+                if kind == "enc" and mode == "diff":
+                    pst.srcs.append({"kind": 1, "t": uc.d_x, "n_mod": nb, "scale_lo": -1.0, "scale_hi": 1.0})
+                else:
+                    pst.srcs.append({"kind": 1, "t": uc.d_x})
+            s1, s2 = self._double_conv(f"{tag}.{uname}", up.conv, cat, nb, Hs, Ws, G, order_rev)
+            if self.train:
+                s1.d_in = d_cat
+            xo = self._new(nb, Hs, Ws, s2.cout)
+            s2.outs = {"a": xo}
+            self._up_plan.append((uc, s1, s2))
+            x = xo
+            producer = ("dec", s2)
+            last = s2
+        return last
+
+    def _head(self, name: str, conv: nn.Conv2d, dec_stages: list) -> Head:
+        ins = [s.outs["a"] for s in dec_stages]
+        nb, H, W, C = ins[0].shape
+        assert conv.in_channels == C * len(ins) and conv.out_channels == 1, \
+            f"{name}: only single-channel heads over 64-channel decoder outputs are supported"
+        hd = Head(name, conv, ins, self._new(nb, 1, H, W, dtype=torch.float32))
+        if self.train:
+            hd.dz = self._new(nb, 1, H, W, dtype=torch.float32, zero=True)
+            wflat = conv.weight.view(-1)
+            for i, s in enumerate(dec_stages):
+                s.srcs.append({"kind": 3, "t": hd.dz, "w": wflat[i * C:(i + 1) * C]})
+            self._ws_need["colsum"] = max(self._ws_need["colsum"], 296 * C)
+        self.heads.append(hd)
+        return hd
+
+    # ------------------------------------------------------------------------------------------------
+    def _build(self) -> None:
+        net, cfg = self.net, self.net.cfg
+        t = cfg.MODEL.TYPE
+        self._up_plan = []
+        ns1 = len(cfg.DATALOADER.S1_BANDS) if hasattr(cfg, "DATALOADER") and hasattr(cfg.DATALOADER, "S1_BANDS") else 0
+        ns2 = len(cfg.DATALOADER.S2_BANDS) if ns1 else 0
+        self.outputs = []  # (head, row slice or None) in the order forward() returns them
+        if t == "unet":
+            lv = self._encoder("u", net.inc, net.encoder, 0, cfg.MODEL.IN_CHANNELS, siamese=False)
+            d = self._decoder("u.dec", net.decoder, lv, "plain")
+            self.outputs = [(self._head("outc", net.outc.conv, [d]), None)]
+        elif t == "siameseunet":
+            lv = self._encoder("s", net.inc, net.encoder, 0, cfg.MODEL.IN_CHANNELS, siamese=True)
+            d = self._decoder("s.dec", net.decoder, lv, "diff")
+            self.outputs = [(self._head("outc", net.outc.conv, [d]), None)]
+        elif t == "dtsiameseunet":
+            lv = self._encoder("s", net.inc, net.encoder, 0, cfg.MODEL.IN_CHANNELS, siamese=True)
+            dc = self._decoder("s.dec_change", net.decoder_change, lv, "diff")
+            ds = self._decoder("s.dec_sem", net.decoder_sem, lv, "copy", order_rev=True)
+            hc = self._head("outc_change", net.outc_change.conv, [dc])
+            hs = self._head("outc_sem", net.outc_sem.conv, [ds])
+            B = self.B
+            self.outputs = [(hc, None), (hs, slice(0, B)), (hs, slice(B, 2 * B))]  # (change, sem_t1, sem_t2)
+        elif t in ("dualstreamunet", "whatevernet2"):
+            lv1 = self._encoder("s1", net.inc_stream1, net.encoder_stream1, 0, ns1, siamese=False)
+            d1 = self._decoder("s1.dec", net.decoder_stream1, lv1, "plain")
+            lv2 = self._encoder("s2", net.inc_stream2, net.encoder_stream2, ns1, ns2, siamese=False)
+            d2 = self._decoder("s2.dec", net.decoder_stream2, lv2, "plain")
+            if t == "dualstreamunet":
+                self.outputs = [(self._head("outc", net.outc.conv, [d1, d2]), None)]
+            else:
+                hf = self._head("outc_fusion", net.outc_fusion.conv, [d1, d2])
+                h1 = self._head("outc_stream1", net.outc_stream1.conv, [d1])
+                h2 = self._head("outc_stream2", net.outc_stream2.conv, [d2])
+                self.outputs = [(hf, None), (h1, None), (h2, None)]
+        elif t == "whatevernet":
+            lv1 = self._encoder("s1", net.inc_stream1, net.encoder_stream1, 0, ns1, siamese=True)
+            d1 = self._decoder("s1.dec", net.decoder_stream1, lv1, "diff")
+            lv2 = self._encoder("s2", net.inc_stream2, net.encoder_stream2, ns1, ns2, siamese=True)
+            d2 = self._decoder("s2.dec", net.decoder_stream2, lv2, "diff")
+            hf = self._head("outc_fusion", net.outc_fusion.conv, [d1, d2])
+            h1 = self._head("outc_stream1", net.outc_stream1.conv, [d1])
+            h2 = self._head("outc_stream2", net.outc_stream2.conv, [d2])
+            self.outputs = [(hf, None), (h1, None), (h2, None)]
+        else:
+            raise ValueError(f"Unknown network ({t}).")
+        self._emit_forward()
+        if self.train:
+            self._emit_backward()
+
+    # ------------------------------------------------------------------------------------------------
+    def _alloc_ws(self) -> None:
+        n = self._ws_need
+        self.ws_stats = self._new(max(n["stats"], 2), dtype=torch.float32)
+        self.ws_stats2 = self._new(max(n["stats2"], 2), dtype=torch.float64)
+        if self.train:
+            self.ws_wgrad = self._new(max(n["wgrad"], 4), dtype=torch.float32)
+            self.ws_bnbwd = self._new(max(n["bnbwd"], 4), dtype=torch.float32)
+            self.ws_colsum = self._new(max(n["colsum"], 4), dtype=torch.float32)
+
+    # ------------------------------------------------------------------------------------------------
+    # forward emission: stages were created in execution order, transposed convs are interleaved by name order
+    # ------------------------------------------------------------------------------------------------
+    def _emit_stage_fwd(self, st: Stage) -> None:
+        eng = self
+        conv, bn = st.conv, st.bn
+        tiles = ops.conv_gemm_tiles(st.H, st.W)
+        C = st.cout
+        if st.first:
+            eng.pack_fwd.append(lambda: ops.pack_weights(2, conv.weight, kpad=st.in_view.shape[3], out=st.Wf))
+        else:
+            eng.pack_fwd.append(lambda: ops.pack_weights(0, conv.weight, out=st.Wf))
+            if eng.train:
+                eng.pack_bwd.append(lambda: ops.pack_weights(1, conv.weight, out=st.Wd))
+        mode = 1 if st.first else 0
+        train = eng.train
+        count = (st.n_img // st.G) * st.H * st.W
+        tpg = (st.n_img // st.G) * tiles
+        spl = max(1, min(32, tpg // 64))
+        outs = st.outs
+
+        def run():
+            stats = eng.ws_stats if train else None
+            ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats)
+            ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2, bn.weight, bn.bias, bn.running_mean,
+                         bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
+                         st.order_rev, st.mean, st.invstd, st.scale, st.shift)
+            ops.bn_apply(st.r, st.scale, st.shift, st.G, bool(outs.get("diff", False)), a=outs.get("a"),
+                         a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"))
+
+        eng.fwd_ops.append(run)
+
+    def _emit_forward(self) -> None:
+        up_by_first_stage = {id(s1): uc for (uc, s1, s2) in self._up_plan}
+        for st in self.stages:
+            uc = up_by_first_stage.get(id(st))
+            if uc is not None:
+                self.pack_fwd.append(lambda uc=uc: ops.pack_weights(3, uc.up.weight, out=uc.Wf))
+                if self.train:
+                    self.pack_bwd.append(lambda uc=uc: ops.pack_weights(4, uc.up.weight, out=uc.Wd))
+                self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
+            self._emit_stage_fwd(st)
+        for hd in self.heads:
+            def run(hd=hd):
+                a1 = hd.inputs[1] if len(hd.inputs) > 1 else None
+                ops.head_fwd(hd.inputs[0], a1, hd.conv.weight.view(-1), hd.conv.bias, hd.logits)
+            self.fwd_ops.append(run)
+
+    # ------------------------------------------------------------------------------------------------
+    # backward emission: reverse order of the forward stages
+    # ------------------------------------------------------------------------------------------------
+    def _wgrad_plan(self, st: Stage):
+        """Choose operand roles / split count for the 3x3 weight gradient and size the workspace."""
+        cin, cout = st.cin, st.cout
+        total = ops.wgrad_tiles(st.n_img, st.H, st.W)
+        if st.first:
+            kp = st.in_view.shape[3]
+            ctas = max(1, kp // 128)
+            splits = max(1, min(total, (148 * 2) // ctas))
+            self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * cout * kp)
+            return ("first", splits)
+        if cout >= 128 or cin < 128:
+            role = "pos"   # M <-> cout (U = dr), N <-> cin
+            ctas = ((cout + 127) // 128) * (cin // 128 if cin % 128 == 0 else cin // 64) * 3
+        else:
+            role = "neg"   # M <-> cin (U = input), N <-> cout
+            ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
+        splits = max(1, min(total, max(1, (148 * 2) // ctas)))
+        self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 9 * cout * cin)
+        return (role, splits)
+
+    def _emit_stage_bwd(self, st: Stage) -> None:
+        eng = self
+        g = self.grads
+        conv, bn = st.conv, st.bn
+        gw, ggam, gbet = g.view_of(conv.weight), g.view_of(bn.weight), g.view_of(bn.bias)
+        role, splits = self._wgrad_plan(st)
+        cin, cout = st.cin, st.cout
+        srcs = st.srcs
+        assert 1 <= len(srcs) <= 3, f"{st.name}: {len(srcs)} gradient sources"
+
+        def run():
+            ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
+                       st.dr)
+            ws = eng.ws_wgrad
+            if role == "first":
+                kp = st.in_view.shape[3]
+                ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
+                ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
+            else:
+                if role == "pos":
+                    ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1)
+                else:
+                    ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin)
+                ops.wgrad_reduce(ws, splits, 9 * cout * cin, 0, cout, cin, 9, gw)
+                if st.d_in is not None:
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
+
+        eng.bwd_ops.append(run)
+
+    def _emit_up_bwd(self, uc: UpConv) -> None:
+        eng = self
+        g = self.grads
+        gw, gb = g.view_of(uc.up.weight), g.view_of(uc.up.bias)
+        c = uc.up.in_channels
+        nb, h, w, _ = uc.x.shape
+        total = ops.wgrad_tiles(nb, h, w)
+        ctas = ((c + 127) // 128) * (c // 128 if c % 128 == 0 else c // 64)
+        splits = max(1, min(total, max(1, (148 * 2) // ctas)))
+        self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 4 * c * c)
+        npix = nb * 4 * h * w
+        nblk = max(1, min(296, npix // 512))
+        self._ws_need["colsum"] = max(self._ws_need["colsum"], nblk * c)
+
+        def run():
+            ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad, splits, 4 * c * c, c * c, c, 1)
+            ops.wgrad_reduce(eng.ws_wgrad, splits, 4 * c * c, 0, c, c, 4, gw)
+            ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
+            ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
+
+        eng.bwd_ops.append(run)
+
+    def _emit_backward(self) -> None:
+        g = self.grads
+        for hd in self.heads:
+            C = hd.inputs[0].shape[3]
+            npix = hd.logits.numel()
+            nblk = max(1, min(296, npix // 512))
+            gw, gb = g.view_of(hd.conv.weight).view(-1), g.view_of(hd.conv.bias)
+
+            def run(hd=hd, C=C, npix=npix, nblk=nblk, gw=gw, gb=gb):
+                dz = hd.dz.view(-1)
+                for i, a in enumerate(hd.inputs):
+                    ops.colsum(a, dz, npix, nblk, self.ws_colsum, gw[i * C:(i + 1) * C])
+                ops.colsum(None, dz, npix, nblk, self.ws_colsum, gb)
+            self.bwd_ops.append(run)
+        up_by_first_stage = {id(s1): uc for (uc, s1, s2) in self._up_plan}
+        for st in reversed(self.stages):
+            self._emit_stage_bwd(st)
+            uc = up_by_first_stage.get(id(st))
+            if uc is not None:
+                self._emit_up_bwd(uc)
+
+    # ------------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------------
+    def _run_fwd_eager(self) -> None:
+        for f in self.pack_fwd:
+            f()
+        for f in self.fwd_ops:
+            f()
+
+    def _run_bwd_eager(self) -> None:
+        for f in self.pack_bwd:
+            f()
+        for f in self.bwd_ops:
+            f()
+
+    def forward(self, x_t1: torch.Tensor, x_t2: torch.Tensor) -> None:
+        """Copies the inputs into the static buffers and runs the forward plan; logits land in head.logits."""
+        self.x_t1.copy_(x_t1, non_blocking=True)
+        self.x_t2.copy_(x_t2, non_blocking=True)
+        self.forward_static()
+
+    def forward_static(self) -> None:
+        if self.use_graphs and self._runs >= 1:
+            if self._g_fwd is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_fwd_eager()
+                self._g_fwd = g
+            self._g_fwd.replay()
+        else:
+            self._run_fwd_eager()
+        self._runs += 1
+
+    def backward_static(self) -> None:
+        """Runs the backward plan from the dz buffers of the heads; gradients land in self.grads.flat."""
+        if self.use_graphs and self._runs >= 2:
+            if self._g_bwd is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_bwd_eager()
+                self._g_bwd = g
+            self._g_bwd.replay()
+        else:
+            self._run_bwd_eager()
+        self._runs += 1
+
+    def output_tensors(self) -> list[torch.Tensor]:
+        outs = []
+        for hd, sl in self.outputs:
+            outs.append(hd.logits if sl is None else hd.logits[sl])
+        return outs
+
+    def launches_per_step(self) -> dict:
+        """Kernel launches of one forward / backward (counted from the plan, not measured)."""
+        n_first = sum(1 for s in self.stages if s.first)
+        n_st = len(self.stages)
+        fwd = len(self.pack_fwd) + n_first + n_st * 4 + len(self.upconvs) + len(self.heads)  # conv, 2x stats, apply
+        if not self.train:
+            fwd -= n_st  # no stats reduce in eval
+            return {"forward": fwd, "backward": 0}
+        bwd = len(self.pack_bwd) + n_st * 5 + sum(1 for s in self.stages if s.d_in is not None) + \
+            len(self.upconvs) * 5 + sum(2 * (len(h.inputs) + 1) for h in self.heads)
+        return {"forward": fwd, "backward": bwd}
