@@ -88,27 +88,40 @@ class Head:
 
 
 class GradArena:
-    """One flat fp32 buffer holding every parameter gradient, laid out in reverse registration order (heads and
-    decoders first, encoder last) so a data-parallel caller can all-reduce it in buckets as backward proceeds."""
+    """One flat fp32 buffer holding every parameter gradient, laid out in the order the backward plan produces
+    them (heads, then decoders deepest-last, then the encoder), so a data-parallel caller can all-reduce a
+    completed prefix while the rest of backward is still running."""
 
-    def __init__(self, module: nn.Module, device: torch.device, skip: set):
+    def __init__(self, module: nn.Module, device: torch.device, write_order: list, skip: set):
         self.params = [(n, p) for n, p in module.named_parameters()]
-        order = [(n, p) for n, p in reversed(self.params) if n not in skip]
+        names = {id(p): n for n, p in self.params}
         total = 0
         self.offsets = {}
-        for n, p in order:
+        self.views = {}
+        seen = set()
+        for p in write_order:
+            n = names[id(p)]
+            if n in seen or n in skip:
+                continue
+            seen.add(n)
             self.offsets[n] = total
             total += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
+        missing = [n for n, _ in self.params if n not in seen and n not in skip]
+        assert not missing, f"parameters without a gradient producer: {missing}"
         self.flat = torch.zeros(total, device=device, dtype=torch.float32)
-        self.views = {n: self.flat[o:o + p.numel()].view(p.shape) for (n, p), o in
-                      zip(order, self.offsets.values())}
+        for n, p in self.params:
+            if n in self.offsets:
+                o = self.offsets[n]
+                self.views[n] = self.flat[o:o + p.numel()].view(p.shape)
         self.skip = skip
+        self._names = names
 
     def view_of(self, p: nn.Parameter) -> torch.Tensor:
-        for n, q in self.params:
-            if q is p:
-                return self.views[n]
-        raise KeyError("parameter not in arena")
+        return self.views[self._names[id(p)]]
+
+    def end_of(self, p: nn.Parameter) -> int:
+        n = self._names[id(p)]
+        return self.offsets[n] + (p.numel() + 3) // 4 * 4
 
 
 class StepEngine:
@@ -127,13 +140,12 @@ class StepEngine:
         self.bwd_ops: list[Callable[[], None]] = []
         self.pack_fwd: list[Callable[[], None]] = []
         self.pack_bwd: list[Callable[[], None]] = []
-        self.bwd_marks: list[tuple[int, int]] = []  # (index into bwd_ops, flat-grad offset completed so far)
+        self.bwd_marks: list[int] = []  # per backward op: length of the flat-gradient prefix complete after it
         self.mem_bytes = 0
         cin_total = self._input_channels()
         self.x_t1 = torch.zeros(B, cin_total, H, W, device=device)
         self.x_t2 = torch.zeros(B, cin_total, H, W, device=device)
-        skip = {n for n, _ in net.named_parameters() if n.startswith("outc_sem_change")}
-        self.grads = GradArena(net, device, skip) if train else None
+        self.grads: Optional[GradArena] = None
         self._ws_need = {"stats": 0, "stats2": 0, "wgrad": 0, "bnbwd": 0, "colsum": 0}
         self._build()
         self._alloc_ws()
@@ -258,14 +270,15 @@ class StepEngine:
             cat = self._new(nb, Hs, Ws, 2 * c)
             # skip half of the concat buffer, written by the encoder's apply kernel
             if mode == "diff":
+                # the activation itself is not materialised: pool and t2 - t1 are produced from registers
                 skip_stage.outs["dif"] = cat[..., :c]
                 skip_stage.outs["diff"] = True
-                if "a" not in skip_stage.outs:
-                    skip_stage.outs["a"] = self._new(enc_n, Hs, Ws, c)
             elif mode == "copy":
-                if "a" not in skip_stage.outs or skip_stage.outs["a"] is None:
-                    skip_stage.outs["a"] = self._new(enc_n, Hs, Ws, c)
-                skip_stage.outs["a2"] = cat[..., :c]
+                if skip_stage.outs.get("a") is None:
+                    skip_stage.outs["a"] = cat[..., :c]
+                else:
+                    assert "a2" not in skip_stage.outs
+                    skip_stage.outs["a2"] = cat[..., :c]
             else:
                 assert "a" not in skip_stage.outs, "plain skip is written straight into the concat buffer"
                 skip_stage.outs["a"] = cat[..., :c]
@@ -475,6 +488,7 @@ class StepEngine:
                     ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
         eng.bwd_ops.append(run)
+        eng.bwd_marks.append(g.end_of(conv.weight))
 
     def _emit_up_bwd(self, uc: UpConv) -> None:
         eng = self
@@ -497,8 +511,20 @@ class StepEngine:
             ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
 
         eng.bwd_ops.append(run)
+        eng.bwd_marks.append(g.end_of(uc.up.weight))
 
     def _emit_backward(self) -> None:
+        up_by_first = {id(s1): uc for (uc, s1, s2) in self._up_plan}
+        order = []
+        for hd in self.heads:
+            order += [hd.conv.weight, hd.conv.bias]
+        for st in reversed(self.stages):
+            order += [st.bn.bias, st.bn.weight, st.conv.bias, st.conv.weight]
+            uc = up_by_first.get(id(st))
+            if uc is not None:
+                order += [uc.up.bias, uc.up.weight]
+        skip = {n for n, _ in self.net.named_parameters() if n.startswith("outc_sem_change")}
+        self.grads = GradArena(self.net, self.device, order, skip)
         g = self.grads
         for hd in self.heads:
             C = hd.inputs[0].shape[3]
@@ -512,6 +538,7 @@ class StepEngine:
                     ops.colsum(a, dz, npix, nblk, self.ws_colsum, gw[i * C:(i + 1) * C])
                 ops.colsum(None, dz, npix, nblk, self.ws_colsum, gb)
             self.bwd_ops.append(run)
+            self.bwd_marks.append(g.end_of(hd.conv.bias))
         up_by_first_stage = {id(s1): uc for (uc, s1, s2) in self._up_plan}
         for st in reversed(self.stages):
             self._emit_stage_bwd(st)

@@ -16,6 +16,16 @@ from . import _lib
 from ._lib import GradSrc
 
 
+# Kernel launches issued through this module since import (our own kernels only; bench.py reports the
+# per-step delta as `gpu_launches`).
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -63,6 +73,7 @@ def pack_input(x0: torch.Tensor, x1: torch.Tensor, c_lo: int, nc: int, cat_mode:
     n_img = B if cat_mode else 2 * B
     if out is None:
         out = torch.empty((n_img, H, W, kpad), device=x0.device, dtype=torch.bfloat16)
+    _count(1)
     _lib.check(_lib.load().b200cd_pack_input(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad,
                                              out.data_ptr(), _stream()))
     return out
@@ -85,6 +96,7 @@ def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.
     if out is None:
         out = torch.empty(shape, device=w.device, dtype=torch.bfloat16)
     assert tuple(out.shape) == shape and out.is_contiguous()
+    _count(1)
     _lib.check(_lib.load().b200cd_pack_weights(mode, w.data_ptr(), out.data_ptr(), d0, d1, kpad, _stream()))
     return out
 
@@ -109,6 +121,7 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
     else:
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
+    _count(1)
     _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
                                             out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
@@ -125,6 +138,7 @@ def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor
     nv, Hv, Wv, cv, v_ld = _nhwc(V)
     assert nv == n and ((Hv, Wv) == (2 * H, 2 * W) if mode == 2 else (Hv, Wv) == (H, W))
     assert ws.dtype == torch.float32
+    _count(1)
     _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
                                              ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
                                              _stream()))
@@ -134,6 +148,7 @@ def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, 
                  grad: torch.Tensor) -> None:
     _require_cuda(ws, grad)
     assert grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == d0 * d1 * taps
+    _count(1)
     _lib.check(_lib.load().b200cd_wgrad_reduce(ws.data_ptr(), splits, split_stride, layout, d0, d1, taps,
                                                grad.data_ptr(), _stream()))
 
@@ -143,6 +158,7 @@ def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group:
              running_var: torch.Tensor, nbt: Optional[torch.Tensor], momentum: float, eps: float, train: bool,
              order_rev: bool, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> None:
     _require_cuda(gamma, beta, running_mean, running_var, mean)
+    _count(2 if train else 1)
     _lib.check(_lib.load().b200cd_bn_stats(_ptr(partial), ld, C_, tiles_per_group, G, float(count), spl, _ptr(ws),
                                            gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
                                            running_var.data_ptr(), _ptr(nbt), momentum, eps, int(train), int(order_rev),
@@ -159,6 +175,7 @@ def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, 
     def ld(t):
         return 0 if t is None else _nhwc(t)[4]
 
+    _count(1)
     _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
                                            int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool), _ptr(dif),
                                            ld(dif), _stream()))
@@ -188,6 +205,7 @@ def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: tor
            srcs: C.Array, G: int, ws: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, dr: torch.Tensor) -> None:
     _require_cuda(r, dr, ws)
     n, H, W, Cc, ld_r = _nhwc(r)
+    _count(3)
     _lib.check(_lib.load().b200cd_bn_bwd(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
                                          shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(), dgamma.data_ptr(),
                                          dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))
@@ -198,6 +216,7 @@ def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: t
     _require_cuda(a0, w, b, logits)
     n, H, W, Cc, ld0 = _nhwc(a0)
     ld1 = 0 if a1 is None else _nhwc(a1)[4]
+    _count(1)
     _lib.check(_lib.load().b200cd_head_fwd(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(), n * H * W,
                                            logits.data_ptr(), _stream()))
 
@@ -209,6 +228,7 @@ def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nb
         Cc, ld = 1, 0
     else:
         Cc, ld = x.shape[3], x.stride(2)
+    _count(2)
     _lib.check(_lib.load().b200cd_colsum(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(),
                                          _stream()))
 
@@ -218,12 +238,14 @@ def pj_fwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional
     _require_cuda(z, t, ws, sums)
     rows = z.shape[0]
     per_row = z.numel() // rows
+    _count(2)
     _lib.check(_lib.load().b200cd_pj_fwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
                                          nblk, ws.data_ptr(), sums.data_ptr(), _stream()))
 
 
 def pj_loss(sums: torch.Tensor, loss: torch.Tensor) -> None:
     _require_cuda(sums, loss)
+    _count(1)
     _lib.check(_lib.load().b200cd_pj_loss(sums.data_ptr(), loss.data_ptr(), _stream()))
 
 
@@ -233,6 +255,7 @@ def pj_bwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional
     _require_cuda(z, t, dz)
     rows = z.shape[0]
     per_row = z.numel() // rows
+    _count(1)
     _lib.check(_lib.load().b200cd_pj_bwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
                                          sums.data_ptr(), _ptr(gptr), gmul, int(accumulate), dz.data_ptr(), _ptr(dt),
                                          _stream()))

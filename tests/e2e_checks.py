@@ -1,0 +1,125 @@
+"""End-to-end parity of the CUDA path (drop-in modules and fused TrainStep) against the oracle on the same seeded
+weights and batch. Shared by tests/test_gpu_e2e.py and tools/gpu_e2e_probe.py."""
+from __future__ import annotations
+
+import torch
+
+from multimodal_siamese_cd_b200 import loss_functions, networks
+from multimodal_siamese_cd_b200.config import synthetic_cfg
+from multimodal_siamese_cd_b200.step import TrainStep
+from oracle import unet_oracle as O
+
+TWO_STREAM = ("dualstreamunet", "whatevernet", "whatevernet2")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def is_prebn_bias(name: str) -> bool:
+    return name.endswith((".conv.conv.0.bias", ".conv.conv.3.bias"))
+
+
+def grad_report(got: dict, ref: dict) -> dict:
+    """global relL2 over all parameters (pre-BN conv biases excluded: analytically zero) + per-parameter stats."""
+    num = den = 0.0
+    per = {}
+    for k, r in ref.items():
+        g = got.get(k)
+        if r is None:
+            assert g is None, f"{k}: reference has no gradient, CUDA path produced one"
+            continue
+        if is_prebn_bias(k):
+            assert g is not None and g.abs().max().item() <= 1e-6, f"{k}: pre-BN bias gradient must be ~0"
+            continue
+        d = (g.double().cpu() - r.double()).norm().item()
+        n = r.double().norm().item()
+        num += d * d
+        den += n * n
+        per[k] = d / max(n, 1e-30)
+    vals = sorted(per.values())
+    worst = max(per, key=per.get)
+    return {"global": (num / max(den, 1e-60)) ** 0.5, "median": vals[len(vals) // 2], "max": vals[-1], "worst": worst}
+
+
+def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alpha: float = 0.5, path: str = "dropin",
+             corr: bool = False, graphs: bool = True, steps: int = 1) -> dict:
+    """Returns error metrics of the CUDA path vs the bf16-storage oracle (q) and the exact fp32 oracle (x)."""
+    dev = torch.device("cuda", 0)
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    xc = 6 if mtype in TWO_STREAM else cin
+    batch = O.synthetic_batch(B, xc, H, W, seed=7, corr=corr)
+    net.to(dev)
+    net.train()
+    net.module.use_cuda_graphs = graphs
+    gb = {k: v.to(dev) for k, v in batch.items() if k != "is_labeled"}
+    got_grads = None
+    for it in range(steps):
+        if it > 0:  # repeat the same step from the same state (exercises graph replay)
+            net.load_state_dict(sd0)
+        if path == "dropin":
+            for p in net.parameters():
+                p.grad = None
+            crit = loss_functions.get_criterion("PowerJaccardLoss")
+            outs = net(gb["x_t1"], gb["x_t2"])
+            if kind == "supervised":
+                loss = crit(outs, gb["y_change"])
+                out_list = [outs]
+            elif kind == "dualtask":
+                c, s1, s2 = outs
+                loss = (crit(c, gb["y_change"]) + (crit(s1, gb["y_sem_t1"]) + crit(s2, gb["y_sem_t2"])) / 2) / 2
+                out_list = [c, s1, s2]
+            else:
+                f, s1, s2 = outs
+                lab = batch["is_labeled"]
+                y = gb["y_change"]
+                p2 = torch.sigmoid(s2)
+                sup = alpha * (crit(f[lab,], y[lab,]) + crit(s1[lab,], y[lab,]) + crit(s2[lab,], y[lab,])) / 3
+                unl = torch.logical_not(lab)
+                loss = sup + (1 - alpha) * crit(s1[unl,], p2[unl,])
+                out_list = [f, s1, s2]
+            loss.backward()
+            got_grads = {n: (p.grad.detach().clone() if p.grad is not None else None)
+                         for n, p in net.module.named_parameters()}
+            got_outs = [o.detach().clone() for o in out_list]
+            got_loss = loss.item()
+        else:
+            ts = TrainStep(net.module, B, H, W, kind=kind, alpha=alpha, device=dev, dp_group=None) if it == 0 else ts
+            tg = {k: gb[k] for k in ts.targets}
+            loss = ts(gb["x_t1"], gb["x_t2"], is_labeled=batch["is_labeled"] if kind == "mmcr" else None, **tg)
+            got_loss = loss.item()
+            got_outs = [o.detach().clone() for o in ts.eng.output_tensors()]
+            g = ts.eng.grads
+            got_grads = {n: (None if n in g.skip else g.views[n].detach().clone()) for n, _ in g.params}
+    torch.cuda.synchronize()
+    from multimodal_siamese_cd_b200 import ops
+    ops.device_status(0)
+    res = {"loss_cuda": got_loss}
+    sd_after = {k[len("module."):]: v.detach().cpu() for k, v in net.state_dict().items()}
+    for tag, q in (("q", True), ("x", False)):
+        sd = O.clone_state(sd0)
+        ref = O.train_step(mtype, sd, batch, kind=kind, alpha=alpha, q=q)
+        ro = ref["outs"] if isinstance(ref["outs"], tuple) else (ref["outs"],)
+        res[f"logits_{tag}"] = max(rel(g, r.detach()) for g, r in zip(got_outs, ro))
+        res[f"loss_{tag}"] = abs(got_loss - ref["loss"].item())
+        res[f"grads_{tag}"] = grad_report(got_grads, ref["grads"])
+        pm, _ = O.change_mask_f1(ro[0].detach(), batch["y_change"])
+        gm, gf1 = O.change_mask_f1(got_outs[0].cpu(), batch["y_change"])
+        _, rf1 = O.change_mask_f1(ro[0].detach(), batch["y_change"])
+        res[f"mask_flips_{tag}"] = int((pm != gm).sum())
+        res[f"f1_diff_{tag}"] = abs(gf1.item() - rf1.item())
+        if q:
+            bn_err = 0.0
+            for k, v in sd.items():
+                if k.endswith("running_mean") or k.endswith("running_var"):
+                    bn_err = max(bn_err, (sd_after[k] - v).abs().max().item())
+                elif k.endswith("num_batches_tracked"):
+                    assert int(sd_after[k]) == int(v), f"{k}: {int(sd_after[k])} != {int(v)}"
+            res["bn_running_maxabs"] = bn_err
+    res["n_pixels"] = got_outs[0].numel()
+    net.module.release_engines()
+    return res
