@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the training-step hot path (fwd + loss + bwd) on synthetic 256x256 S1+S2 patch pairs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config dualstream|siamese|dtsiamese|dtsiamese_ssl|mmcr]
+  python bench.py --impl reference ...   # the reference algorithm's CPU path (oracle port) on the host cores
+
+One JSON line on stdout (rank 0). `value` = whole-job patch-pairs/s with inputs resident in HBM (fused TrainStep,
+CUDA-graph replay); `e2e` = the same metric through the reference-facing drop-in modules
+(net(x_t1, x_t2) -> criterion -> loss.backward()) with pinned HOST inputs copied every step and loss.item() read back.
+For N > 1 launch with torch.distributed.run (one process per GPU, NCCL); per-GPU batch is fixed (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train patch-pairs/s (fwd+bwd, 256x256 S1+S2)"
+UNIT = "patch-pairs/s"
+
+# BASELINE.json configs -> (model type, in_channels, per-GPU batch, step kind, alpha, GF per pair fwd+bwd [BASELINE.md §3])
+CONFIGS = {
+    "siamese": ("siameseunet", 4, 8, "supervised", 0.5, 279.47, "baseline_siamese.yaml"),
+    "dualstream": ("dualstreamunet", 6, 16, "supervised", 0.5, 384.38, "baseline_dualstream.yaml TRAINER.BATCH_SIZE 16"),
+    "dtsiamese": ("dtsiameseunet", 6, 8, "dualtask", 0.5, 488.70, "dtsiamese.yaml MODEL.IN_CHANNELS 6"),
+    "dtsiamese_ssl": ("dtsiameseunet", 6, 8, "mmcr", 0.1, 488.70, "dtsiamese_ssl.yaml MODEL.IN_CHANNELS 6"),
+    "mmcr": ("whatevernet", 6, 64, "mmcr", 0.5, 558.38, "siamese_mmcr_alpha0500_16batch.yaml TRAINER.BATCH_SIZE 64/GPU"),
+}
+H = W = 256
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tensor": d["bf16_tflops_sustained"], "tensor_burst": d["bf16_tflops"], "hbm": d["hbm_gbs"], "src": "measured"}
+    return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in Path(self.f.name).read_text().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        sm_sorted = sorted(sm)
+        busy = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_step_rate(cfgname: str, sample_pairs: int, steps: int, warmup: int, threads=None) -> dict:
+    """The reference algorithm on the host cores: oracle port (pinned against the reference by tests/golden) running
+    zero_grad -> forward -> loss -> backward in fp32 on `sample_pairs` patch pairs per step."""
+    import torch
+
+    from oracle import unet_oracle as O
+    mtype, cin, _, kind, alpha, _, _ = CONFIGS[cfgname]
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd0 = O.reference_state_dict(mtype, in_channels=cin, seed=7)
+    batch = O.synthetic_batch(max(sample_pairs, 3 if kind == "mmcr" else 1), 6 if cin == 6 else cin, H, W, seed=7)
+    n = batch["x_t1"].shape[0]
+    times = []
+    for i in range(warmup + steps):
+        sd = O.clone_state(sd0)
+        t0 = time.perf_counter()
+        O.train_step(mtype, sd, batch, kind=kind, alpha=alpha, q=False)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": n / med, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} patch pairs per step, {steps} timed steps after {warmup} warm-up, fp32 torch CPU kernels, "
+                      f"median step {med:.2f} s", "sec_per_step": med, "pairs": n}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mtype, cin, B, kind, alpha, gf, yaml = CONFIGS[args.config]
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    r = cpu_step_rate(args.config, sample_pairs=2, steps=steps, warmup=warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{yaml}: {mtype}, fwd+loss+bwd ({kind}), 256x256, S1+S2; CPU sample of {r['pairs']} "
+                               f"pairs per step (GPU arm: {B} pairs per GPU per step)"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def profile_step(ts, steps: int = 2) -> dict:
+    """Eager (no graph) passes with CUDA events around every launch: per-kernel-family time, algorithmic FLOPs/bytes."""
+    import torch
+
+    from multimodal_siamese_cd_b200 import ops
+    eng = ts.eng
+    fam = {}
+    l0 = ops.LAUNCHES
+    for it in range(steps + 1):
+        ops.PROFILE = [] if it > 0 else None
+        eng._run_fwd_eager()
+        ts._loss_fwd()
+        ts._loss_bwd()
+        eng._run_bwd_eager()
+        torch.cuda.synchronize()
+        if ops.PROFILE:
+            for name, fl, by, e0, e1 in ops.PROFILE:
+                d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
+                d["ms"] += e0.elapsed_time(e1)
+                d["flops"] += fl
+                d["bytes"] += by
+                d["calls"] += 1
+    ops.PROFILE = None
+    fam["_launches_per_step"] = (ops.LAUNCHES - l0) // (steps + 1)
+    for d in fam.values():
+        if not isinstance(d, dict):
+            continue
+        for k in ("ms", "flops", "bytes"):
+            d[k] /= steps
+        d["calls"] //= steps
+    return fam
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="dualstream", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from multimodal_siamese_cd_b200 import loss_functions, networks, ops, parallel
+    from multimodal_siamese_cd_b200.config import synthetic_cfg
+    from multimodal_siamese_cd_b200.step import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        parallel.enable_data_parallel()
+    W_ = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    mtype, cin, B, kind, alpha, gf_pair, yaml = CONFIGS[args.config]
+    if args.batch:
+        B = args.batch
+    cfg = synthetic_cfg(mtype, in_channels=cin)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg).to(dev).train()
+    xc = 6 if mtype in ("dualstreamunet", "whatevernet", "whatevernet2") else cin
+
+    # synthetic batch, rank r uses seed 7 + r; generated on the host, pinned
+    g = torch.Generator().manual_seed(7 + rank)
+    host = {
+        "x_t1": torch.rand(B, xc, H, W, generator=g).pin_memory(),
+        "x_t2": torch.rand(B, xc, H, W, generator=g).pin_memory(),
+        "y_change": (torch.rand(B, 1, H, W, generator=g) > 0.9).float().pin_memory(),
+        "y_sem_t1": (torch.rand(B, 1, H, W, generator=g) > 0.8).float().pin_memory(),
+        "y_sem_t2": (torch.rand(B, 1, H, W, generator=g) > 0.8).float().pin_memory(),
+    }
+    is_labeled = torch.tensor([i % 3 != 2 for i in range(B)])
+
+    ts = TrainStep(net.module, B, H, W, kind=kind, alpha=alpha, device=dev)
+    tg = {k: host[k] for k in ts.targets}
+    ts.set_inputs(host["x_t1"], host["x_t2"], is_labeled=is_labeled if kind == "mmcr" else None, **tg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    for _ in range(W_):
+        ts.run()
+    l0 = ops.LAUNCHES
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = ts.run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    clocks = sampler.stop() if sampler else None
+    ops.device_status(local)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    loss_val = float(loss.item())
+
+    # ---- end to end through the reference-facing modules ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        crit = loss_functions.get_criterion("PowerJaccardLoss")
+
+        def e2e_step():
+            x1 = host["x_t1"].to(dev, non_blocking=True)
+            x2 = host["x_t2"].to(dev, non_blocking=True)
+            for p in net.parameters():
+                p.grad = None
+            outs = net(x1, x2)
+            if kind == "supervised":
+                loss = crit(outs, host["y_change"].to(dev, non_blocking=True))
+            elif kind == "dualtask":
+                c, s1, s2 = outs
+                loss = (crit(c, host["y_change"].to(dev, non_blocking=True)) +
+                        (crit(s1, host["y_sem_t1"].to(dev, non_blocking=True)) +
+                         crit(s2, host["y_sem_t2"].to(dev, non_blocking=True))) / 2) / 2
+            else:
+                f, s1, s2 = outs
+                y = host["y_change"].to(dev, non_blocking=True)
+                lab = is_labeled
+                p2 = torch.sigmoid(s2)
+                loss = alpha * (crit(f[lab,], y[lab,]) + crit(s1[lab,], y[lab,]) + crit(s2[lab,], y[lab,])) / 3 + \
+                    (1 - alpha) * crit(s1[~lab,], p2[~lab,])
+            loss.backward()
+            return loss.item()  # device -> host read of the step's result (train_supervised.py:79)
+
+        for _ in range(W_):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1) / K
+        t = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = t.item()
+        n_t = {"supervised": 1, "dualtask": 3, "mmcr": 1}[kind]
+        h2d = 2 * B * xc * H * W * 4 + n_t * B * H * W * 4
+        e2e = {"value": B * world / ems * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ems, "api": "networks.create_network(cfg)(x_t1, x_t2) -> get_criterion('PowerJaccardLoss') -> backward()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + per-family breakdown (rank 0, eager with events) ----------------------
+    pk = peaks()
+    fam = profile_step(ts)
+    gpu_launches = fam.pop("_launches_per_step") * K   # our own kernels inside the timed region (graph-replayed)
+    total_ms = sum(d["ms"] for d in fam.values())
+    tensor_fams = ("fprop3x3", "wgrad", "gemm1tap", "convT_dgrad")
+    dom = max(fam, key=lambda k: fam[k]["ms"])
+    d = fam[dom]
+    if dom in tensor_fams:
+        ach = d["flops"] / d["ms"] / 1e9
+        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"]}
+    else:
+        ach = d["bytes"] / d["ms"] / 1e6
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+    roof.update({"kernel": dom, "traffic": None, "share_of_step": d["ms"] / total_ms, "peak_source": pk["src"] +
+                 (" bf16_tflops_sustained" if roof["bound"] == "tensor" else " hbm_gbs"),
+                 "launches_per_step": d["calls"], "ms_per_step": d["ms"]})
+    breakdown = {}
+    for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        b = {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "calls": v["calls"]}
+        if k in tensor_fams:
+            b["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
+        else:
+            b["gbs"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+        breakdown[k] = b
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_step_rate(args.config, sample_pairs=2, steps=3, warmup=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    value = B * world / ms * 1e3
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{yaml}: {mtype}, fwd + {kind} power-Jaccard loss + bwd, 256x256, S1 2-band + S2 4-band, "
+                        f"{B} patch pairs per GPU",
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": f"no flush: one step touches {ts.eng.mem_bytes / 2**30:.1f} GiB of activations/gradients per GPU (>> 126 MB L2)",
+            "precision": "bf16 storage and MMA operands, fp32 accumulation / BatchNorm / loss / parameter gradients",
+        },
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": gpu_launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernel_breakdown": breakdown,
+        "step_roofline": {"gflop_per_pair": gf_pair, "achieved_tflops_per_gpu": value / world * gf_pair / 1e3,
+                          "frac_of_tensor_peak": value / world * gf_pair / 1e3 / pk["tensor"]},
+        "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

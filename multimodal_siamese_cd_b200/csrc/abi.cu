@@ -96,13 +96,20 @@ int make_up2_map(CUtensorMap* m, const void* base, int64_t ld, int c, int w, int
   return make_map(m, base, 5, dims, strides, box);
 }
 
-void tile_shape(int W, int* tw, int* th) {
+// Pixel tile of the implicit GEMM: tw x th <= 128 pixels of ONE image. When the row dimension of a tensor map is the
+// merged (image, row) index (2x2/stride-2 gather or scatter), th must divide H so a tile never spans two images.
+void tile_shape(int W, int H, bool merged_rows, int* tw, int* th) {
   if (W >= 16) {
     *tw = 16;
     *th = 8;
   } else {
     *tw = 8;
     *th = 16;
+  }
+  if (merged_rows) {
+    int t = *th < H ? *th : H;
+    while (H % t != 0) --t;
+    *th = t;
   }
 }
 
@@ -186,7 +193,7 @@ int b200cd_pack_weights(int mode, const float* w, void* out, int d0, int d1, int
 
 int b200cd_conv_gemm_tiles(int H, int W) {
   int tw, th;
-  tile_shape(W, &tw, &th);
+  tile_shape(W, H, false, &tw, &th);
   return ((W + tw - 1) / tw) * ((H + th - 1) / th);
 }
 
@@ -205,7 +212,7 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
   if (int rc = current_err_flag(&err)) return rc;
 
   int tw, th;
-  tile_shape(W, &tw, &th);
+  tile_shape(W, H, mode == 2 || out_mode == 1, &tw, &th);
   b200cd::FpropParams p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
@@ -215,6 +222,7 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
   p.ka = ka;
   p.tw = tw;
   p.th = th;
+  p.rows = tw * th;
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.H = H;

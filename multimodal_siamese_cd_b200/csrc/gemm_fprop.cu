@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
         uint8_t* b_dst = a_dst + kABytes;
         const int tap = it / p.kchunks;
         const int kc = it - tap * p.kchunks;
-        mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+        mbar_arrive_expect_tx(&full[s], p.rows * 128 + L::kBBytes);
         if (p.mode == 0) {
           const int ky = tap / 3, kx = tap - ky * 3;
           tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, img, 0);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
                                                                 (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
           float lo = bf16_lo(w), hi = bf16_hi(w);
           if (p.ragged) {
-            const bool ok = (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
+            const bool ok = (r < p.rows) && (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
             lo = ok ? lo : 0.f;
             hi = ok ? hi : 0.f;
           }

@@ -19,6 +19,7 @@ struct FpropParams {
   int mode, out_mode;
   int taps, kchunks, ka;  // K loop = taps * kchunks chunks of 64 channels; ka = channels per tap
   int tw, th, tiles_x, tiles_y;
+  int rows;               // tw*th <= 128 rows of the tile are real (the A box); the rest of the MMA tile is ignored
   int H, W;               // pixel grid of the GEMM rows
   int N, cout;
   const float* bias;      // nullable

@@ -16,6 +16,7 @@ from pathlib import Path
 import torch
 import torch.nn as nn
 
+from . import parallel
 from .engine import StepEngine
 
 __all__ = ["create_network", "save_checkpoint", "load_checkpoint", "UNet", "DualStreamUNet", "SiameseUNet",
@@ -119,6 +120,7 @@ class _StepFunction(torch.autograd.Function):
                 tgt.copy_(g.reshape(tgt.shape))
             touched.add(id(hd))
         eng.backward_static()
+        parallel.allreduce_gradients(eng.grads.flat)   # SUM over replicas when data parallelism is enabled
         grads = []
         for name, p in eng.grads.params:
             grads.append(None if name in eng.grads.skip else eng.grads.views[name])

@@ -26,6 +26,35 @@ def _count(n: int) -> None:
     LAUNCHES += n
 
 
+# Optional per-call profiling (bench.py's roofline leg): when PROFILE is a list, every wrapper appends
+# (kernel family, algorithmic flops, algorithmic bytes, start event, end event) around its launch(es).
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.name, self.flops, self.bytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+        return False
+
+
+def _nbytes(*ts) -> float:
+    return float(sum(t.shape.numel() * t.element_size() for t in ts if t is not None))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -74,8 +103,9 @@ def pack_input(x0: torch.Tensor, x1: torch.Tensor, c_lo: int, nc: int, cat_mode:
     if out is None:
         out = torch.empty((n_img, H, W, kpad), device=x0.device, dtype=torch.bfloat16)
     _count(1)
-    _lib.check(_lib.load().b200cd_pack_input(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad,
-                                             out.data_ptr(), _stream()))
+    with _Prof("pack_input", 0.0, _nbytes(out) + 4.0 * 2 * B * nc * H * W):
+        _lib.check(_lib.load().b200cd_pack_input(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad,
+                                                 out.data_ptr(), _stream()))
     return out
 
 
@@ -97,7 +127,8 @@ def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.
         out = torch.empty(shape, device=w.device, dtype=torch.bfloat16)
     assert tuple(out.shape) == shape and out.is_contiguous()
     _count(1)
-    _lib.check(_lib.load().b200cd_pack_weights(mode, w.data_ptr(), out.data_ptr(), d0, d1, kpad, _stream()))
+    with _Prof("pack_weights", 0.0, _nbytes(w, out)):
+        _lib.check(_lib.load().b200cd_pack_weights(mode, w.data_ptr(), out.data_ptr(), d0, d1, kpad, _stream()))
     return out
 
 
@@ -122,8 +153,10 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
     _count(1)
-    _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
-                                            out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
+    fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw)):
+        _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
+                                                out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
 
 def wgrad_tiles(n: int, H: int, W: int) -> int:
@@ -139,9 +172,11 @@ def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor
     assert nv == n and ((Hv, Wv) == (2 * H, 2 * W) if mode == 2 else (Hv, Wv) == (H, W))
     assert ws.dtype == torch.float32
     _count(1)
-    _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
-                                             ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
-                                             _stream()))
+    taps = 9 if mode == 0 else (1 if mode == 1 else 4)
+    with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) + 4.0 * splits * taps * cu * cv):
+        _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
+                                                 ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
+                                                 _stream()))
 
 
 def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, d0: int, d1: int, taps: int,
@@ -149,8 +184,9 @@ def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, 
     _require_cuda(ws, grad)
     assert grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == d0 * d1 * taps
     _count(1)
-    _lib.check(_lib.load().b200cd_wgrad_reduce(ws.data_ptr(), splits, split_stride, layout, d0, d1, taps,
-                                               grad.data_ptr(), _stream()))
+    with _Prof("wgrad_reduce", 0.0, 4.0 * (splits + 1) * d0 * d1 * taps):
+        _lib.check(_lib.load().b200cd_wgrad_reduce(ws.data_ptr(), splits, split_stride, layout, d0, d1, taps,
+                                                   grad.data_ptr(), _stream()))
 
 
 def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group: int, G: int, count: float, spl: int,
@@ -159,11 +195,12 @@ def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group:
              order_rev: bool, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> None:
     _require_cuda(gamma, beta, running_mean, running_var, mean)
     _count(2 if train else 1)
-    _lib.check(_lib.load().b200cd_bn_stats(_ptr(partial), ld, C_, tiles_per_group, G, float(count), spl, _ptr(ws),
-                                           gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
-                                           running_var.data_ptr(), _ptr(nbt), momentum, eps, int(train), int(order_rev),
-                                           mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                           _stream()))
+    with _Prof("bn_stats", 0.0, 8.0 * tiles_per_group * G * C_ if train else 0.0):
+        _lib.check(_lib.load().b200cd_bn_stats(_ptr(partial), ld, C_, tiles_per_group, G, float(count), spl, _ptr(ws),
+                                               gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                               running_var.data_ptr(), _ptr(nbt), momentum, eps, int(train),
+                                               int(order_rev), mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                               shift.data_ptr(), _stream()))
 
 
 def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, diff: bool,
@@ -176,9 +213,10 @@ def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, 
         return 0 if t is None else _nhwc(t)[4]
 
     _count(1)
-    _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
-                                           int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool), _ptr(dif),
-                                           ld(dif), _stream()))
+    with _Prof("bn_apply", 0.0, _nbytes(r, a, a2, pool, dif)):
+        _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
+                                               int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool),
+                                               _ptr(dif), ld(dif), _stream()))
 
 
 def make_srcs(srcs: Sequence[dict]) -> C.Array:
@@ -206,9 +244,12 @@ def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: tor
     _require_cuda(r, dr, ws)
     n, H, W, Cc, ld_r = _nhwc(r)
     _count(3)
-    _lib.check(_lib.load().b200cd_bn_bwd(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
-                                         shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(), dgamma.data_ptr(),
-                                         dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))
+    nsrc = sum(1.0 if s.kind == 1 else (0.25 if s.kind == 2 else 0.0) for s in srcs)
+    # two passes: each reads r and every gradient source; the second writes dr
+    with _Prof("bn_bwd", 0.0, _nbytes(r) * (2.0 + 2.0 * nsrc + 1.0)):
+        _lib.check(_lib.load().b200cd_bn_bwd(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                             shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(), dgamma.data_ptr(),
+                                             dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))
 
 
 def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: torch.Tensor,
@@ -217,8 +258,9 @@ def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: t
     n, H, W, Cc, ld0 = _nhwc(a0)
     ld1 = 0 if a1 is None else _nhwc(a1)[4]
     _count(1)
-    _lib.check(_lib.load().b200cd_head_fwd(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(), n * H * W,
-                                           logits.data_ptr(), _stream()))
+    with _Prof("head_fwd", 0.0, _nbytes(a0, a1, logits)):
+        _lib.check(_lib.load().b200cd_head_fwd(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(),
+                                               n * H * W, logits.data_ptr(), _stream()))
 
 
 def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nblk: int, ws: torch.Tensor,
@@ -229,8 +271,9 @@ def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nb
     else:
         Cc, ld = x.shape[3], x.stride(2)
     _count(2)
-    _lib.check(_lib.load().b200cd_colsum(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(),
-                                         _stream()))
+    with _Prof("colsum", 0.0, npix * (2.0 * Cc if x is not None else 0.0) + (4.0 * npix if wgt is not None else 0.0)):
+        _lib.check(_lib.load().b200cd_colsum(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(),
+                                             _stream()))
 
 
 def pj_fwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional[torch.Tensor], sel: int, nblk: int,
@@ -239,8 +282,9 @@ def pj_fwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional
     rows = z.shape[0]
     per_row = z.numel() // rows
     _count(2)
-    _lib.check(_lib.load().b200cd_pj_fwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
-                                         nblk, ws.data_ptr(), sums.data_ptr(), _stream()))
+    with _Prof("pj_fwd", 0.0, 8.0 * z.numel()):
+        _lib.check(_lib.load().b200cd_pj_fwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows,
+                                             per_row, nblk, ws.data_ptr(), sums.data_ptr(), _stream()))
 
 
 def pj_loss(sums: torch.Tensor, loss: torch.Tensor) -> None:
@@ -256,6 +300,7 @@ def pj_bwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional
     rows = z.shape[0]
     per_row = z.numel() // rows
     _count(1)
-    _lib.check(_lib.load().b200cd_pj_bwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows, per_row,
-                                         sums.data_ptr(), _ptr(gptr), gmul, int(accumulate), dz.data_ptr(), _ptr(dt),
-                                         _stream()))
+    with _Prof("pj_bwd", 0.0, (12.0 + (4.0 if dt is not None else 0.0)) * z.numel()):
+        _lib.check(_lib.load().b200cd_pj_bwd(z.data_ptr(), t.data_ptr(), int(t_is_logit), _ptr(rowmask), sel, rows,
+                                             per_row, sums.data_ptr(), _ptr(gptr), gmul, int(accumulate), dz.data_ptr(),
+                                             _ptr(dt), _stream()))

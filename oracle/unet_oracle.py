@@ -241,6 +241,65 @@ def change_mask_f1(logits, y_true):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# default initialisation (so the CPU baseline needs nothing from the product package)
+# ----------------------------------------------------------------------------------------------------------
+def reference_state_dict(model_type, in_channels=6, topology=(64, 128, 256, 512), n_s1=2, n_s2=4, seed=7) -> dict:
+    """state_dict (no 'module.' prefix) with torch's default init drawn in the reference's construction order
+    (utils/networks.py:132-137, 166-174, 209-220, 326-332, 364-371, 391-398, 433-434): nn.Conv2d /
+    nn.ConvTranspose2d draw weight then bias, BatchNorm draws nothing."""
+    import torch.nn as nn
+    topo = list(topology)
+    sd = {}
+
+    def put(prefix, mod):
+        for k, v in mod.state_dict().items():
+            sd[f"{prefix}.{k}"] = v
+
+    def double_conv(prefix, cin, cout):
+        put(f"{prefix}.conv.0", nn.Conv2d(cin, cout, 3, padding=1))
+        put(f"{prefix}.conv.1", nn.BatchNorm2d(cout))
+        put(f"{prefix}.conv.3", nn.Conv2d(cout, cout, 3, padding=1))
+        put(f"{prefix}.conv.4", nn.BatchNorm2d(cout))
+
+    widths = topo[1:] + topo[-1:]
+
+    def enc(prefix):
+        for i, (ci, co) in enumerate(zip(topo, widths), start=1):
+            double_conv(f"{prefix}.down_seq.down{i}.mpconv.1", ci, co)
+
+    def dec(prefix):
+        w = topo[:1] + widths
+        for depth in range(len(topo), 0, -1):
+            below, above = w[depth - 1], (w[depth - 2] if depth > 1 else w[0])
+            put(f"{prefix}.up_seq.up{depth}.up", nn.ConvTranspose2d(below, below, 2, stride=2))
+            double_conv(f"{prefix}.up_seq.up{depth}.conv", 2 * below, above)
+
+    def outc(prefix, cin):
+        put(f"{prefix}.conv", nn.Conv2d(cin, 1, 1))
+
+    torch.manual_seed(seed)
+    t0 = topo[0]
+    if model_type in ("unet", "siameseunet"):
+        double_conv("inc.conv", in_channels * (2 if model_type == "unet" else 1), t0)
+        enc("encoder"); dec("decoder"); outc("outc", t0)
+    elif model_type == "dtsiameseunet":
+        double_conv("inc.conv", in_channels, t0)
+        enc("encoder"); dec("decoder_change"); dec("decoder_sem")
+        outc("outc_change", t0); outc("outc_sem", t0); outc("outc_sem_change", 2)
+    elif model_type in ("dualstreamunet", "whatevernet", "whatevernet2"):
+        mult = 1 if model_type == "whatevernet" else 2
+        for k, nb in ((1, n_s1), (2, n_s2)):
+            double_conv(f"inc_stream{k}.conv", mult * nb, t0)
+            enc(f"encoder_stream{k}"); dec(f"decoder_stream{k}")
+            if model_type != "dualstreamunet":
+                outc(f"outc_stream{k}", t0)
+        outc("outc" if model_type == "dualstreamunet" else "outc_fusion", 2 * t0)
+    else:
+        raise Exception(f"Unknown network ({model_type}).")
+    return sd
+
+
+# ----------------------------------------------------------------------------------------------------------
 # one full step (what parity tests and the CPU baseline run)
 # ----------------------------------------------------------------------------------------------------------
 def clone_state(sd: dict, dtype=torch.float32, requires_grad: bool = True) -> dict:

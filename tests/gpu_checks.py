@@ -25,16 +25,26 @@ def nchw(x_nhwc: torch.Tensor) -> torch.Tensor:
     return x_nhwc.permute(0, 3, 1, 2).contiguous()
 
 
-def err(got: torch.Tensor, ref: torch.Tensor) -> dict:
+def err(got: torch.Tensor, ref: torch.Tensor, bf16_out: bool = False) -> dict:
+    """rel_l2 against the fp32 reference; for kernels whose OUTPUT is stored in bf16 also the comparison against
+    the reference rounded to bf16 (what a perfect kernel would store): `ulp_frac` = fraction of elements that differ
+    from it at all, `rel_l2_rounded` their size (an element differs only when the fp32 sums straddle a rounding
+    boundary, and then by exactly one bf16 ulp)."""
     got = got.double()
+    out = {}
+    if bf16_out:
+        rr = ref.to(torch.bfloat16).double()
+        out["ulp_frac"] = (got != rr).double().mean().item()
+        out["rel_l2_rounded"] = ((got - rr).norm() / rr.norm().clamp_min(1e-30)).item()
     ref = ref.double()
     d = (got - ref)
-    return {
+    out.update({
         "max_abs": d.abs().max().item(),
         "rel_l2": (d.norm() / ref.norm().clamp_min(1e-30)).item(),
         "ref_absmax": ref.abs().max().item(),
         "finite": bool(torch.isfinite(got).all().item()),
-    }
+    })
+    return out
 
 
 def _gen(seed: int) -> torch.Generator:
@@ -125,7 +135,7 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
     ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats)
     ops.device_status()
     ref = F.conv2d(x, w, b, padding=1)
-    res = err(nchw(out.float()), ref)
+    res = err(nchw(out.float()), ref, bf16_out=True)
     got_sum = stats[..., 0].sum(0)
     got_sq = stats[..., 1].sum(0)
     o32 = out.float()
@@ -147,7 +157,7 @@ def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> 
     ops.conv_gemm(0, 0, nhwc(dr).to(torch.bfloat16), Bd, out)
     ops.device_status()
     ref = F.conv_transpose2d(dr, w, padding=1)  # = input gradient of conv2d(x, w, padding=1)
-    res = err(nchw(out.float()), ref)
+    res = err(nchw(out.float()), ref, bf16_out=True)
     res["ok"] = res["finite"] and res["rel_l2"] < tol
     return res
 
@@ -163,7 +173,7 @@ def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3) -> dict:
     ops.conv_gemm(1, 1, nhwc(x).to(torch.bfloat16), Bw, cat[..., c:], bias=b)
     ops.device_status()
     ref = F.conv_transpose2d(x, wt, b, stride=2)
-    res = err(nchw(cat[..., c:].float()), ref)
+    res = err(nchw(cat[..., c:].float()), ref, bf16_out=True)
     res["untouched"] = bool((cat[..., :c] == 3.0).all().item())
     res["ok"] = res["finite"] and res["rel_l2"] < tol and res["untouched"]
     return res
@@ -180,7 +190,7 @@ def check_convt_dgrad(n=2, h=16, w_=16, c=128, seed=6, tol=6e-3) -> dict:
     ops.conv_gemm(2, 0, dcat[..., c:], Bd, out)
     ops.device_status()
     ref = F.conv2d(dout, wt, stride=2)  # input gradient of conv_transpose2d(x, wt, stride=2)
-    res = err(nchw(out.float()), ref)
+    res = err(nchw(out.float()), ref, bf16_out=True)
     res["ok"] = res["finite"] and res["rel_l2"] < tol
     return res
 
@@ -524,11 +534,20 @@ ALL_CHECKS = {
     "conv3x3_64_128_64": lambda: check_conv3x3(1, 64, 64, 64, 128, bias=False, seed=32),
     "conv3x3_slices": lambda: check_conv3x3(2, 32, 32, 192, 256, slice_in=True, slice_out=True, seed=33),
     "conv3x3_512_512_16": lambda: check_conv3x3(2, 16, 16, 512, 512, seed=34),
+    "conv3x3_ragged_8x8": lambda: check_conv3x3(3, 8, 8, 128, 128, seed=35),
+    "conv3x3_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36),
+    "conv3x3_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37),
     "conv3x3_dgrad": check_conv3x3_dgrad,
+    "conv3x3_dgrad_ragged_8x8": lambda: check_conv3x3_dgrad(3, 8, 8, 128, 128, seed=42),
     "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),
     "convt_fwd": check_convt_fwd,
     "convt_fwd_64": lambda: check_convt_fwd(2, 16, 32, 64, seed=51),
+    "convt_fwd_tiny_8x8": lambda: check_convt_fwd(3, 8, 8, 128, seed=52),
+    "convt_fwd_tiny_4x4": lambda: check_convt_fwd(3, 4, 4, 512, seed=53),
+    "convt_fwd_odd_6x12": lambda: check_convt_fwd(2, 6, 12, 64, seed=54),
     "convt_dgrad": check_convt_dgrad,
+    "convt_dgrad_tiny_8x8": lambda: check_convt_dgrad(3, 8, 8, 128, seed=62),
+    "convt_dgrad_tiny_4x4": lambda: check_convt_dgrad(3, 4, 4, 512, seed=63),
     "convt_dgrad_64": lambda: check_convt_dgrad(2, 16, 32, 64, seed=61),
     "wgrad3x3_pos": lambda: check_wgrad3x3(sign=1, halo=0),
     "wgrad3x3_pos_halo": lambda: check_wgrad3x3(sign=1, halo=1),
@@ -536,7 +555,10 @@ ALL_CHECKS = {
     "wgrad3x3_neg_halo": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=1, seed=71),
     "wgrad3x3_64_64_halo": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, seed=72),
     "wgrad3x3_512_512_halo": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=8, seed=73),
+    "wgrad3x3_tiny_4x4": lambda: check_wgrad3x3(3, 4, 4, 512, 512, sign=1, halo=1, splits=2, seed=74),
+    "wgrad3x3_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 128, sign=1, halo=1, splits=7, seed=75),
     "wgrad_convt": check_wgrad_convt,
+    "wgrad_convt_tiny_4x4": lambda: check_wgrad_convt(3, 4, 4, 512, splits=2, seed=82),
     "wgrad_convt_64": lambda: check_wgrad_convt(2, 16, 32, 64, seed=81),
     "wgrad_first": check_wgrad_first,
 }

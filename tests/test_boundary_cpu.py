@@ -1,0 +1,101 @@
+"""CPU: the drop-in boundary — C-ABI symbols, loud failure without CUDA, config shim, planner dry-run, gradient
+arena layout and the bucket plan of the data-parallel backward. No kernel is launched here."""
+from __future__ import annotations
+
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from multimodal_siamese_cd_b200 import _lib, loss_functions, networks, parallel
+from multimodal_siamese_cd_b200.config import CfgNode, load_cfg, synthetic_cfg
+from multimodal_siamese_cd_b200.engine import StepEngine
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "b200cd.h").read_text()
+    declared = set(re.findall(r"\b(b200cd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200cd.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.b200cd_abi_version() == 1
+    # pure host helpers may be called without a GPU
+    assert lib.b200cd_conv_gemm_tiles(256, 256) == 512
+    assert lib.b200cd_wgrad_tiles(2, 32, 32) == 32
+
+
+def test_no_cpu_fallback():
+    net = networks.create_network(synthetic_cfg("siameseunet", in_channels=4, topology=(64, 128)))
+    x = torch.rand(1, 4, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loss_functions.get_criterion("PowerJaccardLoss")(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    assert issubclass(_lib.B200CDError, RuntimeError)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.B200CDError):
+            _lib.init(0)  # fails loudly (no driver / wrong architecture), never silently
+
+
+def test_get_criterion_surface():
+    for name in ("PowerJaccardLoss", "BCEWithLogitsLoss", "SoftDiceLoss", "SoftDiceSquaredSumLoss", "SoftDiceBalancedLoss",
+                 "MeanSquareErrorLoss", "IoULoss", "DiceLikeLoss", "L2"):
+        assert callable(loss_functions.get_criterion(name))
+    with pytest.raises(Exception, match="unknown loss"):
+        loss_functions.get_criterion("nope")
+    with pytest.raises(Exception, match="Unknown network"):
+        networks.create_network(synthetic_cfg("resnet"))
+
+
+def test_cfg_shim_yaml_inheritance(tmp_path):
+    (tmp_path / "base.yaml").write_text("SEED: 7\nTRAINER:\n  LR: 1e-4\n  BATCH_SIZE: 8\nMODEL:\n  TYPE: 'unet'\n  IN_CHANNELS: 3\n"
+                                        "  TOPOLOGY: [64, 128, 256, 512, ]\nDATALOADER:\n  S1_BANDS: [0, 1]\n  S2_BANDS: [2, 1, 0, 3]\n")
+    (tmp_path / "child.yaml").write_text('_BASE_: "base.yaml"\nDEBUG: True\nMODEL:\n  TYPE: \'siameseunet\'\n  IN_CHANNELS: 4\n')
+    cfg = load_cfg(tmp_path / "child.yaml", ["TRAINER.BATCH_SIZE", "16", "MODEL.NEW_KEY", "abc"])
+    assert cfg.MODEL.TYPE == "siameseunet" and cfg.MODEL.IN_CHANNELS == 4 and cfg.MODEL.TOPOLOGY == [64, 128, 256, 512]
+    assert type(cfg.TRAINER.LR) is float and cfg.TRAINER.LR == 1e-4          # PyYAML reads '1e-4' as a string
+    assert cfg.TRAINER.BATCH_SIZE == 16 and cfg.MODEL.NEW_KEY == "abc" and cfg.DEBUG is True and cfg.NAME == "child"
+    assert isinstance(cfg.MODEL, CfgNode) and cfg.clone().MODEL.TYPE == "siameseunet"
+
+
+@pytest.mark.parametrize("mtype,cin,n_params", [("unet", 6, 14794113), ("siameseunet", 4, 14789505),
+                                                ("dualstreamunet", 6, 29581313), ("dtsiameseunet", 6, 20168709),
+                                                ("whatevernet", 6, 29577987), ("whatevernet2", 6, 29581443)])
+def test_parameter_counts_and_plan(mtype, cin, n_params):
+    """Parameter counts of SURVEY App. A.2 and a dry run of the planner (meta device: no kernels, no memory)."""
+    net = networks.create_network(synthetic_cfg(mtype, in_channels=cin))
+    assert sum(p.numel() for p in net.parameters()) == n_params
+    assert all(k.startswith("module.") for k in net.state_dict())
+    eng = StepEngine(net.module, 2, 64, 64, True, torch.device("meta"))
+    g = eng.grads
+    # every parameter except outc_sem_change has exactly one slot; slots tile the flat buffer in write order
+    slots = sorted((g.offsets[n], g.offsets[n] + p.numel()) for n, p in g.params if n not in g.skip)
+    assert all(a1 >= b0 for (_, b0), (a1, _) in zip(slots, slots[1:]))
+    assert {n for n, _ in g.params if n in g.skip} == {n for n, _ in g.params if n.startswith("outc_sem_change")}
+    assert len(eng.bwd_marks) == len(eng.bwd_ops) and eng.bwd_marks == sorted(eng.bwd_marks)
+    assert eng.bwd_marks[-1] == g.flat.numel()
+    for st in eng.stages:
+        assert 1 <= len(st.srcs) <= 3, st.name
+
+
+def test_bucket_plan_covers_gradient_buffer_once():
+    from multimodal_siamese_cd_b200.step import TrainStep
+    net = networks.create_network(synthetic_cfg("dtsiameseunet", in_channels=6)).module
+    eng = StepEngine(net, 2, 64, 64, True, torch.device("meta"))
+    ts = TrainStep.__new__(TrainStep)
+    ts.eng, ts.grad_buckets = eng, 4
+    plan = ts._plan_buckets()
+    assert plan[0][0] == 0 and plan[-1][1] == len(eng.bwd_ops)
+    assert plan[0][2] == 0 and plan[-1][3] == eng.grads.flat.numel()
+    for (o0, o1, g0, g1), (p0, p1, h0, h1) in zip(plan, plan[1:]):
+        assert o1 == p0 and g1 == h0 and o1 > o0 and g1 > g0
+
+
+def test_shard_rows_matches_dataparallel_scatter():
+    assert [parallel.shard_rows(8, r, 2) for r in range(2)] == [slice(0, 4), slice(4, 8)]
+    assert [parallel.shard_rows(10, r, 4) for r in range(4)] == [slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 10)]
