@@ -156,7 +156,13 @@ def profile_step(ts, steps: int = 2) -> dict:
         eng._run_bwd_eager()
         torch.cuda.synchronize()
         if ops.PROFILE:
-            for name, fl, by, e0, e1 in ops.PROFILE:
+            if it == steps and os.environ.get("B200CD_DUMP_CALLS"):
+                with open(os.environ["B200CD_DUMP_CALLS"], "w") as f:
+                    for name, fl, by, e0, e1, tag in ops.PROFILE:
+                        ms_ = e0.elapsed_time(e1)
+                        f.write(f"{name:14s} {ms_ * 1e3:9.1f} us  {fl / ms_ / 1e9 if fl else 0:8.1f} TF  "
+                                f"{by / ms_ / 1e6:8.1f} GB/s  {tag}\n")
+            for name, fl, by, e0, e1, _tag in ops.PROFILE:
                 d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
                 d["ms"] += e0.elapsed_time(e1)
                 d["flops"] += fl

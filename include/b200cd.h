@@ -72,6 +72,16 @@ int b200cd_pack_input(const float* src0, const float* src1, int csrc, int c_lo, 
  *   mode 4 convT dgrad       out[ci][tap*d1 + co] */
 int b200cd_pack_weights(int mode, const float* w, void* out_bf16, int d0, int d1, int kpad, void* stream);
 
+/* The same for every weight of a network in ONE launch. `jobs_dev` is a DEVICE array; job j writes the output elements
+ * [start_j, start_j + size_j) of the concatenated index space (start = running sum of the packed sizes), total = sum. */
+typedef struct {
+  const float* w;
+  void* out_bf16;
+  int32_t mode, d0, d1, kpad;
+  int64_t start;
+} b200cd_pack_job;
+int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * G1 — tcgen05 implicit GEMM, D[pixel, n] = sum_{tap,k} A_tap[pixel, k] * Bw[n, tap*ka + k].
  *   mode 0: 3x3 same-conv, 9 taps — nn.Conv2d(in,out,3,padding=1) utils/networks.py:392,395 (forward;

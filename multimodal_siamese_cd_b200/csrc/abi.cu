@@ -113,11 +113,12 @@ void tile_shape(int W, int H, bool merged_rows, int* tw, int* th) {
   }
 }
 
-int bn_bwd_nblk(int n_img, int H, int W, int C, int G) {
-  const long long wins = static_cast<long long>(n_img / G) * ((H + 1) / 2) * ((W + 1) / 2);
+// blocks per stat-group of the BN-backward kernels: ~4 resident waves of 2 CTAs/SM, at least 64 pixel units per lane
+int bn_bwd_nblk(int n_img, int H, int W, int C, int G, bool pool) {
+  long long units = static_cast<long long>(n_img / G) * (pool ? ((H + 1) / 2) * ((W + 1) / 2) : H * W);
   const int lanes = 256 / (C / 8);
-  long long nblk = wins / (static_cast<long long>(lanes) * 4);
-  const long long cap = (148 * 4) / G;
+  long long nblk = units / (static_cast<long long>(lanes) * (pool ? 8 : 32));
+  const long long cap = (148 * 2 * 4) / G;
   if (nblk > cap) nblk = cap;
   if (nblk < 1) nblk = 1;
   return static_cast<int>(nblk);
@@ -188,6 +189,14 @@ int b200cd_pack_weights(int mode, const float* w, void* out, int d0, int d1, int
   if (mode < 0 || mode > 4 || d0 <= 0 || d1 <= 0) return fail(B200CD_ERR_SHAPE, "pack_weights: bad arguments");
   if (mode == 2 && (kpad % 64 != 0 || 9 * d1 > kpad)) return fail(B200CD_ERR_SHAPE, "pack_weights: bad kpad");
   CUDA_TRY(b200cd::launch_pack_weights(mode, w, out, d0, d1, kpad, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total, void* stream) {
+  static_assert(sizeof(b200cd_pack_job) == sizeof(b200cd::PackJob), "pack job layout");
+  if (jobs_dev == nullptr || njobs < 1 || total < 1) return fail(B200CD_ERR_SHAPE, "pack_weights_batched: empty job table");
+  CUDA_TRY(b200cd::launch_pack_weights_batched(reinterpret_cast<const b200cd::PackJob*>(jobs_dev), njobs, total,
+                                               reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -348,8 +357,8 @@ int b200cd_bn_apply(const void* r, int64_t ld_r, const float* scale, const float
 
 size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G) {
   if (!chan_ok(C) || G <= 0 || n_img % G != 0) return 0;
-  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
-  return static_cast<size_t>(2) * G * C * (nblk + 1);
+  const int a = bn_bwd_nblk(n_img, H, W, C, G, false), b = bn_bwd_nblk(n_img, H, W, C, G, true);
+  return static_cast<size_t>(2) * G * C * ((a > b ? a : b) + 1);
 }
 
 int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
@@ -360,6 +369,7 @@ int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* i
   if (ld_r % 8 || ld_dr % 8 || !aligned16(r) || !aligned16(dr)) return fail(B200CD_ERR_ALIGN, "bn_bwd: alignment");
   b200cd::GradSrcs gs;
   memset(&gs, 0, sizeof(gs));
+  bool pool = false;
   for (int i = 0; i < 3; ++i) {
     gs.s[i].kind = srcs[i].kind;
     gs.s[i].ptr = srcs[i].ptr;
@@ -371,16 +381,17 @@ int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* i
     if (srcs[i].kind < 0 || srcs[i].kind > 3) return fail(B200CD_ERR_SHAPE, "bn_bwd: bad gradient source kind");
     if ((srcs[i].kind == 1 || srcs[i].kind == 2) && (srcs[i].ld % 8 != 0 || !aligned16(srcs[i].ptr)))
       return fail(B200CD_ERR_ALIGN, "bn_bwd: gradient source %d alignment", i);
+    pool = pool || srcs[i].kind == 2;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
+  const int nblk = bn_bwd_nblk(n_img, H, W, C, G, pool);
   float* partial = ws;
-  float* mdy = ws + static_cast<size_t>(2) * G * C * nblk;
-  float* mdyx = mdy + static_cast<size_t>(G) * C;
+  float* coefA = ws + static_cast<size_t>(2) * G * C * nblk;
+  float* coefB = coefA + static_cast<size_t>(G) * C;
   const double count = static_cast<double>(n_img / G) * H * W;
-  CUDA_TRY(b200cd::launch_bn_bwd_reduce(r, ld_r, mean, invstd, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
-  CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, dgamma, dbeta, mdy, mdyx, st));
-  CUDA_TRY(b200cd::launch_bn_bwd_dx(r, ld_r, mean, invstd, scale, shift, mdy, mdyx, gs, n_img, H, W, C, G, dr, ld_dr, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_reduce(r, ld_r, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta, coefA, coefB, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_dx(r, ld_r, scale, shift, coefA, coefB, gs, n_img, H, W, C, G, nblk, dr, ld_dr, st));
   return 0;
 }
 

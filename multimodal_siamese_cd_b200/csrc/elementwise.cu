@@ -104,10 +104,8 @@ __global__ void __launch_bounds__(128) pack_input_kernel(const float* __restrict
 //   mode 3: convT forward     w[d0=ci][d1=co][2][2] -> out[tap*co_count + co][ci]
 //   mode 4: convT dgrad       out[ci][tap*co_count + co]
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
-                                    int d1, int kpad, long long total) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__device__ __forceinline__ float pack_weight_value(int mode, const float* __restrict__ w, int d0, int d1, int kpad,
+                                                   long long i) {
   float v = 0.f;
   if (mode == 0) {
     const int ci = static_cast<int>(i % d1);
@@ -137,7 +135,29 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_
     const int tap = n / d1, co = n - tap * d1;
     v = w[(static_cast<long long>(ci) * d1 + co) * 4 + tap];
   }
-  out[i] = __float2bfloat16_rn(v);
+  return v;
+}
+
+__global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
+                                    int d1, int kpad, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  out[i] = __float2bfloat16_rn(pack_weight_value(mode, w, d0, d1, kpad, i));
+}
+
+// All weights of a step in ONE launch: job j owns output elements [start_j, start_{j+1}).
+__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].start <= i) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const long long li = i - j.start;
+  reinterpret_cast<__nv_bfloat16*>(j.out)[li] = __float2bfloat16_rn(pack_weight_value(j.mode, j.w, j.d0, j.d1, j.kpad, li));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,149 +331,242 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
   }
 }
 
+// Per-pixel variant (no pooling, no difference): a thread keeps its 8 channels, so scale/shift stay in registers;
+// four independent 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256, 4) bn_apply_px_kernel(const ApplyArgs p) {
+  const int cvecs = p.C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int g = blockIdx.y;
+  const int c = cv << 3;
+  const long long npx = static_cast<long long>(p.n_img / p.G) * p.H * p.W;
+  const long long pb = npx * blockIdx.x / gridDim.x, pe = npx * (blockIdx.x + 1) / gridDim.x;
+  float sc[8], sh[8];
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
+  const long long base = static_cast<long long>(g) * npx;
+  const __nv_bfloat16* rb = p.r + base * p.ld_r + c;
+  __nv_bfloat16* ab = p.a ? p.a + base * p.ld_a + c : nullptr;
+  __nv_bfloat16* a2b = p.a2 ? p.a2 + base * p.ld_a2 + c : nullptr;
+  long long i = pb + l;
+  for (; i + 3 * lanes < pe; i += 4 * lanes) {
+    uint4 rv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rv[u] = ldg16(rb + (i + u * lanes) * p.ld_r);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(rv[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+      const uint4 o = pack8(v);
+      if (ab) *reinterpret_cast<uint4*>(ab + (i + u * lanes) * p.ld_a) = o;
+      if (a2b) *reinterpret_cast<uint4*>(a2b + (i + u * lanes) * p.ld_a2) = o;
+    }
+  }
+  for (; i < pe; i += lanes) {
+    float v[8];
+    unpack8(ldg16(rb + i * p.ld_r), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    const uint4 o = pack8(v);
+    if (ab) *reinterpret_cast<uint4*>(ab + i * p.ld_a) = o;
+    if (a2b) *reinterpret_cast<uint4*>(a2b + i * p.ld_a2) = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// BN backward. dy = (sum of gradient sources) * [y > 0]; pass 1 reduces (sum dy, sum dy*xhat) per
-// (stat-group, channel); pass 2 writes dr = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)).
-// Gradient sources are gathered on the fly (skip connections with sign, max-pool routing, 1x1 head).
+// BN + ReLU backward. dy = (sum of gradient sources) * [y > 0].
+//   pass 1 (reduce): per (stat-group, channel) S1 = sum dy, S2 = sum dy*r   (block partials, fp32)
+//   finalize (fp64): sum(dy*xhat) = invstd*(S2 - mean*S1); dgamma, dbeta; and the two per-channel
+//                    coefficients of pass 2:  A = -scale*m2*invstd,  B = scale*(m2*mean*invstd - m1)
+//                    with m1 = S1/N, m2 = sum(dy*xhat)/N
+//   pass 2 (dx):     dr = scale*dy + r*A + B      (= scale*(dy - m1 - xhat*m2)), stored bf16
+// Gradient sources are gathered on the fly (skip connections with sign, max-pool routing, 1x1 head), so
+// neither the summed gradient nor the ReLU mask nor the post-BN activation is ever materialised.
+// Two thread mappings: per pixel (no max-pool source) and per 2x2 window (max-pool routing needs the
+// four activations of the window). A thread keeps its 8 channels for its whole pixel range, so the
+// per-channel constants live in registers.
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
   const __nv_bfloat16* r;
   long long ld_r;
-  const float *mean, *invstd, *scale, *shift;  // per (group, channel); scale = gamma*invstd, shift = beta - mean*scale
+  const float *scale, *shift;  // [G][C]; y = r*scale + shift exactly as the forward apply kernel computes it
   GradSrcs srcs;
   int n_img, H, W, C, G;
 };
 
-// dy for the 4 pixels of window (n, y2, x2), channels c..c+7; xhat returned as well.
-__device__ __forceinline__ void window_dy(const BwdArgs& p, int n, int y2, int x2, int c, int g, float (&dy)[4][8],
-                                          float (&xh)[4][8], bool (&valid)[4]) {
-  float mu[8], is[8], sc[8], sh[8];
-  load8f(p.mean + g * p.C + c, mu);
-  load8f(p.invstd + g * p.C + c, is);
-  load8f(p.scale + g * p.C + c, sc);
-  load8f(p.shift + g * p.C + c, sh);
-  float aq[4][8];
-  bool pos[4][8];
+// sum of the direct (kind 1) and head (kind 3) sources at pixel `pix` (index inside image n) -> dy[8]
+__device__ __forceinline__ void gather_px(const BwdArgs& p, int n, long long pix, long long hw, int c, float (&dy)[8]) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-    valid[k] = (y < p.H) && (x < p.W);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dy[k][j] = 0.f;
-      xh[k][j] = 0.f;
-      aq[k][j] = 0.f;
-      pos[k][j] = false;
-    }
-    if (valid[k]) {
-      const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
-      float rv[8];
-      unpack8(ldg16(p.r + pix * p.ld_r + c), rv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[k][j] = (rv[j] - mu[j]) * is[j];
-        // bit-identical to the forward apply kernel: same (scale, shift) arrays, same fma
-        const float yv = fmaf(rv[j], sc[j], sh[j]);
-        pos[k][j] = yv > 0.f;
-        aq[k][j] = round_bf16(fmaxf(yv, 0.f));
-      }
-    }
-  }
+  for (int j = 0; j < 8; ++j) dy[j] = 0.f;
 #pragma unroll
   for (int si = 0; si < 3; ++si) {
     const GradSrc& s = p.srcs.s[si];
-    if (s.kind == 0) continue;
+    if (s.kind != 1 && s.kind != 3) continue;
     int ns = n;
     float scale = 1.f;
     if (s.n_mod > 0) {
       scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
       ns = n % s.n_mod;
     }
+    const long long gp = static_cast<long long>(ns) * hw + pix;
     if (s.kind == 1) {
-      const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
+      float gv[8];
+      unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + gp * s.ld + c), gv);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!valid[k]) continue;
-        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-        const long long pix = (static_cast<long long>(ns) * p.H + y) * p.W + x;
-        float gv[8];
-        unpack8(ldg16(gp + pix * s.ld + c), gv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dy[k][j] = fmaf(scale, gv[j], dy[k][j]);
-      }
-    } else if (s.kind == 2) {
-      if (valid[3]) {  // complete window only (MaxPool2d floors)
-        const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(s.ptr);
-        const long long ppix = (static_cast<long long>(ns) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
-        float gv[8];
-        unpack8(ldg16(gp + ppix * s.ld + c), gv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // first maximum in row-major order, as ATen's max_pool2d_with_indices
-          int arg = 0;
-          float best = aq[0][j];
-#pragma unroll
-          for (int k = 1; k < 4; ++k)
-            if (aq[k][j] > best) {
-              best = aq[k][j];
-              arg = k;
-            }
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k == arg) dy[k][j] = fmaf(scale, gv[j], dy[k][j]);
-        }
-      }
+      for (int j = 0; j < 8; ++j) dy[j] = fmaf(scale, gv[j], dy[j]);
     } else {
-      const float* dz = reinterpret_cast<const float*>(s.ptr);
+      const float d = scale * __ldg(reinterpret_cast<const float*>(s.ptr) + gp);
       float wv[8];
       load8f(s.w + c, wv);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!valid[k]) continue;
-        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-        const long long pix = (static_cast<long long>(ns) * p.H + y) * p.W + x;
-        const float d = scale * __ldg(dz + pix);
+      for (int j = 0; j < 8; ++j) dy[j] = fmaf(d, wv[j], dy[j]);
+    }
+  }
+}
+
+// max-pool source(s): add the pooled gradient to the arg-max element of the window (first maximum in row-major
+// order on the bf16-rounded activations, as ATen's max_pool2d_with_indices on the stored tensor).
+__device__ __forceinline__ void route_pool(const BwdArgs& p, int n, int y2, int x2, int c, const float (&aq)[4][8],
+                                           float (&dy)[4][8]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dy[k][j] = fmaf(d, wv[j], dy[k][j]);
+  for (int si = 0; si < 3; ++si) {
+    const GradSrc& s = p.srcs.s[si];
+    if (s.kind != 2) continue;
+    int ns = n;
+    float scale = 1.f;
+    if (s.n_mod > 0) {
+      scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
+      ns = n % s.n_mod;
+    }
+    const long long ppix = (static_cast<long long>(ns) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
+    float gv[8];
+    unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + ppix * s.ld + c), gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0;
+      float best = aq[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (aq[k][j] > best) {
+          best = aq[k][j];
+          arg = k;
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dy[k][j] += (k == arg) ? scale * gv[j] : 0.f;
+    }
+  }
+}
+
+// Loads the window's r values, gathers + masks dy. Returns validity of the 4 pixels.
+__device__ __forceinline__ void window_dy(const BwdArgs& p, int n, int y2, int x2, int c, const float (&sc)[8],
+                                          const float (&sh)[8], float (&rv)[4][8], float (&dy)[4][8],
+                                          bool (&valid)[4]) {
+  const long long hw = static_cast<long long>(p.H) * p.W;
+  float aq[4][8];
+  bool pos[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+    valid[k] = (y < p.H) && (x < p.W);
+    if (valid[k]) {
+      const long long pix = static_cast<long long>(y) * p.W + x;
+      unpack8(ldg16(p.r + (static_cast<long long>(n) * hw + pix) * p.ld_r + c), rv[k]);
+      gather_px(p, n, pix, hw, c, dy[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float yv = fmaf(rv[k][j], sc[j], sh[j]);  // bit-identical to the forward apply kernel
+        pos[k][j] = yv > 0.f;
+        aq[k][j] = round_bf16(fmaxf(yv, 0.f));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rv[k][j] = 0.f;
+        dy[k][j] = 0.f;
+        aq[k][j] = 0.f;
+        pos[k][j] = false;
       }
     }
   }
+  if (valid[3]) route_pool(p, n, y2, x2, c, aq, dy);  // complete windows only (MaxPool2d floors)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) dy[k][j] = pos[k][j] ? dy[k][j] : 0.f;
 }
 
-// grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) window lanes
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
+// grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) lanes over pixels / windows
+template <bool POOL>
+__global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
   extern __shared__ float shred[];  // [lanes][C][2]
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
   const int cv = threadIdx.x % cvecs;
   const int l = threadIdx.x / cvecs;
   const int g = blockIdx.y;
-  const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+  const int c = cv << 3;
   const int per_group = p.n_img / p.G;
-  const long long wins = static_cast<long long>(per_group) * H2 * W2;
-  const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
-  float s1[8], s2[8];
+  float sc[8], sh[8], s1[8], s2[8];
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const int c = cv << 3;
-  for (long long w = wb + l; w < we; w += lanes) {
-    const int x2 = static_cast<int>(w % W2);
-    const int y2 = static_cast<int>((w / W2) % H2);
-    const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
-    float dy[4][8], xh[4][8];
-    bool valid[4];
-    window_dy(p, n, y2, x2, c, g, dy, xh, valid);
+  if (POOL) {
+    const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+    const long long wins = static_cast<long long>(per_group) * H2 * W2;
+    const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
+    for (long long w = wb + l; w < we; w += lanes) {
+      const int x2 = static_cast<int>(w % W2);
+      const int y2 = static_cast<int>((w / W2) % H2);
+      const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
+      float rv[4][8], dy[4][8];
+      bool valid[4];
+      window_dy(p, n, y2, x2, c, sc, sh, rv, dy, valid);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += dy[k][j];
+          s2[j] = fmaf(dy[k][j], rv[k][j], s2[j]);
+        }
+    }
+  } else {
+    const long long hw = static_cast<long long>(p.H) * p.W;
+    const long long npx = static_cast<long long>(per_group) * hw;
+    const long long pb = npx * blockIdx.x / gridDim.x, pe = npx * (blockIdx.x + 1) / gridDim.x;
+    const __nv_bfloat16* rbase = p.r + static_cast<long long>(g) * per_group * hw * p.ld_r + c;
+    long long i = pb + l;
+    // two pixels per iteration: both r loads and both source gathers are independent -> more loads in flight
+    for (; i + lanes < pe; i += 2 * lanes) {
+      const long long i1 = i + lanes;
+      const uint4 r0 = ldg16(rbase + i * p.ld_r), r1 = ldg16(rbase + i1 * p.ld_r);
+      float d0[8], d1[8], v0[8], v1[8];
+      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+      gather_px(p, g * per_group + static_cast<int>(i1 / hw), i1 % hw, hw, c, d1);
+      unpack8(r0, v0);
+      unpack8(r1, v1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s1[j] += dy[k][j];
-        s2[j] = fmaf(dy[k][j], xh[k][j], s2[j]);
+        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+        const float m1 = fmaf(v1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
+        s1[j] += m0 + m1;
+        s2[j] = fmaf(m0, v0[j], fmaf(m1, v1[j], s2[j]));
       }
+    }
+    for (; i < pe; i += lanes) {
+      float d0[8], v0[8];
+      unpack8(ldg16(rbase + i * p.ld_r), v0);
+      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+        s1[j] += m0;
+        s2[j] = fmaf(m0, v0[j], s2[j]);
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -474,60 +587,105 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs p, flo
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int G, double count,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ mdy,
-                                       float* __restrict__ mdyx) {
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ scale, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coefA, float* __restrict__ coefB) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
-    double a = 0.0, b = 0.0;
+    double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < nblk; ++i) {
       const float* o = partial + ((static_cast<long long>(g) * nblk + i) * C + c) * 2;
-      a += o[0];
-      b += o[1];
+      s1 += o[0];
+      s2 += o[1];
     }
-    mdy[g * C + c] = static_cast<float>(a / count);
-    mdyx[g * C + c] = static_cast<float>(b / count);
-    tb += a;
-    tg += b;
+    const double mu = mean[g * C + c], is = invstd[g * C + c], sc = scale[g * C + c];
+    const double sdyx = is * (s2 - mu * s1);  // sum dy * xhat
+    const double m1 = s1 / count, m2 = sdyx / count;
+    coefA[g * C + c] = static_cast<float>(-sc * m2 * is);
+    coefB[g * C + c] = static_cast<float>(sc * (m2 * mu * is - m1));
+    tb += s1;
+    tg += sdyx;
   }
   dgamma[c] = static_cast<float>(tg);
   dbeta[c] = static_cast<float>(tb);
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ mdy,
-                                                        const float* __restrict__ mdyx, __nv_bfloat16* __restrict__ dr,
-                                                        long long ld_dr) {
+template <bool POOL>
+__global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
+                                                           const float* __restrict__ coefB,
+                                                           __nv_bfloat16* __restrict__ dr, long long ld_dr) {
   const int cvecs = p.C >> 3;
-  const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
-  const long long total = static_cast<long long>(p.n_img) * H2 * W2 * cvecs;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int g = blockIdx.y;
+  const int c = cv << 3;
   const int per_group = p.n_img / p.G;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % cvecs);
-    long long w = i / cvecs;
-    const int x2 = static_cast<int>(w % W2);
-    w /= W2;
-    const int y2 = static_cast<int>(w % H2);
-    const int n = static_cast<int>(w / H2);
-    const int g = n / per_group;
-    const int c = cv << 3;
-    float dy[4][8], xh[4][8];
-    bool valid[4];
-    window_dy(p, n, y2, x2, c, g, dy, xh, valid);
-    float m1[8], m2[8], sc[8];
-    load8f(mdy + g * p.C + c, m1);
-    load8f(mdyx + g * p.C + c, m2);
-    load8f(p.scale + g * p.C + c, sc);
+  float sc[8], sh[8], ca[8], cb[8];
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
+  load8f(coefA + g * p.C + c, ca);
+  load8f(coefB + g * p.C + c, cb);
+  const long long hw = static_cast<long long>(p.H) * p.W;
+  if (POOL) {
+    const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
+    const long long wins = static_cast<long long>(per_group) * H2 * W2;
+    const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
+    for (long long w = wb + l; w < we; w += lanes) {
+      const int x2 = static_cast<int>(w % W2);
+      const int y2 = static_cast<int>((w / W2) % H2);
+      const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
+      float rv[4][8], dy[4][8];
+      bool valid[4];
+      window_dy(p, n, y2, x2, c, sc, sh, rv, dy, valid);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!valid[k]) continue;
-      const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-      const long long pix = (static_cast<long long>(n) * p.H + y) * p.W + x;
-      float o[8];
+      for (int k = 0; k < 4; ++k) {
+        if (!valid[k]) continue;
+        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
+        const long long pix = static_cast<long long>(n) * hw + static_cast<long long>(y) * p.W + x;
+        float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dy[k][j] - m1[j] - xh[k][j] * m2[j]);
-      *reinterpret_cast<uint4*>(dr + pix * ld_dr + c) = pack8(o);
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], dy[k][j], fmaf(rv[k][j], ca[j], cb[j]));
+        *reinterpret_cast<uint4*>(dr + pix * ld_dr + c) = pack8(o);
+      }
+    }
+  } else {
+    const long long npx = static_cast<long long>(per_group) * hw;
+    const long long pb = npx * blockIdx.x / gridDim.x, pe = npx * (blockIdx.x + 1) / gridDim.x;
+    const long long base = static_cast<long long>(g) * per_group * hw;
+    const __nv_bfloat16* rbase = p.r + base * p.ld_r + c;
+    __nv_bfloat16* obase = dr + base * ld_dr + c;
+    long long i = pb + l;
+    for (; i + lanes < pe; i += 2 * lanes) {
+      const long long i1 = i + lanes;
+      const uint4 r0 = ldg16(rbase + i * p.ld_r), r1 = ldg16(rbase + i1 * p.ld_r);
+      float d0[8], d1[8], v0[8], v1[8], o0[8], o1[8];
+      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+      gather_px(p, g * per_group + static_cast<int>(i1 / hw), i1 % hw, hw, c, d1);
+      unpack8(r0, v0);
+      unpack8(r1, v1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+        const float m1 = fmaf(v1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
+        o0[j] = fmaf(sc[j], m0, fmaf(v0[j], ca[j], cb[j]));
+        o1[j] = fmaf(sc[j], m1, fmaf(v1[j], ca[j], cb[j]));
+      }
+      *reinterpret_cast<uint4*>(obase + i * ld_dr) = pack8(o0);
+      *reinterpret_cast<uint4*>(obase + i1 * ld_dr) = pack8(o1);
+    }
+    for (; i < pe; i += lanes) {
+      float d0[8], v0[8], o0[8];
+      unpack8(ldg16(rbase + i * p.ld_r), v0);
+      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+        o0[j] = fmaf(sc[j], m0, fmaf(v0[j], ca[j], cb[j]));
+      }
+      *reinterpret_cast<uint4*>(obase + i * ld_dr) = pack8(o0);
     }
   }
 }
@@ -801,6 +959,11 @@ cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int
   return cudaGetLastError();
 }
 
+cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total, cudaStream_t st) {
+  pack_weights_batched_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(jobs, njobs, total);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
                                    double* partial2, cudaStream_t st) {
   dim3 grid((C + 31) / 32, G, spl);
@@ -832,46 +995,61 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
   p.pool = reinterpret_cast<__nv_bfloat16*>(pool);
   p.dif = reinterpret_cast<__nv_bfloat16*>(dif);
   p.ld_a = ld_a; p.ld_a2 = ld_a2; p.ld_p = ld_p; p.ld_d = ld_d;
+  if (!diff && pool == nullptr && C % 64 == 0 && 256 % (C / 8) == 0) {
+    const long long npx = static_cast<long long>(n_img / G) * H * W;
+    long long nblk = npx / ((256 / (C / 8)) * 16);
+    const long long cap = (148 * 4 * 4) / G;
+    nblk = nblk > cap ? cap : (nblk < 1 ? 1 : nblk);
+    bn_apply_px_kernel<<<dim3(static_cast<unsigned>(nblk), G), 256, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   const long long total = static_cast<long long>(diff ? n_img / 2 : n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 
-static BwdArgs make_bwd_args(const void* r, long long ld_r, const float* mean, const float* invstd, const float* scale,
-                             const float* shift, const GradSrcs& srcs, int n_img, int H, int W, int C, int G) {
+static BwdArgs make_bwd_args(const void* r, long long ld_r, const float* scale, const float* shift, const GradSrcs& srcs,
+                             int n_img, int H, int W, int C, int G) {
   BwdArgs p;
   p.r = reinterpret_cast<const __nv_bfloat16*>(r);
   p.ld_r = ld_r;
-  p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift;
+  p.scale = scale; p.shift = shift;
   p.srcs = srcs;
   p.n_img = n_img; p.H = H; p.W = W; p.C = C; p.G = G;
   return p;
 }
 
-cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* mean, const float* invstd,
-                                 const float* scale, const float* shift, const GradSrcs& srcs, int n_img, int H, int W,
-                                 int C, int G, int nblk, float* partial, cudaStream_t st) {
-  const BwdArgs p = make_bwd_args(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G);
+static bool has_pool_src(const GradSrcs& s) { return s.s[0].kind == 2 || s.s[1].kind == 2 || s.s[2].kind == 2; }
+
+cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* scale, const float* shift,
+                                 const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk, float* partial,
+                                 cudaStream_t st) {
+  const BwdArgs p = make_bwd_args(r, ld_r, scale, shift, srcs, n_img, H, W, C, G);
   const int lanes = 256 / (C / 8);
   const size_t smem = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
   dim3 grid(nblk, G);
-  bn_bwd_reduce_kernel<<<grid, 256, smem, st>>>(p, partial);
+  if (has_pool_src(srcs)) bn_bwd_reduce_kernel<true><<<grid, 256, smem, st>>>(p, partial);
+  else bn_bwd_reduce_kernel<false><<<grid, 256, smem, st>>>(p, partial);
   return cudaGetLastError();
 }
 
-cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, float* dgamma,
-                                   float* dbeta, float* mdy, float* mdyx, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, G, count, dgamma, dbeta, mdy, mdyx);
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, const float* mean,
+                                   const float* invstd, const float* scale, float* dgamma, float* dbeta, float* coefA,
+                                   float* coefB, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta,
+                                                          coefA, coefB);
   return cudaGetLastError();
 }
 
-cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* mean, const float* invstd,
-                             const float* scale, const float* shift, const float* mdy, const float* mdyx,
-                             const GradSrcs& srcs, int n_img, int H, int W, int C, int G, void* dr, long long ld_dr,
-                             cudaStream_t st) {
-  const BwdArgs p = make_bwd_args(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G);
-  const long long total = static_cast<long long>(n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  bn_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, mdy, mdyx, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
+cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, const float* shift, const float* coefA,
+                             const float* coefB, const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk,
+                             void* dr, long long ld_dr, cudaStream_t st) {
+  const BwdArgs p = make_bwd_args(r, ld_r, scale, shift, srcs, n_img, H, W, C, G);
+  dim3 grid(nblk, G);
+  if (has_pool_src(srcs))
+    bn_bwd_dx_kernel<true><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
+  else
+    bn_bwd_dx_kernel<false><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
   return cudaGetLastError();
 }
 

@@ -65,6 +65,13 @@ struct GradSrcs {
 
 cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B,
                               int H, int W, int kpad, void* out, cudaStream_t st);
+struct PackJob {        // layout == b200cd_pack_job (include/b200cd.h)
+  const float* w;
+  void* out;
+  int mode, d0, d1, kpad;
+  long long start;      // first output element (running sum over the jobs) this job owns
+};
+cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total, cudaStream_t st);
 cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, cudaStream_t st);
 cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
                                    double* partial2, cudaStream_t st);
@@ -75,15 +82,15 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
 cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
                             int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
                             void* pool, long long ld_p, void* dif, long long ld_d, cudaStream_t st);
-cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* mean, const float* invstd,
-                                 const float* scale, const float* shift, const GradSrcs& srcs, int n_img, int H, int W,
-                                 int C, int G, int nblk, float* partial, cudaStream_t st);
-cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, float* dgamma,
-                                   float* dbeta, float* mdy, float* mdyx, cudaStream_t st);
-cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* mean, const float* invstd,
-                             const float* scale, const float* shift, const float* mdy, const float* mdyx,
-                             const GradSrcs& srcs, int n_img, int H, int W, int C, int G, void* dr, long long ld_dr,
-                             cudaStream_t st);
+cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* scale, const float* shift,
+                                 const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk, float* partial,
+                                 cudaStream_t st);
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, const float* mean,
+                                   const float* invstd, const float* scale, float* dgamma, float* dbeta, float* coefA,
+                                   float* coefB, cudaStream_t st);
+cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, const float* shift, const float* coefA,
+                             const float* coefB, const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk,
+                             void* dr, long long ld_dr, cudaStream_t st);
 cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
                             const float* b, long long npix, float* logits, cudaStream_t st);
 cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,

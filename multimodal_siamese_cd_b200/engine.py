@@ -375,9 +375,17 @@ class StepEngine:
             self.outputs = [(hf, None), (h1, None), (h2, None)]
         else:
             raise ValueError(f"Unknown network ({t}).")
+        self._pack_specs_fwd, self._pack_specs_bwd = [], []
         self._emit_forward()
         if self.train:
             self._emit_backward()
+        # every weight of the step is converted to its bf16 GEMM operand layout by ONE launch (the fp32 master
+        # weights belong to the optimizer and change every step)
+        if self.device.type == "cuda":
+            for specs, dst in ((self._pack_specs_fwd, self.pack_fwd), (self._pack_specs_bwd, self.pack_bwd)):
+                if specs:
+                    tab, nj, tot = ops.make_pack_jobs(specs, self.device)
+                    dst.append(lambda tab=tab, nj=nj, tot=tot: ops.pack_weights_batched(tab, nj, tot))
 
     # ------------------------------------------------------------------------------------------------
     def _alloc_ws(self) -> None:
@@ -398,11 +406,11 @@ class StepEngine:
         tiles = ops.conv_gemm_tiles(st.H, st.W)
         C = st.cout
         if st.first:
-            eng.pack_fwd.append(lambda: ops.pack_weights(2, conv.weight, kpad=st.in_view.shape[3], out=st.Wf))
+            eng._pack_specs_fwd.append((2, conv.weight, st.Wf, st.in_view.shape[3]))
         else:
-            eng.pack_fwd.append(lambda: ops.pack_weights(0, conv.weight, out=st.Wf))
+            eng._pack_specs_fwd.append((0, conv.weight, st.Wf, 0))
             if eng.train:
-                eng.pack_bwd.append(lambda: ops.pack_weights(1, conv.weight, out=st.Wd))
+                eng._pack_specs_bwd.append((1, conv.weight, st.Wd, 0))
         mode = 1 if st.first else 0
         train = eng.train
         count = (st.n_img // st.G) * st.H * st.W
@@ -426,9 +434,9 @@ class StepEngine:
         for st in self.stages:
             uc = up_by_first_stage.get(id(st))
             if uc is not None:
-                self.pack_fwd.append(lambda uc=uc: ops.pack_weights(3, uc.up.weight, out=uc.Wf))
+                self._pack_specs_fwd.append((3, uc.up.weight, uc.Wf, 0))
                 if self.train:
-                    self.pack_bwd.append(lambda uc=uc: ops.pack_weights(4, uc.up.weight, out=uc.Wd))
+                    self._pack_specs_bwd.append((4, uc.up.weight, uc.Wd, 0))
                 self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
             self._emit_stage_fwd(st)
         for hd in self.heads:

@@ -32,10 +32,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ("name", "flops", "bytes", "e0")
+    __slots__ = ("name", "flops", "bytes", "e0", "tag")
 
-    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
-        self.name, self.flops, self.bytes = name, flops, nbytes
+    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0, tag: str = ""):
+        self.name, self.flops, self.bytes, self.tag = name, flops, nbytes, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -47,7 +47,7 @@ class _Prof:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1, self.tag))
         return False
 
 
@@ -132,6 +132,35 @@ def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.
     return out
 
 
+_PACK_JOB_DTYPE = None
+
+
+def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int]:
+    """specs: (mode, weight fp32 tensor, out bf16 tensor, kpad). Returns (device job table, njobs, total elements)
+    for pack_weights_batched (b200cd_pack_job layout: two pointers, four int32, one int64 = 40 bytes)."""
+    import numpy as np
+    global _PACK_JOB_DTYPE
+    if _PACK_JOB_DTYPE is None:
+        _PACK_JOB_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("mode", "<i4"), ("d0", "<i4"), ("d1", "<i4"),
+                                    ("kpad", "<i4"), ("start", "<i8")], align=True)
+        assert _PACK_JOB_DTYPE.itemsize == 40
+    arr = np.zeros(len(specs), dtype=_PACK_JOB_DTYPE)
+    total = 0
+    for i, (mode, w, out, kpad) in enumerate(specs):
+        assert w.dtype == torch.float32 and w.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+        arr[i] = (w.data_ptr(), out.data_ptr(), mode, w.shape[0], w.shape[1], kpad, total)
+        total += out.numel()
+    table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    return table, len(specs), total
+
+
+def pack_weights_batched(table: torch.Tensor, njobs: int, total: int) -> None:
+    _require_cuda(table)
+    _count(1)
+    with _Prof("pack_weights", 0.0, 6.0 * total):
+        _lib.check(_lib.load().b200cd_pack_weights_batched(table.data_ptr(), njobs, total, _stream()))
+
+
 def conv_gemm_tiles(H: int, W: int) -> int:
     return _lib.load().b200cd_conv_gemm_tiles(H, W)
 
@@ -154,7 +183,7 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
         cout = 0
     _count(1)
     fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
-    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw)):
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode}"):
         _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
                                                 out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
@@ -173,7 +202,8 @@ def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor
     assert ws.dtype == torch.float32
     _count(1)
     taps = 9 if mode == 0 else (1 if mode == 1 else 4)
-    with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) + 4.0 * splits * taps * cu * cv):
+    with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) + 4.0 * splits * taps * cu * cv,
+               f"{n}x{H}x{W} m{cu} n{cv} mode{mode} sign{sign} splits{splits}"):
         _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
                                                  ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
                                                  _stream()))
@@ -213,7 +243,8 @@ def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, 
         return 0 if t is None else _nhwc(t)[4]
 
     _count(1)
-    with _Prof("bn_apply", 0.0, _nbytes(r, a, a2, pool, dif)):
+    with _Prof("bn_apply", 0.0, _nbytes(r, a, a2, pool, dif),
+               f"{n}x{H}x{W}x{Cc} G{G} diff{int(diff)} pool{int(pool is not None)}"):
         _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
                                                int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool),
                                                _ptr(dif), ld(dif), _stream()))
@@ -246,7 +277,8 @@ def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: tor
     _count(3)
     nsrc = sum(1.0 if s.kind == 1 else (0.25 if s.kind == 2 else 0.0) for s in srcs)
     # two passes: each reads r and every gradient source; the second writes dr
-    with _Prof("bn_bwd", 0.0, _nbytes(r) * (2.0 + 2.0 * nsrc + 1.0)):
+    with _Prof("bn_bwd", 0.0, _nbytes(r) * (2.0 + 2.0 * nsrc + 1.0),
+               f"{n}x{H}x{W}x{Cc} G{G} srcs{[s.kind for s in srcs]}"):
         _lib.check(_lib.load().b200cd_bn_bwd(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
                                              shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(), dgamma.data_ptr(),
                                              dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))

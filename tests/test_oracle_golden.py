@@ -39,7 +39,9 @@ def test_default_init_matches_reference(name):
     ref_keys = set(fix["init"]) | {k for k in fix["bn"] if k.endswith("num_batches_tracked")}
     assert set(sd.keys()) == ref_keys
     for k, fp in fix["init"].items():
-        assert torch.equal(fingerprint(sd[k]), fp), k
+        got = fingerprint(sd[k])
+        assert torch.equal(got[2:], fp[2:]), k                       # leading values: bit-identical draws
+        assert torch.allclose(got[:2], fp[:2], rtol=1e-10, atol=1e-12), k   # norm / sum (reduction order may differ)
 
 
 @pytest.mark.parametrize("name", CASES)
