@@ -97,9 +97,12 @@ int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int6
  *   stats: NULL or fp32 [num_tiles][N][2] per-tile (sum, sum of squares) of the stored bf16 values — the
  *          batch statistics nn.BatchNorm2d (utils/networks.py:393,396) needs; num_tiles from
  *          b200cd_conv_gemm_tiles. A tile never spans two images.
+ *   flags: bit 0 (mode 0 only) = load the activation tile once per kx with a one-row halo and serve the three ky
+ *          taps from it (less L2 -> SM traffic; same result bit for bit).
+ *          bit 1 = use a 128 x 256 output tile when N (out_mode 1: cout) is a multiple of 256 and bit 0 is clear.
  *   requires ka % 64 == 0, N % 64 == 0, a_ld % 8 == 0, out_ld % 8 == 0.
  * ------------------------------------------------------------------------------------------------- */
-int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
                      const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
                      void* stream);
 /* tiles_per_image for (H, W): stats has n_img * tiles_per_image rows. */
@@ -149,10 +152,11 @@ int b200cd_bn_stats(const float* partial, int ld, int C, int tiles_per_group, in
  * (:147-150, 183-186, 223-228) and the skip half of torch.cat([x2, x1]) (:449).
  *   r: conv output bf16 [n_img][H][W][C]; diff=1: images [0,n_img/2) are t1, the rest t2, and
  *   dif[n] = a[n + n_img/2] - a[n]. Outputs (each nullable): a, a2 (second copy, e.g. a concat slice),
- *   pool [n_img][H/2][W/2][C], dif [n_img/2][H][W][C]. */
+ *   pool [n_img][H/2][W/2][C], dif [n_img/2][H][W][C], pool_idx uint8 [n_img][H/2][W/2][C] (dense): position 0..3
+ *   (row-major in the 2x2 window) of the first maximum of the stored activations — what MaxPool2d's backward needs. */
 int b200cd_bn_apply(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
                     int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
-                    void* dif, int64_t ld_d, void* stream);
+                    void* dif, int64_t ld_d, void* pool_idx, void* stream);
 
 /* Gradient sources summed on the fly by the BN backward kernels. */
 typedef struct {
@@ -160,7 +164,7 @@ typedef struct {
                        arg-max of each 2x2 window (MaxPool2d backward); 3 fp32 dz[pixel] times w[channel]
                        (OutConv backward, utils/networks.py:457) */
   const void* ptr;
-  const float* w;   /* kind 3 */
+  const float* w;   /* kind 3: head weights; kind 2: the uint8 pool_idx tensor written by b200cd_bn_apply */
   int64_t ld;
   int32_t n_mod;    /* > 0: source image = n % n_mod and scale = n < n_mod ? scale_lo : scale_hi
                        (the t2 - t1 difference feeds +d to t2 and -d to t1) */

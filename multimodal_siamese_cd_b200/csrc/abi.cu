@@ -113,11 +113,11 @@ void tile_shape(int W, int H, bool merged_rows, int* tw, int* th) {
   }
 }
 
-// blocks per stat-group of the BN-backward kernels: ~4 resident waves of 2 CTAs/SM, at least 64 pixel units per lane
-int bn_bwd_nblk(int n_img, int H, int W, int C, int G, bool pool) {
-  long long units = static_cast<long long>(n_img / G) * (pool ? ((H + 1) / 2) * ((W + 1) / 2) : H * W);
+// blocks per stat-group of the BN-backward kernels: up to ~4 waves of 2 CTAs/SM, at least 32 pixels per lane
+int bn_bwd_nblk(int n_img, int H, int W, int C, int G) {
+  const long long units = static_cast<long long>(n_img / G) * H * W;
   const int lanes = 256 / (C / 8);
-  long long nblk = units / (static_cast<long long>(lanes) * (pool ? 8 : 32));
+  long long nblk = units / (static_cast<long long>(lanes) * 32);
   const long long cap = (148 * 2 * 4) / G;
   if (nblk > cap) nblk = cap;
   if (nblk < 1) nblk = 1;
@@ -206,7 +206,7 @@ int b200cd_conv_gemm_tiles(int H, int W) {
   return ((W + tw - 1) / tw) * ((H + th - 1) / th);
 }
 
-int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
                      const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
                      void* stream) {
   if (mode < 0 || mode > 2 || out_mode < 0 || out_mode > 1) return fail(B200CD_ERR_SHAPE, "conv_gemm: bad mode");
@@ -222,6 +222,7 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
 
   int tw, th;
   tile_shape(W, H, mode == 2 || out_mode == 1, &tw, &th);
+  const int halo = (mode == 0 && (flags & 1)) ? 1 : 0;
   b200cd::FpropParams p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
@@ -231,7 +232,7 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
   p.ka = ka;
   p.tw = tw;
   p.th = th;
-  p.rows = tw * th;
+  p.rows = halo ? tw * (th + 2) : tw * th;  // rows the A box delivers (expect_tx); the tile itself is tw*th
   p.tiles_x = (W + tw - 1) / tw;
   p.tiles_y = (H + th - 1) / th;
   p.H = H;
@@ -242,13 +243,16 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
   p.stats = reinterpret_cast<float2*>(stats);
   p.ragged = (H % th != 0 || W % tw != 0) ? 1 : 0;
   p.err = err;
+  // N tile: 64 when the width is not a multiple of 128; 256 on request (flags bit 1) when it divides the width —
+  // a 128 x 256 tile reads 96 B/clk of operands from shared memory per MMA instead of 128 B/clk (the SM's limit).
   const int width = out_mode == 1 ? cout : N;
-  const int bn = (width % 128 == 0) ? 128 : 64;
+  int bn = (width % 128 == 0) ? 128 : 64;
+  if ((flags & 2) && width % 256 == 0 && !halo) bn = 256;
 
   CUtensorMap mapA, mapB, mapO;
   int rc;
   if (mode == 2) rc = make_up2_map(&mapA, A, a_ld, ka, W, H, n_img, tw, th);
-  else rc = make_nhwc_map(&mapA, A, a_ld, ka, W, H, n_img, tw, th);
+  else rc = make_nhwc_map(&mapA, A, a_ld, ka, W, H, n_img, tw, halo ? th + 2 : th);
   if (rc) return rc;
   {
     const uint64_t ktot = static_cast<uint64_t>(p.taps) * ka;
@@ -261,7 +265,7 @@ int b200cd_conv_gemm(int mode, int out_mode, const void* A, int64_t a_ld, int n_
   else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);
   if (rc) return rc;
   const int num_tiles = n_img * p.tiles_x * p.tiles_y;
-  CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
+  CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, halo, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -343,22 +347,23 @@ int b200cd_bn_stats(const float* partial, int ld, int C, int tiles_per_group, in
 
 int b200cd_bn_apply(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
                     int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
-                    void* dif, int64_t ld_d, void* stream) {
+                    void* dif, int64_t ld_d, void* pool_idx, void* stream) {
   if (C % 8 != 0 || n_img % G != 0 || (diff && (n_img % 2 != 0 || G != 2)))
     return fail(B200CD_ERR_SHAPE, "bn_apply: bad C/G/diff combination");
   if (ld_r % 8 || (a && ld_a % 8) || (a2 && ld_a2 % 8) || (pool && ld_p % 8) || (dif && ld_d % 8))
     return fail(B200CD_ERR_ALIGN, "bn_apply: ld must be a multiple of 8");
   if (!aligned16(r) || !aligned16(a) || !aligned16(a2) || !aligned16(pool) || !aligned16(dif))
     return fail(B200CD_ERR_ALIGN, "bn_apply: pointers must be 16-byte aligned");
+  if (pool_idx != nullptr && (pool == nullptr || (reinterpret_cast<uintptr_t>(pool_idx) & 7u)))
+    return fail(B200CD_ERR_ALIGN, "bn_apply: pool_idx needs pool and 8-byte alignment");
   CUDA_TRY(b200cd::launch_bn_apply(r, ld_r, scale, shift, n_img, H, W, C, G, diff, a, ld_a, a2, ld_a2, pool, ld_p, dif,
-                                   ld_d, reinterpret_cast<cudaStream_t>(stream)));
+                                   ld_d, pool_idx, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
 size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G) {
   if (!chan_ok(C) || G <= 0 || n_img % G != 0) return 0;
-  const int a = bn_bwd_nblk(n_img, H, W, C, G, false), b = bn_bwd_nblk(n_img, H, W, C, G, true);
-  return static_cast<size_t>(2) * G * C * ((a > b ? a : b) + 1);
+  return static_cast<size_t>(2) * G * C * (bn_bwd_nblk(n_img, H, W, C, G) + 1);
 }
 
 int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
@@ -369,7 +374,7 @@ int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* i
   if (ld_r % 8 || ld_dr % 8 || !aligned16(r) || !aligned16(dr)) return fail(B200CD_ERR_ALIGN, "bn_bwd: alignment");
   b200cd::GradSrcs gs;
   memset(&gs, 0, sizeof(gs));
-  bool pool = false;
+  if (static_cast<long long>(n_img) * H * W >= (1ll << 31)) return fail(B200CD_ERR_SHAPE, "bn_bwd: more than 2^31 pixels");
   for (int i = 0; i < 3; ++i) {
     gs.s[i].kind = srcs[i].kind;
     gs.s[i].ptr = srcs[i].ptr;
@@ -381,10 +386,11 @@ int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* i
     if (srcs[i].kind < 0 || srcs[i].kind > 3) return fail(B200CD_ERR_SHAPE, "bn_bwd: bad gradient source kind");
     if ((srcs[i].kind == 1 || srcs[i].kind == 2) && (srcs[i].ld % 8 != 0 || !aligned16(srcs[i].ptr)))
       return fail(B200CD_ERR_ALIGN, "bn_bwd: gradient source %d alignment", i);
-    pool = pool || srcs[i].kind == 2;
+    if (srcs[i].kind == 2 && srcs[i].w == nullptr)
+      return fail(B200CD_ERR_SHAPE, "bn_bwd: a max-pool source needs the arg-max index tensor in .w");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nblk = bn_bwd_nblk(n_img, H, W, C, G, pool);
+  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
   float* partial = ws;
   float* coefA = ws + static_cast<size_t>(2) * G * C * nblk;
   float* coefB = coefA + static_cast<size_t>(G) * C;

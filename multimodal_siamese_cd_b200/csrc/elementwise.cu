@@ -258,6 +258,7 @@ struct ApplyArgs {
   int n_img, H, W, C, G, diff;
   __nv_bfloat16 *a, *a2, *pool, *dif;
   long long ld_a, ld_a2, ld_p, ld_d;
+  unsigned char* pidx;  // optional [n][H/2][W/2][C]: position (0..3) of the window maximum, for the backward routing
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
@@ -313,6 +314,25 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
       if (p.pool && full) {
         const long long ppix = (static_cast<long long>(nn) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
         *reinterpret_cast<uint4*>(p.pool + ppix * p.ld_p + c) = pack8(amax[rep]);
+        if (p.pidx) {
+          // first maximum in row-major order of the STORED (bf16) activations, as ATen's max_pool2d_with_indices
+          unsigned long long packed = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int arg = 0;
+            float best = round_bf16(av[rep][0][j]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+              const float v = round_bf16(av[rep][k][j]);
+              if (v > best) {
+                best = v;
+                arg = k;
+              }
+            }
+            packed |= static_cast<unsigned long long>(arg) << (8 * j);
+          }
+          *reinterpret_cast<unsigned long long*>(p.pidx + ppix * p.C + c) = packed;
+        }
       }
     }
     if (p.diff && p.dif) {
@@ -383,11 +403,10 @@ __global__ void __launch_bounds__(256, 4) bn_apply_px_kernel(const ApplyArgs p) 
 //                    coefficients of pass 2:  A = -scale*m2*invstd,  B = scale*(m2*mean*invstd - m1)
 //                    with m1 = S1/N, m2 = sum(dy*xhat)/N
 //   pass 2 (dx):     dr = scale*dy + r*A + B      (= scale*(dy - m1 - xhat*m2)), stored bf16
-// Gradient sources are gathered on the fly (skip connections with sign, max-pool routing, 1x1 head), so
-// neither the summed gradient nor the ReLU mask nor the post-BN activation is ever materialised.
-// Two thread mappings: per pixel (no max-pool source) and per 2x2 window (max-pool routing needs the
-// four activations of the window). A thread keeps its 8 channels for its whole pixel range, so the
-// per-channel constants live in registers.
+// Gradient sources are gathered on the fly (skip connections with sign, max-pool routing through the
+// stored arg-max index, 1x1 head), so neither the summed gradient nor the ReLU mask nor the post-BN
+// activation is ever materialised. A thread keeps its 8 channels for its whole pixel range (per-channel
+// constants live in registers) and handles 4 pixels per iteration (independent 16-byte loads in flight).
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
   const __nv_bfloat16* r;
@@ -397,28 +416,43 @@ struct BwdArgs {
   int n_img, H, W, C, G;
 };
 
-// sum of the direct (kind 1) and head (kind 3) sources at pixel `pix` (index inside image n) -> dy[8]
-__device__ __forceinline__ void gather_px(const BwdArgs& p, int n, long long pix, long long hw, int c, float (&dy)[8]) {
+// sum of the gradient sources at global pixel `gpix` (= n*H*W + y*W + x) -> dy[8] (unmasked)
+__device__ __forceinline__ void gather_px(const BwdArgs& p, int gpix, int hw, int c, float (&dy)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) dy[j] = 0.f;
 #pragma unroll
   for (int si = 0; si < 3; ++si) {
     const GradSrc& s = p.srcs.s[si];
-    if (s.kind != 1 && s.kind != 3) continue;
-    int ns = n;
+    if (s.kind == 0) continue;
+    int sp = gpix;  // pixel index in the source tensor
     float scale = 1.f;
     if (s.n_mod > 0) {
+      const int n = gpix / hw;
       scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
-      ns = n % s.n_mod;
+      sp = gpix - (n - n % s.n_mod) * hw;
     }
-    const long long gp = static_cast<long long>(ns) * hw + pix;
     if (s.kind == 1) {
       float gv[8];
-      unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + gp * s.ld + c), gv);
+      unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + static_cast<long long>(sp) * s.ld + c), gv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dy[j] = fmaf(scale, gv[j], dy[j]);
+    } else if (s.kind == 2) {
+      const int n = sp / hw, pix = sp - n * hw;
+      const int y = pix / p.W, x = pix - y * p.W;
+      const int H2 = p.H >> 1, W2 = p.W >> 1;
+      if ((y >> 1) < H2 && (x >> 1) < W2) {  // MaxPool2d floors: the last odd row/column feeds no window
+        const long long pp = (static_cast<long long>(n) * H2 + (y >> 1)) * W2 + (x >> 1);
+        const unsigned long long idx =
+            __ldg(reinterpret_cast<const unsigned long long*>(reinterpret_cast<const unsigned char*>(s.w) + pp * p.C + c));
+        float gv[8];
+        unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + pp * s.ld + c), gv);
+        const unsigned me = ((y & 1) << 1) | (x & 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dy[j] += (((idx >> (8 * j)) & 0xffull) == me) ? scale * gv[j] : 0.f;
+      }
     } else {
-      const float d = scale * __ldg(reinterpret_cast<const float*>(s.ptr) + gp);
+      const float d = scale * __ldg(reinterpret_cast<const float*>(s.ptr) + sp);
       float wv[8];
       load8f(s.w + c, wv);
 #pragma unroll
@@ -427,80 +461,84 @@ __device__ __forceinline__ void gather_px(const BwdArgs& p, int n, long long pix
   }
 }
 
-// max-pool source(s): add the pooled gradient to the arg-max element of the window (first maximum in row-major
-// order on the bf16-rounded activations, as ATen's max_pool2d_with_indices on the stored tensor).
-__device__ __forceinline__ void route_pool(const BwdArgs& p, int n, int y2, int x2, int c, const float (&aq)[4][8],
-                                           float (&dy)[4][8]) {
+constexpr int kBwdUnroll = 4;
+
+// The same for kBwdUnroll pixels at once, source by source, with all loads of a source issued before any is used
+// (memory-level parallelism: the kernels are pure streaming).
+__device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)[kBwdUnroll], int hw, int c,
+                                             float (&dy)[kBwdUnroll][8]) {
+#pragma unroll
+  for (int u = 0; u < kBwdUnroll; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dy[u][j] = 0.f;
 #pragma unroll
   for (int si = 0; si < 3; ++si) {
     const GradSrc& s = p.srcs.s[si];
-    if (s.kind != 2) continue;
-    int ns = n;
-    float scale = 1.f;
-    if (s.n_mod > 0) {
-      scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
-      ns = n % s.n_mod;
+    if (s.kind == 0) continue;
+    int sp[kBwdUnroll];
+    float scale[kBwdUnroll];
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      sp[u] = gpix[u];
+      scale[u] = 1.f;
+      if (s.n_mod > 0) {
+        const int n = gpix[u] / hw;
+        scale[u] = n < s.n_mod ? s.scale_lo : s.scale_hi;
+        sp[u] = gpix[u] - (n - n % s.n_mod) * hw;
+      }
     }
-    const long long ppix = (static_cast<long long>(ns) * (p.H >> 1) + y2) * (p.W >> 1) + x2;
-    float gv[8];
-    unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + ppix * s.ld + c), gv);
+    if (s.kind == 1) {
+      uint4 g[kBwdUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int arg = 0;
-      float best = aq[0][j];
+      for (int u = 0; u < kBwdUnroll; ++u)
+        g[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + static_cast<long long>(sp[u]) * s.ld + c);
 #pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (aq[k][j] > best) {
-          best = aq[k][j];
-          arg = k;
-        }
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        float gv[8];
+        unpack8(g[u], gv);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dy[k][j] += (k == arg) ? scale * gv[j] : 0.f;
-    }
-  }
-}
-
-// Loads the window's r values, gathers + masks dy. Returns validity of the 4 pixels.
-__device__ __forceinline__ void window_dy(const BwdArgs& p, int n, int y2, int x2, int c, const float (&sc)[8],
-                                          const float (&sh)[8], float (&rv)[4][8], float (&dy)[4][8],
-                                          bool (&valid)[4]) {
-  const long long hw = static_cast<long long>(p.H) * p.W;
-  float aq[4][8];
-  bool pos[4][8];
+        for (int j = 0; j < 8; ++j) dy[u][j] = fmaf(scale[u], gv[j], dy[u][j]);
+      }
+    } else if (s.kind == 2) {
+      const int H2 = p.H >> 1, W2 = p.W >> 1;
+      uint4 g[kBwdUnroll];
+      unsigned long long idx[kBwdUnroll];
+      unsigned me[kBwdUnroll];
+      bool in[kBwdUnroll];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-    valid[k] = (y < p.H) && (x < p.W);
-    if (valid[k]) {
-      const long long pix = static_cast<long long>(y) * p.W + x;
-      unpack8(ldg16(p.r + (static_cast<long long>(n) * hw + pix) * p.ld_r + c), rv[k]);
-      gather_px(p, n, pix, hw, c, dy[k]);
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const int n = sp[u] / hw, pix = sp[u] - n * hw;
+        const int y = pix / p.W, x = pix - y * p.W;
+        in[u] = (y >> 1) < H2 && (x >> 1) < W2;  // MaxPool2d floors: the last odd row/column feeds no window
+        const long long pp = in[u] ? (static_cast<long long>(n) * H2 + (y >> 1)) * W2 + (x >> 1) : 0;
+        me[u] = ((y & 1) << 1) | (x & 1);
+        idx[u] = __ldg(reinterpret_cast<const unsigned long long*>(reinterpret_cast<const unsigned char*>(s.w) + pp * p.C + c));
+        g[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + pp * s.ld + c);
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float yv = fmaf(rv[k][j], sc[j], sh[j]);  // bit-identical to the forward apply kernel
-        pos[k][j] = yv > 0.f;
-        aq[k][j] = round_bf16(fmaxf(yv, 0.f));
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        float gv[8];
+        unpack8(g[u], gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dy[u][j] += (in[u] && ((idx[u] >> (8 * j)) & 0xffull) == me[u]) ? scale[u] * gv[j] : 0.f;
       }
     } else {
+      float d[kBwdUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        rv[k][j] = 0.f;
-        dy[k][j] = 0.f;
-        aq[k][j] = 0.f;
-        pos[k][j] = false;
-      }
+      for (int u = 0; u < kBwdUnroll; ++u) d[u] = scale[u] * __ldg(reinterpret_cast<const float*>(s.ptr) + sp[u]);
+      float wv[8];
+      load8f(s.w + c, wv);
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[u][j] = fmaf(d[u], wv[j], dy[u][j]);
     }
   }
-  if (valid[3]) route_pool(p, n, y2, x2, c, aq, dy);  // complete windows only (MaxPool2d floors)
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dy[k][j] = pos[k][j] ? dy[k][j] : 0.f;
 }
 
-// grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) lanes over pixels / windows
-template <bool POOL>
-__global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
+// grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) pixel lanes
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
   extern __shared__ float shred[];  // [lanes][C][2]
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
@@ -508,64 +546,49 @@ __global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_reduce_kernel(const 
   const int l = threadIdx.x / cvecs;
   const int g = blockIdx.y;
   const int c = cv << 3;
-  const int per_group = p.n_img / p.G;
+  const int hw = p.H * p.W;
+  const int npx = (p.n_img / p.G) * hw;
+  const int gbase = g * npx;
+  const int pb = static_cast<int>(static_cast<long long>(npx) * blockIdx.x / gridDim.x);
+  const int pe = static_cast<int>(static_cast<long long>(npx) * (blockIdx.x + 1) / gridDim.x);
   float sc[8], sh[8], s1[8], s2[8];
   load8f(p.scale + g * p.C + c, sc);
   load8f(p.shift + g * p.C + c, sh);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  if (POOL) {
-    const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
-    const long long wins = static_cast<long long>(per_group) * H2 * W2;
-    const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
-    for (long long w = wb + l; w < we; w += lanes) {
-      const int x2 = static_cast<int>(w % W2);
-      const int y2 = static_cast<int>((w / W2) % H2);
-      const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
-      float rv[4][8], dy[4][8];
-      bool valid[4];
-      window_dy(p, n, y2, x2, c, sc, sh, rv, dy, valid);
+  const __nv_bfloat16* rbase = p.r + static_cast<long long>(gbase) * p.ld_r + c;
+  int i = pb + l;
+  for (; i + (kBwdUnroll - 1) * lanes < pe; i += kBwdUnroll * lanes) {
+    uint4 rr[kBwdUnroll];
+    int gp[kBwdUnroll];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += dy[k][j];
-          s2[j] = fmaf(dy[k][j], rv[k][j], s2[j]);
-        }
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      rr[u] = ldg16(rbase + static_cast<long long>(i + u * lanes) * p.ld_r);
+      gp[u] = gbase + i + u * lanes;
     }
-  } else {
-    const long long hw = static_cast<long long>(p.H) * p.W;
-    const long long npx = static_cast<long long>(per_group) * hw;
-    const long long pb = npx * blockIdx.x / gridDim.x, pe = npx * (blockIdx.x + 1) / gridDim.x;
-    const __nv_bfloat16* rbase = p.r + static_cast<long long>(g) * per_group * hw * p.ld_r + c;
-    long long i = pb + l;
-    // two pixels per iteration: both r loads and both source gathers are independent -> more loads in flight
-    for (; i + lanes < pe; i += 2 * lanes) {
-      const long long i1 = i + lanes;
-      const uint4 r0 = ldg16(rbase + i * p.ld_r), r1 = ldg16(rbase + i1 * p.ld_r);
-      float d0[8], d1[8], v0[8], v1[8];
-      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
-      gather_px(p, g * per_group + static_cast<int>(i1 / hw), i1 % hw, hw, c, d1);
-      unpack8(r0, v0);
-      unpack8(r1, v1);
+    float d[kBwdUnroll][8];
+    gather_multi(p, gp, hw, c, d);
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      float v[8];
+      unpack8(rr[u], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-        const float m1 = fmaf(v1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
-        s1[j] += m0 + m1;
-        s2[j] = fmaf(m0, v0[j], fmaf(m1, v1[j], s2[j]));
+        const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[u][j] : 0.f;
+        s1[j] += m;
+        s2[j] = fmaf(m, v[j], s2[j]);
       }
     }
-    for (; i < pe; i += lanes) {
-      float d0[8], v0[8];
-      unpack8(ldg16(rbase + i * p.ld_r), v0);
-      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+  }
+  for (; i < pe; i += lanes) {
+    float d[8], v[8];
+    unpack8(ldg16(rbase + static_cast<long long>(i) * p.ld_r), v);
+    gather_px(p, gbase + i, hw, c, d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-        s1[j] += m0;
-        s2[j] = fmaf(m0, v0[j], s2[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+      s1[j] += m;
+      s2[j] = fmaf(m, v[j], s2[j]);
     }
   }
 #pragma unroll
@@ -576,9 +599,9 @@ __global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_reduce_kernel(const 
   __syncthreads();
   for (int ch = threadIdx.x; ch < p.C; ch += 256) {
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < lanes; ++i) {
-      a += shred[(i * p.C + ch) * 2];
-      b += shred[(i * p.C + ch) * 2 + 1];
+    for (int k = 0; k < lanes; ++k) {
+      a += shred[(k * p.C + ch) * 2];
+      b += shred[(k * p.C + ch) * 2 + 1];
     }
     float* o = partial + ((static_cast<long long>(g) * gridDim.x + blockIdx.x) * p.C + ch) * 2;
     o[0] = a;
@@ -612,8 +635,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   dbeta[c] = static_cast<float>(tb);
 }
 
-template <bool POOL>
-__global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
+__global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
                                                            const float* __restrict__ coefB,
                                                            __nv_bfloat16* __restrict__ dr, long long ld_dr) {
   const int cvecs = p.C >> 3;
@@ -622,71 +644,51 @@ __global__ void __launch_bounds__(256, POOL ? 1 : 2) bn_bwd_dx_kernel(const BwdA
   const int l = threadIdx.x / cvecs;
   const int g = blockIdx.y;
   const int c = cv << 3;
-  const int per_group = p.n_img / p.G;
+  const int hw = p.H * p.W;
+  const int npx = (p.n_img / p.G) * hw;
+  const int gbase = g * npx;
+  const int pb = static_cast<int>(static_cast<long long>(npx) * blockIdx.x / gridDim.x);
+  const int pe = static_cast<int>(static_cast<long long>(npx) * (blockIdx.x + 1) / gridDim.x);
   float sc[8], sh[8], ca[8], cb[8];
   load8f(p.scale + g * p.C + c, sc);
   load8f(p.shift + g * p.C + c, sh);
   load8f(coefA + g * p.C + c, ca);
   load8f(coefB + g * p.C + c, cb);
-  const long long hw = static_cast<long long>(p.H) * p.W;
-  if (POOL) {
-    const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
-    const long long wins = static_cast<long long>(per_group) * H2 * W2;
-    const long long wb = wins * blockIdx.x / gridDim.x, we = wins * (blockIdx.x + 1) / gridDim.x;
-    for (long long w = wb + l; w < we; w += lanes) {
-      const int x2 = static_cast<int>(w % W2);
-      const int y2 = static_cast<int>((w / W2) % H2);
-      const int n = g * per_group + static_cast<int>(w / (static_cast<long long>(W2) * H2));
-      float rv[4][8], dy[4][8];
-      bool valid[4];
-      window_dy(p, n, y2, x2, c, sc, sh, rv, dy, valid);
+  const __nv_bfloat16* rbase = p.r + static_cast<long long>(gbase) * p.ld_r + c;
+  __nv_bfloat16* obase = dr + static_cast<long long>(gbase) * ld_dr + c;
+  int i = pb + l;
+  for (; i + (kBwdUnroll - 1) * lanes < pe; i += kBwdUnroll * lanes) {
+    uint4 rr[kBwdUnroll];
+    int gp[kBwdUnroll];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!valid[k]) continue;
-        const int y = 2 * y2 + (k >> 1), x = 2 * x2 + (k & 1);
-        const long long pix = static_cast<long long>(n) * hw + static_cast<long long>(y) * p.W + x;
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], dy[k][j], fmaf(rv[k][j], ca[j], cb[j]));
-        *reinterpret_cast<uint4*>(dr + pix * ld_dr + c) = pack8(o);
-      }
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      rr[u] = ldg16(rbase + static_cast<long long>(i + u * lanes) * p.ld_r);
+      gp[u] = gbase + i + u * lanes;
     }
-  } else {
-    const long long npx = static_cast<long long>(per_group) * hw;
-    const long long pb = npx * blockIdx.x / gridDim.x, pe = npx * (blockIdx.x + 1) / gridDim.x;
-    const long long base = static_cast<long long>(g) * per_group * hw;
-    const __nv_bfloat16* rbase = p.r + base * p.ld_r + c;
-    __nv_bfloat16* obase = dr + base * ld_dr + c;
-    long long i = pb + l;
-    for (; i + lanes < pe; i += 2 * lanes) {
-      const long long i1 = i + lanes;
-      const uint4 r0 = ldg16(rbase + i * p.ld_r), r1 = ldg16(rbase + i1 * p.ld_r);
-      float d0[8], d1[8], v0[8], v1[8], o0[8], o1[8];
-      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
-      gather_px(p, g * per_group + static_cast<int>(i1 / hw), i1 % hw, hw, c, d1);
-      unpack8(r0, v0);
-      unpack8(r1, v1);
+    float d[kBwdUnroll][8];
+    gather_multi(p, gp, hw, c, d);
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      float v[8], o[8];
+      unpack8(rr[u], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-        const float m1 = fmaf(v1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
-        o0[j] = fmaf(sc[j], m0, fmaf(v0[j], ca[j], cb[j]));
-        o1[j] = fmaf(sc[j], m1, fmaf(v1[j], ca[j], cb[j]));
+        const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[u][j] : 0.f;
+        o[j] = fmaf(sc[j], m, fmaf(v[j], ca[j], cb[j]));
       }
-      *reinterpret_cast<uint4*>(obase + i * ld_dr) = pack8(o0);
-      *reinterpret_cast<uint4*>(obase + i1 * ld_dr) = pack8(o1);
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(i + u * lanes) * ld_dr) = pack8(o);
     }
-    for (; i < pe; i += lanes) {
-      float d0[8], v0[8], o0[8];
-      unpack8(ldg16(rbase + i * p.ld_r), v0);
-      gather_px(p, g * per_group + static_cast<int>(i / hw), i % hw, hw, c, d0);
+  }
+  for (; i < pe; i += lanes) {
+    float d[8], v[8], o[8];
+    unpack8(ldg16(rbase + static_cast<long long>(i) * p.ld_r), v);
+    gather_px(p, gbase + i, hw, c, d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float m0 = fmaf(v0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-        o0[j] = fmaf(sc[j], m0, fmaf(v0[j], ca[j], cb[j]));
-      }
-      *reinterpret_cast<uint4*>(obase + i * ld_dr) = pack8(o0);
+    for (int j = 0; j < 8; ++j) {
+      const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+      o[j] = fmaf(sc[j], m, fmaf(v[j], ca[j], cb[j]));
     }
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(i) * ld_dr) = pack8(o);
   }
 }
 
@@ -983,7 +985,7 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
 
 cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
                             int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
-                            void* pool, long long ld_p, void* dif, long long ld_d, cudaStream_t st) {
+                            void* pool, long long ld_p, void* dif, long long ld_d, void* pool_idx, cudaStream_t st) {
   ApplyArgs p;
   p.r = reinterpret_cast<const __nv_bfloat16*>(r);
   p.ld_r = ld_r;
@@ -995,6 +997,7 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
   p.pool = reinterpret_cast<__nv_bfloat16*>(pool);
   p.dif = reinterpret_cast<__nv_bfloat16*>(dif);
   p.ld_a = ld_a; p.ld_a2 = ld_a2; p.ld_p = ld_p; p.ld_d = ld_d;
+  p.pidx = reinterpret_cast<unsigned char*>(pool_idx);
   if (!diff && pool == nullptr && C % 64 == 0 && 256 % (C / 8) == 0) {
     const long long npx = static_cast<long long>(n_img / G) * H * W;
     long long nblk = npx / ((256 / (C / 8)) * 16);
@@ -1019,8 +1022,6 @@ static BwdArgs make_bwd_args(const void* r, long long ld_r, const float* scale, 
   return p;
 }
 
-static bool has_pool_src(const GradSrcs& s) { return s.s[0].kind == 2 || s.s[1].kind == 2 || s.s[2].kind == 2; }
-
 cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* scale, const float* shift,
                                  const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk, float* partial,
                                  cudaStream_t st) {
@@ -1028,8 +1029,7 @@ cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* sca
   const int lanes = 256 / (C / 8);
   const size_t smem = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
   dim3 grid(nblk, G);
-  if (has_pool_src(srcs)) bn_bwd_reduce_kernel<true><<<grid, 256, smem, st>>>(p, partial);
-  else bn_bwd_reduce_kernel<false><<<grid, 256, smem, st>>>(p, partial);
+  bn_bwd_reduce_kernel<<<grid, 256, smem, st>>>(p, partial);
   return cudaGetLastError();
 }
 
@@ -1046,10 +1046,7 @@ cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, 
                              void* dr, long long ld_dr, cudaStream_t st) {
   const BwdArgs p = make_bwd_args(r, ld_r, scale, shift, srcs, n_img, H, W, C, G);
   dim3 grid(nblk, G);
-  if (has_pool_src(srcs))
-    bn_bwd_dx_kernel<true><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
-  else
-    bn_bwd_dx_kernel<false><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
+  bn_bwd_dx_kernel<<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
   return cudaGetLastError();
 }
 

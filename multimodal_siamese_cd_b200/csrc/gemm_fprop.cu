@@ -24,10 +24,16 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
-template <int BN, int STAGES>
+// HALO (3x3 mode only): one stage = one kx and one 64-channel chunk; the A box carries a halo row above and below
+// the tile (th+2 rows, <= 160 rows = 20 KB) and serves the three ky taps as address offsets of ky*tw rows (whole
+// 1024-byte swizzle atoms, tw % 8 == 0), so A crosses L2 -> SM 3.6 times per output tile instead of 9; B = three
+// weight tiles (one per ky).
+template <int BN, int STAGES, bool HALO>
 struct FpropSmem {
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kABuf = HALO ? 160 * 128 : kABytes;
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kBBytes = (HALO ? 3 : 1) * kBTile;
+  static constexpr int kStageBytes = kABuf + kBBytes;
   static constexpr int kBarOff = STAGES * kStageBytes;
   static constexpr int kTmemSlotOff = kBarOff + 8 * (2 * STAGES + 1);
   static constexpr int kBiasOff = kTmemSlotOff + 16;
@@ -36,12 +42,12 @@ struct FpropSmem {
   static constexpr int kDynamic = kTotal + 1024;  // slack for the manual 1024-byte alignment
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool HALO>
 __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__ CUtensorMap mapA,
                                                          const __grid_constant__ CUtensorMap mapB,
                                                          const __grid_constant__ CUtensorMap mapO,
                                                          const FpropParams p) {
-  using L = FpropSmem<BN, STAGES>;
+  using L = FpropSmem<BN, STAGES, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
   const int ty = (tile / p.tiles_x) % p.tiles_y;
   const int img = tile / (p.tiles_x * p.tiles_y);
   const int x0 = tx * p.tw, y0 = ty * p.th;
-  const int iters = p.taps * p.kchunks;
+  const int iters = (HALO ? 3 : p.taps) * p.kchunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -78,8 +84,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
     tmem_relinquish();
   }
   if (threadIdx.x >= 64) {
-    const int t = threadIdx.x - 64;
-    if (t < BN) {
+    for (int t = threadIdx.x - 64; t < BN; t += 128) {
       float b = 0.f;
       if (p.bias) b = p.bias[p.out_mode == 1 ? (n0 + t) % p.cout : (n0 + t)];
       bias_s[t] = b;
@@ -98,10 +103,17 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1, p.err, DEV_ERR_EMPTY_TIMEOUT);
         uint8_t* a_dst = smem + s * L::kStageBytes;
-        uint8_t* b_dst = a_dst + kABytes;
-        const int tap = it / p.kchunks;
+        uint8_t* b_dst = a_dst + L::kABuf;
+        const int tap = it / p.kchunks;  // HALO: tap == kx
         const int kc = it - tap * p.kchunks;
         mbar_arrive_expect_tx(&full[s], p.rows * 128 + L::kBBytes);
+        if (HALO) {
+          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + tap - 1, y0 - 1, img, 0);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+            tma_load_2d(b_dst + ky * L::kBTile, &mapB, &full[s], (ky * 3 + tap) * p.ka + kc * 64, n0);
+          continue;
+        }
         if (p.mode == 0) {
           const int ky = tap / 3, kx = tap - ky * 3;
           tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, img, 0);
@@ -124,13 +136,24 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
         mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
-        const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-        const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+        const uint32_t b_addr = a_addr + L::kABuf;
+        if (HALO) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row: +2 in the >>4 address field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t adesc = make_smem_desc(a_addr + ky * p.tw * 128, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(b_addr + ky * L::kBTile, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || ky > 0 || k > 0) ? 1u : 0u);
+          }
+        } else {
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row: +2 in the >>4 address field
+            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -150,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
       tmem_ld_wait();
       const int slab = (c32 * 32) >> 6;
       const int chunk0 = ((c32 * 32) & 63) >> 3;
-      uint8_t* row = stg + slab * kABytes + m * 128;
+      uint8_t* row = stg + slab * L::kABuf + m * 128;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         float f[8];
@@ -175,10 +198,10 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
       for (int slab = 0; slab < BN / 64; ++slab) {
         const int n = n0 + slab * 64;
         if (p.out_mode == 0) {
-          tma_store_5d(&mapO, stg + slab * kABytes, n, x0, y0, img, 0);
+          tma_store_5d(&mapO, stg + slab * L::kABuf, n, x0, y0, img, 0);
         } else {
           const int tap = n / p.cout, co = n - tap * p.cout;
-          tma_store_5d(&mapO, stg + slab * kABytes, co, tap & 1, x0, tap >> 1, img * p.H + y0);
+          tma_store_5d(&mapO, stg + slab * L::kABuf, co, tap & 1, x0, tap >> 1, img * p.H + y0);
         }
       }
       tma_store_commit();
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
       for (int slab = 0; slab < BN / 64; ++slab) {
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         for (int r = rq * 32; r < rq * 32 + 32; ++r) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + slab * kABytes + r * 128 +
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + slab * L::kABuf + r * 128 +
                                                                 (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
           float lo = bf16_lo(w), hi = bf16_hi(w);
           if (p.ragged) {
@@ -212,14 +235,14 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
         dst[3] = q1;
       }
       named_barrier_sync(2, 128);
-      if (t < BN) {
+      for (int ch = t; ch < BN; ch += 128) {
         float s = 0.f, qq = 0.f;
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
-          s += red[((r4 * BN) + t) * 2];
-          qq += red[((r4 * BN) + t) * 2 + 1];
+          s += red[((r4 * BN) + ch) * 2];
+          qq += red[((r4 * BN) + ch) * 2 + 1];
         }
-        p.stats[static_cast<size_t>(tile) * p.N + n0 + t] = make_float2(s, qq);
+        p.stats[static_cast<size_t>(tile) * p.N + n0 + ch] = make_float2(s, qq);
       }
     }
     if (t == 0) tma_store_wait_read0();
@@ -233,30 +256,36 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool HALO>
 cudaError_t launch_one(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                        const FpropParams& p, int num_tiles, cudaStream_t stream) {
-  using L = FpropSmem<BN, STAGES>;
+  using L = FpropSmem<BN, STAGES, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fprop_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(fprop_kernel<BN, STAGES, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::kDynamic);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid(num_tiles, p.N / BN, 1);
-  fprop_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, stream>>>(mapA, mapB, mapO, p);
+  fprop_kernel<BN, STAGES, HALO><<<grid, kThreads, L::kDynamic, stream>>>(mapA, mapB, mapO, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
-                         const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
-  // 3 stages of (16 KB A + BN*128 B) keep two CTAs resident per SM, so one CTA's epilogue overlaps the
-  // other's main loop.
-  if (bn == 128) return launch_one<128, 3>(mapA, mapB, mapO, p, num_tiles, stream);
-  if (bn == 64) return launch_one<64, 4>(mapA, mapB, mapO, p, num_tiles, stream);
+                         const FpropParams& p, int bn, int halo, int num_tiles, cudaStream_t stream) {
+  // Shared memory is sized so that two CTAs stay resident per SM where possible: one CTA's epilogue then overlaps
+  // the other's main loop.
+  if (halo) {
+    if (bn == 128) return launch_one<128, 3, true>(mapA, mapB, mapO, p, num_tiles, stream);  // 204 KB: 1 CTA / SM
+    if (bn == 64) return launch_one<64, 2, true>(mapA, mapB, mapO, p, num_tiles, stream);    // 88 KB: 2 CTAs / SM
+    return cudaErrorInvalidValue;
+  }
+  if (bn == 256) return launch_one<256, 4, false>(mapA, mapB, mapO, p, num_tiles, stream);  // 192 KB: 1 CTA / SM
+  if (bn == 128) return launch_one<128, 3, false>(mapA, mapB, mapO, p, num_tiles, stream);
+  if (bn == 64) return launch_one<64, 4, false>(mapA, mapB, mapO, p, num_tiles, stream);
   return cudaErrorInvalidValue;
 }
 

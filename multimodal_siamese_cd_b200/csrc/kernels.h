@@ -28,7 +28,7 @@ struct FpropParams {
   int* err;
 };
 cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
-                         const FpropParams& p, int bn, int num_tiles, cudaStream_t stream);
+                         const FpropParams& p, int bn, int halo, int num_tiles, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // G2: weight-gradient kernel. D_tap[m, n] = sum_pixels U[pixel, m] * V_tap[pixel, n]
@@ -54,7 +54,7 @@ cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const
 struct GradSrc {
   int kind;          // 0 none, 1 direct bf16 NHWC, 2 pooled bf16 (half resolution, routed to the arg-max), 3 head (dz*w)
   const void* ptr;   // bf16 tensor (kinds 1, 2) or fp32 dz[pixel] (kind 3)
-  const float* w;    // kind 3: 1x1 head weights for these channels
+  const float* w;    // kind 3: 1x1 head weights for these channels; kind 2: the uint8 arg-max index tensor
   long long ld;      // elements per pixel
   int n_mod;         // > 0: source image = n % n_mod, scale = (n < n_mod) ? scale_lo : scale_hi
   float scale_lo, scale_hi;
@@ -81,7 +81,7 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
                                float* scale, float* shift, cudaStream_t st);
 cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
                             int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
-                            void* pool, long long ld_p, void* dif, long long ld_d, cudaStream_t st);
+                            void* pool, long long ld_p, void* dif, long long ld_d, void* pool_idx, cudaStream_t st);
 cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* scale, const float* shift,
                                  const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk, float* partial,
                                  cudaStream_t st);

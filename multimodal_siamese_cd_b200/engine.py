@@ -230,11 +230,13 @@ class StepEngine:
         for lname, down in encoder.down_seq.items():
             pool = self._new(n_img, h // 2, w // 2, prev.cout)
             prev.outs["pool"] = pool
+            pidx = self._new(n_img, h // 2, w // 2, prev.cout, dtype=torch.uint8) if self.train else None
+            prev.outs["pool_idx"] = pidx
             h, w = h // 2, w // 2
             d1, d2 = self._double_conv(f"{tag}.{lname}", down.mpconv[1], pool, n_img, h, w, G)
             if self.train:
                 d1.d_in = self._new(n_img, h, w, prev.cout)  # gradient w.r.t. the pooled tensor
-                prev.srcs.append({"kind": 2, "t": d1.d_in})
+                prev.srcs.append({"kind": 2, "t": d1.d_in, "w": pidx})
             levels.append(d2)
             prev = d2
         return levels
@@ -425,7 +427,7 @@ class StepEngine:
                          bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
                          st.order_rev, st.mean, st.invstd, st.scale, st.shift)
             ops.bn_apply(st.r, st.scale, st.shift, st.G, bool(outs.get("diff", False)), a=outs.get("a"),
-                         a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"))
+                         a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"), pool_idx=outs.get("pool_idx"))
 
         eng.fwd_ops.append(run)
 

@@ -165,8 +165,13 @@ def conv_gemm_tiles(H: int, W: int) -> int:
     return _lib.load().b200cd_conv_gemm_tiles(H, W)
 
 
+FPROP_HALO_POLICY = "auto"  # 3x3 convs using the halo variant: "auto" (N % 128 != 0 or K-chunk count >= 8), "n64", "all", "none"
+FPROP_WIDE_TILES = True     # 128 x 256 output tiles where N % 256 == 0 and the halo variant is not used
+
+
 def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
-              bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> None:
+              bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+              halo: Optional[bool] = None, wide: Optional[bool] = None) -> None:
     """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x)."""
     _require_cuda(A, Bw, out)
     n, Ha, Wa, ka, a_ld = _nhwc(A)
@@ -181,10 +186,19 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
     else:
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
+    # tile policy (measured on B200, profiles/r01_probe_kernels_call7.json): 128x256 tiles where N % 256 == 0;
+    # otherwise the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)
+    if wide is None:
+        wide = FPROP_WIDE_TILES and N % 256 == 0 and halo is not True
+    if halo is None:
+        pol = FPROP_HALO_POLICY
+        halo = mode == 0 and not wide and (pol == "all" or (pol in ("n64", "auto") and N % 128 != 0) or
+                                           (pol == "auto" and ka >= 512))
+    flags = (1 if (halo and mode == 0) else 0) | (2 if wide else 0)
     _count(1)
     fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
-    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode}"):
-        _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode} halo{flags}"):
+        _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, flags, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
                                                 out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
 
@@ -235,7 +249,7 @@ def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group:
 
 def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, diff: bool,
              a: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
-             dif: Optional[torch.Tensor] = None) -> None:
+             dif: Optional[torch.Tensor] = None, pool_idx: Optional[torch.Tensor] = None) -> None:
     _require_cuda(r, scale, shift)
     n, H, W, Cc, ld_r = _nhwc(r)
 
@@ -247,7 +261,7 @@ def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, 
                f"{n}x{H}x{W}x{Cc} G{G} diff{int(diff)} pool{int(pool is not None)}"):
         _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
                                                int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool),
-                                               _ptr(dif), ld(dif), _stream()))
+                                               _ptr(dif), ld(dif), _ptr(pool_idx), _stream()))
 
 
 def make_srcs(srcs: Sequence[dict]) -> C.Array:
@@ -258,7 +272,7 @@ def make_srcs(srcs: Sequence[dict]) -> C.Array:
         t = s["t"]
         arr[i].kind = s["kind"]
         arr[i].ptr = t.data_ptr()
-        arr[i].w = s["w"].data_ptr() if s.get("w") is not None else None
+        arr[i].w = s["w"].data_ptr() if s.get("w") is not None else None   # head weights (3) / pool arg-max index (2)
         arr[i].ld = t.stride(2) if s["kind"] in (1, 2) else 0
         arr[i].n_mod = s.get("n_mod", 0)
         arr[i].scale_lo = s.get("scale_lo", 1.0)

@@ -110,7 +110,7 @@ def check_pack_input() -> dict:
 
 # ----------------------------------------------------------------------------------------------------
 def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, slice_out=False, seed=3,
-                  tol=6e-3) -> dict:
+                  tol=6e-3, halo=None, wide=None) -> dict:
     """conv_gemm mode 0 vs F.conv2d (fp32 math on the bf16-rounded operands); output is bf16 so the bound is
     one bf16 ulp (2^-8 relative) plus accumulation-order noise."""
     g = _gen(seed)
@@ -132,7 +132,7 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
     tiles = ops.conv_gemm_tiles(H, W)
     stats = torch.zeros(n * tiles, cout, 2, device=DEV)
     Bw = ops.pack_weights(0, w)
-    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats)
+    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats, halo=halo, wide=wide)
     ops.device_status()
     ref = F.conv2d(x, w, b, padding=1)
     res = err(nchw(out.float()), ref, bf16_out=True)
@@ -309,9 +309,14 @@ def check_bn_apply(n=4, H=16, W=32, Cc=64, seed=10) -> dict:
     a = torch.empty(n, H, W, Cc, device=DEV, dtype=torch.bfloat16)
     cat = torch.zeros(n // 2, H, W, 2 * Cc, device=DEV, dtype=torch.bfloat16)
     pool = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.bfloat16)
-    ops.bn_apply(r, scale, shift, G, True, a=a, pool=pool, dif=cat[..., :Cc])
+    pidx = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.uint8)
+    ops.bn_apply(r, scale, shift, G, True, a=a, pool=pool, dif=cat[..., :Cc], pool_idx=pidx)
     torch.cuda.synchronize()
     res = {}
+    # arg-max index: first maximum of the stored window in row-major order
+    win = a.float().view(n, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 5, 2, 4).reshape(n, H // 2, W // 2, Cc, 4)
+    res["pool_idx_ok"] = bool(torch.equal(pidx.long(), win.argmax(-1)) or
+                              torch.equal(win.gather(-1, pidx.long().unsqueeze(-1)).squeeze(-1), win.max(-1).values))
     bn = torch.nn.BatchNorm2d(Cc).to(DEV)
     with torch.no_grad():
         bn.weight.copy_(gamma)
@@ -329,7 +334,8 @@ def check_bn_apply(n=4, H=16, W=32, Cc=64, seed=10) -> dict:
     res["running_var"] = err(rv, bn.running_var)
     res["nbt"] = int(nbt.item())
     res["ok"] = (res["a"]["rel_l2"] < 4e-3 and res["pool"]["rel_l2"] < 4e-3 and res["diff"]["rel_l2"] < 6e-3 and
-                 res["running_mean"]["max_abs"] < 1e-5 and res["running_var"]["max_abs"] < 1e-4 and res["nbt"] == 2)
+                 res["running_mean"]["max_abs"] < 1e-5 and res["running_var"]["max_abs"] < 1e-4 and res["nbt"] == 2 and
+                 res["pool_idx_ok"])
     return res
 
 
@@ -343,9 +349,12 @@ def check_bn_bwd(n=4, H=16, W=32, Cc=64, seed=11) -> dict:
     d_pool = bf16r(torch.randn(n, H // 2, W // 2, Cc, device=DEV, generator=g))
     d_dir = bf16r(torch.randn(n, H, W, Cc, device=DEV, generator=g))
     d_skip_b = d_skip.to(torch.bfloat16)
+    pidx = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.uint8)
+    ops.bn_apply(r, scale, shift, G, False, pool=torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.bfloat16),
+                 pool_idx=pidx)
     srcs = ops.make_srcs([
         {"kind": 1, "t": d_skip_b[..., :Cc], "n_mod": h, "scale_lo": -1.0, "scale_hi": 1.0},
-        {"kind": 2, "t": d_pool.to(torch.bfloat16)},
+        {"kind": 2, "t": d_pool.to(torch.bfloat16), "w": pidx},
         {"kind": 1, "t": d_dir.to(torch.bfloat16)},
     ])
     ws = torch.empty(ops.bn_bwd_ws_floats(n, H, W, Cc, G), device=DEV)
@@ -537,6 +546,16 @@ ALL_CHECKS = {
     "conv3x3_ragged_8x8": lambda: check_conv3x3(3, 8, 8, 128, 128, seed=35),
     "conv3x3_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36),
     "conv3x3_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37),
+    "conv3x3_wide_128_256": lambda: check_conv3x3(2, 32, 32, 128, 256, seed=39, halo=False, wide=True),
+    "conv3x3_wide_slices_192_512": lambda: check_conv3x3(2, 16, 16, 192, 512, slice_in=True, slice_out=True, seed=40, halo=False, wide=True),
+    "conv3x3_narrow_128_256": lambda: check_conv3x3(2, 32, 32, 128, 256, seed=39, halo=False, wide=False),
+    "conv3x3_halo_64_64": lambda: check_conv3x3(2, 32, 32, 64, 64, halo=True),
+    "conv3x3_nohalo_64_64": lambda: check_conv3x3(2, 32, 32, 64, 64, halo=False),
+    "conv3x3_halo_128_128": lambda: check_conv3x3(2, 16, 16, 128, 128, seed=31, halo=True),
+    "conv3x3_halo_slices_192_256": lambda: check_conv3x3(2, 32, 32, 192, 256, slice_in=True, slice_out=True, seed=33, halo=True),
+    "conv3x3_halo_ragged_8x8": lambda: check_conv3x3(3, 8, 8, 128, 64, seed=38, halo=True),
+    "conv3x3_halo_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36, halo=True),
+    "conv3x3_halo_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37, halo=True),
     "conv3x3_dgrad": check_conv3x3_dgrad,
     "conv3x3_dgrad_ragged_8x8": lambda: check_conv3x3_dgrad(3, 8, 8, 128, 128, seed=42),
     "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),

@@ -48,6 +48,8 @@ def perf() -> dict:
         ("down4_512_512_16", 32, 16, 512, 512),
         ("up1a_128_64_256", 16, 256, 128, 64),
         ("up4a_1024_256_32", 16, 32, 1024, 256),
+        ("up2a_256_64_128", 16, 128, 256, 64),
+        ("down1a_64_128_128", 32, 128, 64, 128),
     ]
     for name, n, H, cin, cout in shapes:
         try:
@@ -57,9 +59,11 @@ def perf() -> dict:
             o = torch.empty(n, H, H, cout, device=dev, dtype=torch.bfloat16)
             tiles = ops.conv_gemm_tiles(H, H)
             stats = torch.empty(n * tiles, cout, 2, device=dev)
-            ms = time_fn(lambda: ops.conv_gemm(0, 0, A, Bw, o, stats=stats))
             flops = 2.0 * n * H * H * cout * cin * 9
-            rec = {"fprop_ms": ms, "fprop_tflops": flops / ms / 1e9}
+            rec = {}
+            for halo, wide in ((False, False), (True, False), (False, True)):
+                ms = time_fn(lambda: ops.conv_gemm(0, 0, A, Bw, o, stats=stats, halo=halo, wide=wide))
+                rec[f"fprop_halo{int(halo)}_wide{int(wide)}_tflops"] = flops / ms / 1e9
             dr = torch.randn(n, H, H, cout, device=dev).to(torch.bfloat16)
             total = ops.wgrad_tiles(n, H, H)
             for halo in (0, 1):
