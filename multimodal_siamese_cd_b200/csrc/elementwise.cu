@@ -609,30 +609,50 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, 
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int G, double count,
-                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                       const float* __restrict__ scale, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coefA, float* __restrict__ coefB) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 32 channels x 32 lanes: the lanes split the per-block partials, then a fixed-order tree in shared memory
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int G,
+                                                             double count, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd,
+                                                             const float* __restrict__ scale, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, float* __restrict__ coefA,
+                                                             float* __restrict__ coefB) {
+  __shared__ double sh[32][33][2];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double tg = 0.0, tb = 0.0;
   for (int g = 0; g < G; ++g) {
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nblk; ++i) {
-      const float* o = partial + ((static_cast<long long>(g) * nblk + i) * C + c) * 2;
-      s1 += o[0];
-      s2 += o[1];
+    if (c < C) {
+      for (int i = ly; i < nblk; i += 32) {
+        const float2 o = __ldg(reinterpret_cast<const float2*>(partial + ((static_cast<long long>(g) * nblk + i) * C + c) * 2));
+        s1 += o.x;
+        s2 += o.y;
+      }
     }
-    const double mu = mean[g * C + c], is = invstd[g * C + c], sc = scale[g * C + c];
-    const double sdyx = is * (s2 - mu * s1);  // sum dy * xhat
-    const double m1 = s1 / count, m2 = sdyx / count;
-    coefA[g * C + c] = static_cast<float>(-sc * m2 * is);
-    coefB[g * C + c] = static_cast<float>(sc * (m2 * mu * is - m1));
-    tb += s1;
-    tg += sdyx;
+    sh[ly][cx][0] = s1;
+    sh[ly][cx][1] = s2;
+    __syncthreads();
+    if (ly == 0 && c < C) {
+      s1 = 0.0;
+      s2 = 0.0;
+      for (int k = 0; k < 32; ++k) {
+        s1 += sh[k][cx][0];
+        s2 += sh[k][cx][1];
+      }
+      const double mu = mean[g * C + c], is = invstd[g * C + c], sc = scale[g * C + c];
+      const double sdyx = is * (s2 - mu * s1);  // sum dy * xhat
+      const double m1 = s1 / count, m2 = sdyx / count;
+      coefA[g * C + c] = static_cast<float>(-sc * m2 * is);
+      coefB[g * C + c] = static_cast<float>(sc * (m2 * mu * is - m1));
+      tb += s1;
+      tg += sdyx;
+    }
+    __syncthreads();
   }
-  dgamma[c] = static_cast<float>(tg);
-  dbeta[c] = static_cast<float>(tb);
+  if (ly == 0 && c < C) {
+    dgamma[c] = static_cast<float>(tg);
+    dbeta[c] = static_cast<float>(tb);
+  }
 }
 
 __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
@@ -775,12 +795,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   }
 }
 
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
+                                                             float* __restrict__ out) {
+  __shared__ double sh[32][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double a = 0.0;
-  for (int i = 0; i < nblk; ++i) a += partial[static_cast<long long>(i) * C + c];
-  out[c] = static_cast<float>(a);
+  if (c < C)
+    for (int i = ly; i < nblk; i += 32) a += partial[static_cast<long long>(i) * C + c];
+  sh[ly][cx] = a;
+  __syncthreads();
+  if (ly == 0 && c < C) {
+    a = 0.0;
+    for (int k = 0; k < 32; ++k) a += sh[k][cx];
+    out[c] = static_cast<float>(a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -808,9 +837,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, lo
     src = static_cast<long long>(a) * ld1 + k;
     dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
   }
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += ws[static_cast<long long>(s) * split_stride + src];
-  grad[dst] = acc;
+  // fixed summation order (deterministic); four independent chains keep several loads in flight
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* q = ws + src;
+  int sp = 0;
+#pragma unroll 2
+  for (; sp + 3 < splits; sp += 4) {
+    a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
+    a1 += __ldg(q + static_cast<long long>(sp + 1) * split_stride);
+    a2 += __ldg(q + static_cast<long long>(sp + 2) * split_stride);
+    a3 += __ldg(q + static_cast<long long>(sp + 3) * split_stride);
+  }
+  for (; sp < splits; ++sp) a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
+  grad[dst] = (a0 + a1) + (a2 + a3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1036,8 +1075,8 @@ cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* sca
 cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, const float* mean,
                                    const float* invstd, const float* scale, float* dgamma, float* dbeta, float* coefA,
                                    float* coefB, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta,
-                                                          coefA, coefB);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta,
+                                                         coefA, coefB);
   return cudaGetLastError();
 }
 
@@ -1068,7 +1107,7 @@ cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, 
 }
 
 cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float* out, cudaStream_t st) {
-  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, out);
+  colsum_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, nblk, C, out);
   return cudaGetLastError();
 }
 
