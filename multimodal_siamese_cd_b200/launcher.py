@@ -1,0 +1,51 @@
+"""Run one of the reference's scripts UNCHANGED with the B200 modules substituted for `utils.networks` and
+`utils.loss_functions` (and an fvcore stand-in if fvcore/yacs are not installed).
+
+    python -m multimodal_siamese_cd_b200.launcher REF_ROOT SCRIPT [script args...]
+    e.g.  ... launcher /path/to/multimodal_siamese_cd train_supervised.py -c baseline_siamese -o OUT -d DATA
+
+The reference tree is only read. Under torchrun (WORLD_SIZE > 1) the process group is initialised and the reference's
+nn.DataParallel semantics are enabled (parallel.enable_data_parallel): global-batch loss, SUM-reduced gradients.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import runpy
+import sys
+
+
+def substitute_modules(ref_root: str) -> None:
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    from .config import install_fvcore_stub
+    install_fvcore_stub()
+    from . import loss_functions, networks
+    utils_pkg = importlib.import_module("utils")          # the reference's package (namespace or regular)
+    sys.modules["utils.networks"] = networks
+    sys.modules["utils.loss_functions"] = loss_functions
+    utils_pkg.networks = networks
+    utils_pkg.loss_functions = loss_functions
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) < 2:
+        raise SystemExit(__doc__)
+    ref_root, script, rest = os.path.abspath(argv[0]), argv[1], argv[2:]
+    substitute_modules(ref_root)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+
+        from . import parallel
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        parallel.enable_data_parallel()
+    os.chdir(ref_root)                                     # the scripts read configs/<name>.yaml relative to cwd
+    sys.argv = [script, *rest]
+    runpy.run_path(os.path.join(ref_root, script), run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

@@ -99,3 +99,37 @@ def test_bucket_plan_covers_gradient_buffer_once():
 def test_shard_rows_matches_dataparallel_scatter():
     assert [parallel.shard_rows(8, r, 2) for r in range(2)] == [slice(0, 4), slice(4, 8)]
     assert [parallel.shard_rows(10, r, 4) for r in range(4)] == [slice(0, 3), slice(3, 6), slice(6, 9), slice(9, 10)]
+
+
+def test_launcher_substitutes_reference_modules(tmp_path, monkeypatch):
+    """A script written like the reference's drivers (`from utils import networks, loss_functions`) gets the B200
+    modules; the (fake) reference tree is not modified."""
+    import sys
+
+    from multimodal_siamese_cd_b200 import launcher
+    ref = tmp_path / "ref"
+    (ref / "utils").mkdir(parents=True)
+    (ref / "utils" / "__init__.py").write_text("")
+    (ref / "utils" / "networks.py").write_text("raise ImportError('the reference module must not be imported')\n")
+    (ref / "utils" / "loss_functions.py").write_text("raise ImportError('the reference module must not be imported')\n")
+    (ref / "utils" / "experiment_manager.py").write_text("from fvcore.common.config import CfgNode as _CfgNode\n")
+    (ref / "driver.py").write_text(
+        "import sys\nfrom utils import networks, loss_functions, experiment_manager\n"
+        "open(sys.argv[1], 'w').write(networks.__name__ + ' ' + loss_functions.__name__ + ' ' + "
+        "experiment_manager._CfgNode.__module__)\n")
+    out = tmp_path / "out.txt"
+    saved = {k: sys.modules.get(k) for k in ("utils", "utils.networks", "utils.loss_functions", "utils.experiment_manager")}
+    monkeypatch.chdir(tmp_path)
+    try:
+        launcher.main([str(ref), "driver.py", str(out)])
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if str(ref) in sys.path:
+            sys.path.remove(str(ref))
+    got = out.read_text().split()
+    assert got[0] == "multimodal_siamese_cd_b200.networks" and got[1] == "multimodal_siamese_cd_b200.loss_functions"
+    assert got[2] in ("multimodal_siamese_cd_b200.config", "fvcore.common.config")
