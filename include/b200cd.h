@@ -72,15 +72,19 @@ int b200cd_pack_input(const float* src0, const float* src1, int csrc, int c_lo, 
  *   mode 4 convT dgrad       out[ci][tap*d1 + co] */
 int b200cd_pack_weights(int mode, const float* w, void* out_bf16, int d0, int d1, int kpad, void* stream);
 
-/* The same for every weight of a network in ONE launch. `jobs_dev` is a DEVICE array; job j writes the output elements
- * [start_j, start_j + size_j) of the concatenated index space (start = running sum of the packed sizes), total = sum. */
+/* The same for every weight of a network in ONE launch. `jobs_dev` is a DEVICE array; job j owns the thread blocks
+ * [start_j, start_j + b200cd_pack_job_blocks(mode_j, d0_j, d1_j, kpad_j)) (start = running sum, total_blocks = sum).
+ * When out2_bf16 is not NULL the same weights are also written in layout mode2 (e.g. mode 0 + mode 1: the forward and
+ * the input-gradient operand of one convolution) from a single read of w. */
 typedef struct {
   const float* w;
   void* out_bf16;
-  int32_t mode, d0, d1, kpad;
+  void* out2_bf16;
+  int32_t mode, mode2, d0, d1, kpad, reserved;
   int64_t start;
 } b200cd_pack_job;
-int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total, void* stream);
+int b200cd_pack_job_blocks(int mode, int d0, int d1, int kpad);
+int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total_blocks, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * G1 — tcgen05 implicit GEMM, D[pixel, n] = sum_{tap,k} A_tap[pixel, k] * Bw[n, tap*ka + k].
@@ -100,6 +104,9 @@ int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int6
  *   flags: bit 0 (mode 0 only) = load the activation tile once per kx with a one-row halo and serve the three ky
  *          taps from it (less L2 -> SM traffic; same result bit for bit).
  *          bit 1 = use a 128 x 256 output tile when N (out_mode 1: cout) is a multiple of 256 and bit 0 is clear.
+ *          bit 2 (mode 0, out_mode 0 only) = CTA-pair kernel: two SMs compute one 256-pixel tile with cta_group::2 MMAs,
+ *          each loading half of the weight tile; persistent, weights resident in shared memory when they fit
+ *          (same result bit for bit).
  *   requires ka % 64 == 0, N % 64 == 0, a_ld % 8 == 0, out_ld % 8 == 0.
  * ------------------------------------------------------------------------------------------------- */
 int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,

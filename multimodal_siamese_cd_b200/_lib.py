@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200cd_device_status": (_i, [_i, _vp]),
     "b200cd_pack_input": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200cd_pack_weights": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
+    "b200cd_pack_job_blocks": (_i, [_i, _i, _i, _i]),
     "b200cd_pack_weights_batched": (_i, [_vp, _i, _i64, _vp]),
     "b200cd_conv_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "b200cd_conv_gemm_tiles": (_i, [_i, _i]),

@@ -192,10 +192,16 @@ int b200cd_pack_weights(int mode, const float* w, void* out, int d0, int d1, int
   return 0;
 }
 
-int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total, void* stream) {
+int b200cd_pack_job_blocks(int mode, int d0, int d1, int kpad) {
+  if (mode < 0 || mode > 4 || d0 <= 0 || d1 <= 0) return 0;
+  return b200cd::pack_job_blocks(mode, d0, d1, kpad);
+}
+
+int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total_blocks, void* stream) {
   static_assert(sizeof(b200cd_pack_job) == sizeof(b200cd::PackJob), "pack job layout");
-  if (jobs_dev == nullptr || njobs < 1 || total < 1) return fail(B200CD_ERR_SHAPE, "pack_weights_batched: empty job table");
-  CUDA_TRY(b200cd::launch_pack_weights_batched(reinterpret_cast<const b200cd::PackJob*>(jobs_dev), njobs, total,
+  if (jobs_dev == nullptr || njobs < 1 || total_blocks < 1 || total_blocks > 0x7fffffffll)
+    return fail(B200CD_ERR_SHAPE, "pack_weights_batched: empty job table");
+  CUDA_TRY(b200cd::launch_pack_weights_batched(reinterpret_cast<const b200cd::PackJob*>(jobs_dev), njobs, total_blocks,
                                                reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -222,7 +228,8 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
 
   int tw, th;
   tile_shape(W, H, mode == 2 || out_mode == 1, &tw, &th);
-  const int halo = (mode == 0 && (flags & 1)) ? 1 : 0;
+  const int pair = (mode == 0 && out_mode == 0 && (flags & 4)) ? 1 : 0;
+  const int halo = (mode == 0 && ((flags & 1) || pair)) ? 1 : 0;
   b200cd::FpropParams p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
@@ -248,6 +255,7 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   const int width = out_mode == 1 ? cout : N;
   int bn = (width % 128 == 0) ? 128 : 64;
   if ((flags & 2) && width % 256 == 0 && !halo) bn = 256;
+  if (pair && width % 256 == 0) bn = 256;
 
   CUtensorMap mapA, mapB, mapO;
   int rc;
@@ -258,14 +266,17 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
     const uint64_t ktot = static_cast<uint64_t>(p.taps) * ka;
     const uint64_t dims[2] = {ktot, (uint64_t)N};
     const uint64_t strides[1] = {ktot * 2};
-    const uint32_t box[2] = {64, (uint32_t)bn};
+    const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};  // pair: each CTA loads half of the weight tile
     if ((rc = make_map(&mapB, Bw, 2, dims, strides, box))) return rc;
   }
   if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout, W, H, n_img, tw, th);
   else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);
   if (rc) return rc;
   const int num_tiles = n_img * p.tiles_x * p.tiles_y;
-  CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, halo, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
+  if (pair)
+    CUDA_TRY(b200cd::launch_fprop_pair(mapA, mapB, mapO, p, bn, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
+  else
+    CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, halo, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -145,19 +145,79 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_
   out[i] = __float2bfloat16_rn(pack_weight_value(mode, w, d0, d1, kpad, i));
 }
 
-// All weights of a step in ONE launch: job j owns output elements [start_j, start_{j+1}).
-__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs, long long total) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// All weights of a step in ONE launch. Job j owns thread blocks [start_j, start_{j+1}). For the conv / transposed-conv
+// layouts a block moves one 32 (d0) x 32 (d1) x taps tile through shared memory: the fp32 source rows are read as
+// contiguous runs of 32*taps floats and both operand layouts (forward and input-gradient) are written from the same
+// tile in 64-byte runs, so the master weights are read once per step. Other shapes (first layer, odd sizes) use the
+// element-wise path, 2048 outputs per block.
+constexpr int kPackTile = 32;
+constexpr int kPackGenericPerBlock = 2048;
+
+__device__ __forceinline__ void pack_tile_store(int mode, const float* tile, int pitch, int taps, __nv_bfloat16* out,
+                                                int d0, int d1, int r0, int c0) {
+  // tile[r][cl * taps + tap] = w[r0 + r][c0 + cl][tap]
+  const int n = kPackTile * kPackTile * taps;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int fast = i & 31;
+    const int rest = i >> 5;
+    const int tap = rest % taps;
+    const int slow = rest / taps;
+    if (mode == 0) {         // out[co = d0][tap][ci = d1]
+      out[(static_cast<long long>(r0 + slow) * taps + tap) * d1 + c0 + fast] =
+          __float2bfloat16_rn(tile[slow * pitch + fast * taps + tap]);
+    } else if (mode == 1) {  // out[ci = d1][tap'][co = d0] = w[co][ci][8 - tap']
+      out[(static_cast<long long>(c0 + slow) * taps + tap) * d0 + r0 + fast] =
+          __float2bfloat16_rn(tile[fast * pitch + slow * taps + (taps - 1 - tap)]);
+    } else if (mode == 3) {  // out[tap * d1 + co][ci = d0]
+      out[(static_cast<long long>(tap) * d1 + c0 + slow) * d0 + r0 + fast] =
+          __float2bfloat16_rn(tile[fast * pitch + slow * taps + tap]);
+    } else {                 // mode 4: out[ci = d0][tap * d1 + co]
+      out[static_cast<long long>(r0 + slow) * (taps * d1) + static_cast<long long>(tap) * d1 + c0 + fast] =
+          __float2bfloat16_rn(tile[slow * pitch + fast * taps + tap]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[kPackTile * (kPackTile * 9 + 1)];
+  const long long b = blockIdx.x;
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].start <= i) lo = mid;
+    if (jobs[mid].start <= b) lo = mid;
     else hi = mid - 1;
   }
   const PackJob j = jobs[lo];
-  const long long li = i - j.start;
-  reinterpret_cast<__nv_bfloat16*>(j.out)[li] = __float2bfloat16_rn(pack_weight_value(j.mode, j.w, j.d0, j.d1, j.kpad, li));
+  const int lb = static_cast<int>(b - j.start);
+  const bool tiled = j.mode != 2 && j.d0 % kPackTile == 0 && j.d1 % kPackTile == 0;
+  if (!tiled) {
+    long long total;
+    if (j.mode == 0 || j.mode == 1) total = 9ll * j.d0 * j.d1;
+    else if (j.mode == 2) total = static_cast<long long>(j.d0) * j.kpad;
+    else total = 4ll * j.d0 * j.d1;
+    const long long e0 = static_cast<long long>(lb) * kPackGenericPerBlock;
+    for (int k = threadIdx.x; k < kPackGenericPerBlock; k += blockDim.x) {
+      const long long li = e0 + k;
+      if (li >= total) break;
+      reinterpret_cast<__nv_bfloat16*>(j.out)[li] = __float2bfloat16_rn(pack_weight_value(j.mode, j.w, j.d0, j.d1, j.kpad, li));
+      if (j.out2 != nullptr)
+        reinterpret_cast<__nv_bfloat16*>(j.out2)[li] = __float2bfloat16_rn(pack_weight_value(j.mode2, j.w, j.d0, j.d1, j.kpad, li));
+    }
+    return;
+  }
+  const int taps = (j.mode == 0 || j.mode == 1) ? 9 : 4;
+  const int pitch = kPackTile * taps + 1;
+  const int tiles1 = j.d1 / kPackTile;
+  const int r0 = (lb / tiles1) * kPackTile, c0 = (lb % tiles1) * kPackTile;
+  const int run = kPackTile * taps;
+  for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
+    const int r = i / run, k = i - r * run;
+    tile[r * pitch + k] = __ldg(j.w + (static_cast<long long>(r0 + r) * j.d1 + c0) * taps + k);
+  }
+  __syncthreads();
+  pack_tile_store(j.mode, tile, pitch, taps, reinterpret_cast<__nv_bfloat16*>(j.out), j.d0, j.d1, r0, c0);
+  if (j.out2 != nullptr)
+    pack_tile_store(j.mode2, tile, pitch, taps, reinterpret_cast<__nv_bfloat16*>(j.out2), j.d0, j.d1, r0, c0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,11 +238,26 @@ __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float2* __re
   double s = 0.0, q = 0.0;
   if (c < C) {
     const float2* base = partial + static_cast<long long>(g) * tiles_per_group * ld + c;
-    for (int t = tb + l; t < te; t += 8) {
+    // four independent loads in flight per thread; the summation order is fixed (deterministic)
+    double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
+    int t = tb + l;
+    for (; t + 24 < te; t += 32) {
+      const float2 v0 = __ldg(base + static_cast<long long>(t) * ld);
+      const float2 v1 = __ldg(base + static_cast<long long>(t + 8) * ld);
+      const float2 v2 = __ldg(base + static_cast<long long>(t + 16) * ld);
+      const float2 v3 = __ldg(base + static_cast<long long>(t + 24) * ld);
+      s += v0.x; q += v0.y;
+      s1 += v1.x; q1 += v1.y;
+      s2 += v2.x; q2 += v2.y;
+      s3 += v3.x; q3 += v3.y;
+    }
+    for (; t < te; t += 8) {
       const float2 v = __ldg(base + static_cast<long long>(t) * ld);
       s += v.x;
       q += v.y;
     }
+    s = (s + s1) + (s2 + s3);
+    q = (q + q1) + (q2 + q3);
   }
   sh[l][threadIdx.x & 31][0] = s;
   sh[l][threadIdx.x & 31][1] = q;
@@ -198,16 +273,21 @@ __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float2* __re
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ partial2, int spl, int C, int G, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ nbt, float momentum, float eps, int train, int order_rev,
-                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
-                                   float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 8 channels x 32 lanes: lane sp of a channel's warp holds split sp (spl <= 32), a fixed-order shuffle tree
+// sums them (one round of load latency instead of spl dependent ones); lane 0 finishes the channel.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ partial2, int spl, int C, int G,
+                                                          double count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var, long long* __restrict__ nbt,
+                                                          float momentum, float eps, int train, int order_rev,
+                                                          float* __restrict__ mean, float* __restrict__ invstd,
+                                                          float* __restrict__ scale, float* __restrict__ shift) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;  // whole warp
   if (!train) {
     // eval: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta for every group
+    if (lane != 0) return;
     const float is = 1.0f / sqrtf(running_var[c] + eps);
     for (int g = 0; g < G; ++g) {
       mean[g * C + c] = running_mean[c];
@@ -222,28 +302,37 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial2, int spl,
   for (int gi = 0; gi < G; ++gi) {
     const int g = order_rev ? G - 1 - gi : gi;
     double s = 0.0, q = 0.0;
-    for (int sp = 0; sp < spl; ++sp) {
+    for (int sp = lane; sp < spl; sp += 32) {
       const double* o = partial2 + ((static_cast<long long>(sp) * G + g) * C + c) * 2;
       s += o[0];
       q += o[1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
     }
     const double mu = s / count;
     double var = q / count - mu * mu;
     if (var < 0.0) var = 0.0;
     const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     const float muf = static_cast<float>(mu);
-    mean[g * C + c] = muf;
-    invstd[g * C + c] = is;
-    const float sc = gamma[c] * is;
-    scale[g * C + c] = sc;
-    shift[g * C + c] = beta[c] - muf * sc;
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     rm = (1.f - momentum) * rm + momentum * muf;
     rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
+    if (lane == 0) {
+      mean[g * C + c] = muf;
+      invstd[g * C + c] = is;
+      const float sc = gamma[c] * is;
+      scale[g * C + c] = sc;
+      shift[g * C + c] = beta[c] - muf * sc;
+    }
   }
-  running_mean[c] = rm;
-  running_var[c] = rv;
-  if (c == 0 && nbt != nullptr) *nbt += G;
+  if (lane == 0) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
+    if (c == 0 && nbt != nullptr) *nbt += G;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,11 +712,26 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   for (int g = 0; g < G; ++g) {
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-      for (int i = ly; i < nblk; i += 32) {
-        const float2 o = __ldg(reinterpret_cast<const float2*>(partial + ((static_cast<long long>(g) * nblk + i) * C + c) * 2));
+      const float2* base = reinterpret_cast<const float2*>(partial) + static_cast<long long>(g) * nblk * C + c;
+      double a1 = 0.0, b1 = 0.0, a2 = 0.0, b2 = 0.0, a3 = 0.0, b3 = 0.0;
+      int i = ly;
+      for (; i + 96 < nblk; i += 128) {  // four independent loads in flight; fixed order
+        const float2 o0 = __ldg(base + static_cast<long long>(i) * C);
+        const float2 o1 = __ldg(base + static_cast<long long>(i + 32) * C);
+        const float2 o2 = __ldg(base + static_cast<long long>(i + 64) * C);
+        const float2 o3 = __ldg(base + static_cast<long long>(i + 96) * C);
+        s1 += o0.x; s2 += o0.y;
+        a1 += o1.x; b1 += o1.y;
+        a2 += o2.x; b2 += o2.y;
+        a3 += o3.x; b3 += o3.y;
+      }
+      for (; i < nblk; i += 32) {
+        const float2 o = __ldg(base + static_cast<long long>(i) * C);
         s1 += o.x;
         s2 += o.y;
       }
+      s1 = (s1 + a1) + (a2 + a3);
+      s2 = (s2 + b1) + (b2 + b3);
     }
     sh[ly][cx][0] = s1;
     sh[ly][cx][1] = s2;
@@ -777,7 +881,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   if (l < lanes) {
-    for (long long i = pb + l; i < pe; i += lanes) {
+    long long i = pb + l;
+    for (; i + 3 * lanes < pe; i += 4 * lanes) {  // four independent 16-byte loads in flight
+      uint4 xv[4];
+      float wg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xv[u] = ldg16(x + (i + u * lanes) * ld + c);
+        wg[u] = wgt ? __ldg(wgt + i + u * lanes) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(xv[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = fmaf(wg[u], v[j], s[j]);
+      }
+    }
+    for (; i < pe; i += lanes) {
       float v[8];
       unpack8(ldg16(x + i * ld + c), v);
       const float wg = wgt ? __ldg(wgt + i) : 1.f;
@@ -801,8 +922,19 @@ __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __re
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   double a = 0.0;
-  if (c < C)
-    for (int i = ly; i < nblk; i += 32) a += partial[static_cast<long long>(i) * C + c];
+  if (c < C) {
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = ly;
+    for (; i + 96 < nblk; i += 128) {
+      const float v0 = __ldg(partial + static_cast<long long>(i) * C + c);
+      const float v1 = __ldg(partial + static_cast<long long>(i + 32) * C + c);
+      const float v2 = __ldg(partial + static_cast<long long>(i + 64) * C + c);
+      const float v3 = __ldg(partial + static_cast<long long>(i + 96) * C + c);
+      a += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; i < nblk; i += 32) a += __ldg(partial + static_cast<long long>(i) * C + c);
+    a = (a + a1) + (a2 + a3);
+  }
   sh[ly][cx] = a;
   __syncthreads();
   if (ly == 0 && c < C) {
@@ -850,6 +982,55 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, lo
   }
   for (; sp < splits; ++sp) a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
   grad[dst] = (a0 + a1) + (a2 + a3);
+}
+
+// Many splits, few weights (the 64-channel layers: 98 splits of 36 864 weights): block = 32 consecutive workspace
+// elements x 8 parts; part p sums splits p, p+8, ... (two chains), then a fixed-order sum over the parts in shared
+// memory. Same result on every run.
+__global__ void __launch_bounds__(256) wgrad_reduce_wide_kernel(const float* __restrict__ ws, int splits,
+                                                                long long split_stride, int layout, int d0, int d1,
+                                                                int taps, float* __restrict__ grad, long long total) {
+  __shared__ float sh[8][33];
+  const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const long long i = static_cast<long long>(blockIdx.x) * 32 + e;
+  float acc = 0.f;
+  long long dst = 0;
+  if (i < total) {
+    long long src;
+    if (layout == 0) {
+      const int b = static_cast<int>(i % d1);
+      const int a = static_cast<int>((i / d1) % d0);
+      const int tap = static_cast<int>(i / (static_cast<long long>(d1) * d0));
+      src = i;
+      dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
+    } else {
+      const int k = static_cast<int>(i % (taps * d1));
+      const int a = static_cast<int>(i / (taps * d1));
+      const int tap = k / d1, b = k - tap * d1;
+      const long long ld1 = split_stride / d0;
+      src = static_cast<long long>(a) * ld1 + k;
+      dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
+    }
+    const float* q = ws + src;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int sp = part;
+    for (; sp + 24 < splits; sp += 32) {
+      a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
+      a1 += __ldg(q + static_cast<long long>(sp + 8) * split_stride);
+      a2 += __ldg(q + static_cast<long long>(sp + 16) * split_stride);
+      a3 += __ldg(q + static_cast<long long>(sp + 24) * split_stride);
+    }
+    for (; sp < splits; sp += 8) a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  sh[part][e] = acc;
+  __syncthreads();
+  if (part == 0 && i < total) {
+    float r = sh[0][e];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += sh[k][e];
+    grad[dst] = r;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1000,8 +1181,17 @@ cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int
   return cudaGetLastError();
 }
 
-cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total, cudaStream_t st) {
-  pack_weights_batched_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(jobs, njobs, total);
+int pack_job_blocks(int mode, int d0, int d1, int kpad) {
+  if (mode != 2 && d0 % kPackTile == 0 && d1 % kPackTile == 0) return (d0 / kPackTile) * (d1 / kPackTile);
+  long long total;
+  if (mode == 0 || mode == 1) total = 9ll * d0 * d1;
+  else if (mode == 2) total = static_cast<long long>(d0) * kpad;
+  else total = 4ll * d0 * d1;
+  return static_cast<int>((total + kPackGenericPerBlock - 1) / kPackGenericPerBlock);
+}
+
+cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total_blocks, cudaStream_t st) {
+  pack_weights_batched_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, st>>>(jobs, njobs);
   return cudaGetLastError();
 }
 
@@ -1016,7 +1206,7 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
                                const float* beta, float* running_mean, float* running_var, long long* nbt,
                                float momentum, float eps, int train, int order_rev, float* mean, float* invstd,
                                float* scale, float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial2, spl, C, G, count, gamma, beta, running_mean,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial2, spl, C, G, count, gamma, beta, running_mean,
                                                       running_var, nbt, momentum, eps, train, order_rev, mean, invstd,
                                                       scale, shift);
   return cudaGetLastError();
@@ -1114,8 +1304,12 @@ cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float*
 cudaError_t launch_wgrad_reduce(const float* ws, int splits, long long split_stride, int layout, int d0, int d1,
                                 int taps, float* grad, cudaStream_t st) {
   const long long total = static_cast<long long>(d0) * d1 * taps;
-  wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
-                                                                             taps, grad, total);
+  if (splits >= 16 && total <= (1ll << 20))
+    wgrad_reduce_wide_kernel<<<static_cast<int>((total + 31) / 32), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
+                                                                                  taps, grad, total);
+  else
+    wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
+                                                                               taps, grad, total);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,450 @@
+// G1p — 3x3 implicit-GEMM convolution on CTA PAIRS (tcgen05 cta_group::2), persistent, sm_100a only.
+//
+// Why a second kernel: ncu on gemm_fprop.cu shows the convolutions bound by the L2 -> SM operand stream
+// (l1tex__m_xbar2l1tex_read_bytes ~ 39 B/clk/SM, the fabric's limit), not by the tensor pipe, and most of that stream
+// is the WEIGHT tile, which every CTA re-reads for every 128-pixel tile. Here two CTAs on the two SMs of a TPC compute
+// one 256-pixel x BN tile with a single M = 256 MMA: each CTA loads its own 128 pixels of A (with the one-row halo, so
+// the three ky taps share one box) and only HALF of the weight tile, which the tensor cores of both SMs read. The
+// kernel is persistent (one pair per TPC, static round-robin over work items) with
+//   * separate shared-memory rings for A boxes (one per kx and 64-channel chunk) and B half-tiles (one per tap),
+//   * weights held resident in the B ring when all taps of the layer fit (64 -> 64, 128 -> 64, 64 -> 128 channels:
+//     the weight stream then disappears entirely),
+//   * two accumulators in TMEM, so the epilogue of item i (TMEM -> +bias -> bf16 -> swizzled staging -> TMA store,
+//     BatchNorm partial sums of the rounded values) runs under the MMAs of item i+1.
+//
+// Replaces (reference): nn.Conv2d(.,.,3,padding=1) utils/networks.py:392,395 — forward and, with flipped/transposed
+// weights, its input gradient. Same math and rounding points as fprop_kernel<., ., HALO> (results are bit-identical:
+// the K loop runs in the same order).
+//
+// Warp roles (192 threads per CTA): warp 0 = TMA producer (both CTAs), warp 1 = TMEM owner + MMA issuer (leader CTA
+// issues for the pair), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b200cd {
+
+namespace {
+
+constexpr int kThreads = 320;  // producer warp, MMA warp, two epilogue warpgroups
+constexpr int kABox = 160 * 128;  // tw x (th + 2) <= 160 pixels x 64 bf16 (16 x 10 or 8 x 18 boxes)
+constexpr int kStageSlab = 128 * 128;  // one 64-channel slab of the output tile
+
+template <int BN>
+struct PairCfg {
+  static constexpr int kBTile = (BN / 2) * 128;  // this CTA's half of a weight tile: BN/2 rows x 64 bf16
+  // weight tiles per B-ring slot (= per barrier): with 64-wide tiles an MMA lasts 32 cycles, so the three ky tiles of a
+  // step travel together and the issuer handles one barrier per 12 MMAs
+  static constexpr int kG = BN == 64 ? 3 : 1;
+  static constexpr int kBSlot = kG * kBTile;
+  static constexpr int kStg = BN == 64 ? 1 : 2;                   // staging slabs per epilogue group
+  static constexpr int kSA = BN == 64 ? 5 : 3;
+  static constexpr int kSB = BN == 256 ? 6 : (BN == 128 ? 12 : 6);
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kSA * kABox;
+  static constexpr int kStgOff = kBOff + kSB * kBSlot;           // two staging slabs (ping-pong) per epilogue group
+  static constexpr int kBarOff = kStgOff + 2 * kStg * kStageSlab;       // a_full, a_empty, b_full, b_empty, acc_full[2], acc_empty[2]
+  static constexpr int kNumBars = 2 * kSA + 2 * kSB + 4;
+  static constexpr int kTmemSlotOff = kBarOff + 8 * kNumBars;
+  static constexpr int kBiasOff = kTmemSlotOff + 16;
+  static constexpr int kRedOff = kBiasOff + 2 * BN * 4;          // one bias copy per epilogue group
+  static constexpr int kTotal = kRedOff + 2 * 4 * 64 * 2 * 4;    // per group: [row quarter][64 channels][sum, sumsq]
+  // slack for the manual 1024-byte alignment, capped at the 227 KB limit (the kernel checks that the aligned layout
+  // still fits and reports DEV_ERR_SMEM_LAYOUT otherwise; the dynamic window starts 1024-aligned in practice)
+  static constexpr int kDynamic = kTotal + 1024 <= 232448 ? kTotal + 1024 : 232448;
+  static constexpr int kTmemCols = 2 * BN;
+  static_assert(kTotal + 16 <= 232448, "shared memory budget");
+};
+
+template <int BN, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ CUtensorMap mapO,
+                                                                 const FpropParams p, const int num_tiles) {
+  using L = PairCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t align_pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  if (align_pad + L::kTotal > static_cast<uint32_t>(L::kDynamic)) {  // uniform over the grid: nobody touches a barrier
+    if (threadIdx.x == 0) atomicCAS(p.err, 0, DEV_ERR_SMEM_LAYOUT);
+    return;
+  }
+  uint8_t* smem = smem_raw + align_pad;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* a_empty = a_full + L::kSA;
+  uint64_t* b_full = a_empty + L::kSA;
+  uint64_t* b_empty = b_full + L::kSB;
+  uint64_t* acc_full = b_empty + L::kSB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlotOff);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOff);
+  float* red = reinterpret_cast<float*>(smem + L::kRedOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int num_pairs = (num_tiles + 1) >> 1;
+  const int n_blocks = p.N / BN;
+  const int num_items = num_pairs * n_blocks;  // item = n_block * num_pairs + pair (pairs fastest: all pairs share B)
+  const int steps = 3 * p.kchunks;             // A boxes per item
+  constexpr bool resident = RESIDENT;  // host: n_blocks == 1 and all 3 * steps weight tiles fit in the B ring
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapO);
+    for (int s = 0; s < L::kSA; ++s) {
+      mbar_init(&a_full[s], 1);  // the leader's producer arms it with the bytes of BOTH CTAs' loads
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < L::kSB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);  // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, L::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (one warp per CTA, one elected lane issues; full barriers live in the leader) ------
+    uint32_t sa = 0, pa = 1, sb = 0, pb = 1;  // ring slot and the parity to wait for on its empty barrier
+    bool first = true;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int nb = item / num_pairs;
+      const int tile = 2 * (item - nb * num_pairs) + static_cast<int>(rank);
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);  // >= n_img for the phantom tile of an odd count: zero fill
+      const int x0 = tx * p.tw, y0 = ty * p.th;
+      const int nrow = nb * BN + static_cast<int>(rank) * (BN / 2);
+      int kx = 0, kc = 0;  // same K order as fprop_kernel<., ., HALO>: kx outer, 64-channel chunk inner
+      for (int st = 0; st < steps; ++st) {
+        mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
+        if (elect_one_sync()) {
+          if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
+          tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
+        }
+        __syncwarp();
+        if (++sa == L::kSA) {
+          sa = 0;
+          pa ^= 1;
+        }
+        if (!resident || first) {
+          if (L::kG == 3) {
+            if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
+            if (elect_one_sync()) {
+              if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+                tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot + ky * L::kBTile, &mapB, &b_full[sb],
+                                 (ky * 3 + kx) * p.ka + kc * 64, nrow);
+            }
+            __syncwarp();
+            if (++sb == L::kSB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          } else {
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {
+              if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
+              if (elect_one_sync()) {
+                if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
+                tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb], (ky * 3 + kx) * p.ka + kc * 64, nrow);
+              }
+              __syncwarp();
+              if (++sb == L::kSB) {  // resident: the layer's tiles fill at most kSB slots, once, in order
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+        }
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++kx;
+        }
+      }
+      first = false;
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA; M = 256 across the pair) ----------------
+      // The whole warp runs the loop (uniform control flow, operands in uniform registers); one elected lane issues.
+      // Descriptors are (low word, constant high word) pairs so that stepping an operand is one 32-bit add.
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      const uint32_t desc_hi = smem_desc_hi(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem + L::kAOff), 16);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem + L::kBOff), 16);
+      const uint32_t ky_step = static_cast<uint32_t>(p.tw * 128) >> 4;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot and the parity to wait for on its full barrier
+      uint32_t n_item = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++n_item) {
+        const uint32_t buf = n_item & 1;
+        mbar_wait(&acc_empty[buf], ((n_item >> 1) & 1) ^ 1, p.err, DEV_ERR_ACC_TIMEOUT);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        if (resident) sb = 0;
+#pragma unroll 1
+        for (int st = 0; st < steps; ++st) {
+          mbar_wait(&a_full[sa], pa, p.err, DEV_ERR_FULL_TIMEOUT);
+          const uint32_t a_lo = a_lo0 + sa * (kABox >> 4);
+          if (L::kG == 3 || resident) {
+            // the three weight tiles of this step sit behind one barrier (kG == 3) or are resident: 12 MMAs and the
+            // commits under one election
+            if (L::kG == 3) {
+              if (!resident || n_item == 0) mbar_wait(&b_full[sb], resident ? 0u : pb, p.err, DEV_ERR_FULL_TIMEOUT);
+            } else if (n_item == 0) {
+              mbar_wait(&b_full[sb], 0, p.err, DEV_ERR_FULL_TIMEOUT);
+              mbar_wait(&b_full[sb + 1], 0, p.err, DEV_ERR_FULL_TIMEOUT);
+              mbar_wait(&b_full[sb + 2], 0, p.err, DEV_ERR_FULL_TIMEOUT);
+            }
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + sb * (L::kBSlot >> 4);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // +32 bytes along K inside the swizzled 128-byte row: +2 in the >>4 field
+                  umma_bf16_2cta_lo(tmem_d, a_lo + ky * ky_step + 2 * k, b_lo + ky * (L::kBTile >> 4) + 2 * k, desc_hi,
+                                    idesc, st > 0 || ky > 0 || k > 0);
+              if (!resident) umma_commit_2cta(&b_empty[sb], 3);
+              umma_commit_2cta(&a_empty[sa], 3);
+            }
+            __syncwarp();
+            sb += L::kG == 3 ? 1 : 3;
+            if (!resident && sb == L::kSB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          } else {
+            tc_fence_after();
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(&b_full[sb], pb, p.err, DEV_ERR_FULL_TIMEOUT);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + sb * (L::kBSlot >> 4);
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_2cta_lo(tmem_d, a_lo + ky * ky_step + 2 * k, b_lo + 2 * k, desc_hi, idesc,
+                                    st > 0 || ky > 0 || k > 0);
+                umma_commit_2cta(&b_empty[sb], 3);
+                if (ky == 2) umma_commit_2cta(&a_empty[sa], 3);
+              }
+              __syncwarp();
+              if (++sb == L::kSB) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+          if (++sa == L::kSA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        if (elect_one_sync()) umma_commit_2cta(&acc_full[buf], 3);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue: two groups of 128 threads, group g drains accumulator g (items g, g+2, ...) --------
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // row of this CTA's tile = pixel (m / tw, m % tw)
+    const int t = threadIdx.x - 64 - grp * 128;
+    const uint32_t bar1 = 1 + 2 * grp, bar2 = 2 + 2 * grp;
+    uint8_t* stg = smem + L::kStgOff + grp * L::kStg * kStageSlab;
+    bias_s += grp * BN;
+    red += grp * 4 * 64 * 2;
+    uint32_t n_item = grp, n_slab = 0;
+    int bias_nb = -1;
+    for (int item = cluster_id + grp * num_clusters; item < num_items; item += 2 * num_clusters, n_item += 2) {
+      const int nb = item / num_pairs;
+      const int tile = 2 * (item - nb * num_pairs) + static_cast<int>(rank);
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.tw, y0 = ty * p.th;
+      const int n0 = nb * BN;
+      const bool real = tile < num_tiles;
+      if (nb != bias_nb) {  // uniform across the 128 threads
+        named_barrier_sync(bar1, 128);
+        for (int i = t; i < BN; i += 128) bias_s[i] = p.bias ? p.bias[n0 + i] : 0.f;
+        named_barrier_sync(bar1, 128);
+        bias_nb = nb;
+      }
+      const uint32_t buf = grp;
+      mbar_wait(&acc_full[buf], (n_item >> 1) & 1, p.err, DEV_ERR_ACC_TIMEOUT);
+      tc_fence_after();
+#pragma unroll 1
+      for (int slab = 0; slab < BN / 64; ++slab, ++n_slab) {
+        uint8_t* sbuf = stg + (n_slab % L::kStg) * kStageSlab;
+        // the TMA store that last used this staging buffer has finished reading it
+        if (t == 0 && n_slab >= L::kStg) {
+          if (L::kStg == 2) tma_store_wait_read1();
+          else tma_store_wait_read0();
+        }
+        named_barrier_sync(bar1, 128);
+        uint8_t* row = sbuf + m * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + slab * 64 + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[cc * 8 + j]) + bias_s[slab * 64 + h * 32 + cc * 8 + j];
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            const int phys = (h * 4 + cc) ^ (m & 7);
+            *reinterpret_cast<uint4*>(row + phys * 16) = o;
+          }
+        }
+        if (slab == BN / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA issuer (leader's barrier)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+        }
+        fence_proxy_async_smem();
+        named_barrier_sync(bar1, 128);
+        if (t == 0) {
+          tma_store_5d(&mapO, sbuf, n0 + slab * 64, x0, y0, img, 0);  // clipped at the tensor bounds
+          tma_store_commit();
+        }
+        if (p.stats != nullptr) {
+          // per-channel partial sums over the 128 staged (bf16-rounded) rows; conflict-free swizzled reads
+          const int cp = t & 31;  // channel pair inside the slab
+          const int rq = t >> 5;  // row quarter
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          for (int r = rq * 32; r < rq * 32 + 32; ++r) {
+            const uint32_t w =
+                *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+            float lo = bf16_lo(w), hi = bf16_hi(w);
+            if (p.ragged) {
+              const bool ok = (r < p.tw * p.th) && (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
+              lo = ok ? lo : 0.f;
+              hi = ok ? hi : 0.f;
+            }
+            s0 += lo;
+            q0 += lo * lo;
+            s1 += hi;
+            q1 += hi * hi;
+          }
+          float* dst = red + ((rq * 64) + 2 * cp) * 2;
+          dst[0] = s0;
+          dst[1] = q0;
+          dst[2] = s1;
+          dst[3] = q1;
+          named_barrier_sync(bar2, 128);
+          if (t < 64 && real) {
+            float s = 0.f, qq = 0.f;
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+              s += red[((r4 * 64) + t) * 2];
+              qq += red[((r4 * 64) + t) * 2 + 1];
+            }
+            p.stats[static_cast<size_t>(tile) * p.N + n0 + slab * 64 + t] = make_float2(s, qq);
+          }
+          // `red` is rewritten only after the next slab's first named barrier, which every reader passes first
+        }
+      }
+    }
+    if (t == 0) tma_store_wait_read0();
+  }
+
+  // teardown: both CTAs stay alive until every MMA / multicast arrive / store of the pair has retired
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, L::kTmemCols);
+  }
+}
+
+template <int BN, bool RESIDENT>
+cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const FpropParams& p,
+                        int num_tiles, cudaStream_t stream) {
+  using L = PairCfg<BN>;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_pair_kernel<BN, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(sms & ~1);
+    qc.blockDim = dim3(kThreads);
+    qc.dynamicSmemBytes = L::kDynamic;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, fprop_pair_kernel<BN, RESIDENT>, &qc);
+    if (e != cudaSuccess) return e;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    max_clusters = n < sms / 2 ? n : sms / 2;
+  }
+  const int num_items = ((num_tiles + 1) / 2) * (p.N / BN);
+  const int clusters = num_items < max_clusters ? num_items : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kDynamic;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT>, mapA, mapB, mapO, p, num_tiles);
+}
+
+}  // namespace
+
+cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
+                              const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
+  if (p.mode != 0 || p.out_mode != 0) return cudaErrorInvalidValue;
+  // weights resident in shared memory when one N block covers the layer and all 9 * kchunks half-tiles fit the B ring
+  const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
+                            : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
+  const bool res = p.N == bn && 9 * p.kchunks <= cap;
+  if (bn == 256) return res ? launch_pair<256, true>(mapA, mapB, mapO, p, num_tiles, stream)
+                            : launch_pair<256, false>(mapA, mapB, mapO, p, num_tiles, stream);
+  if (bn == 128) return res ? launch_pair<128, true>(mapA, mapB, mapO, p, num_tiles, stream)
+                            : launch_pair<128, false>(mapA, mapB, mapO, p, num_tiles, stream);
+  if (bn == 64) return res ? launch_pair<64, true>(mapA, mapB, mapO, p, num_tiles, stream)
+                           : launch_pair<64, false>(mapA, mapB, mapO, p, num_tiles, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b200cd

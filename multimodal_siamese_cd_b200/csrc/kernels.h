@@ -30,6 +30,10 @@ struct FpropParams {
 cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                          const FpropParams& p, int bn, int halo, int num_tiles, cudaStream_t stream);
 
+// G1p (gemm_fprop2.cu): mode 0 / out_mode 0 on CTA pairs (cta_group::2), persistent, halo A boxes (p.rows = tw*(th+2)).
+cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
+                              const FpropParams& p, int bn, int num_tiles, cudaStream_t stream);
+
 // ----------------------------------------------------------------------------------------------
 // G2: weight-gradient kernel. D_tap[m, n] = sum_pixels U[pixel, m] * V_tap[pixel, n]
 //   (both operands MN-major straight out of NHWC memory), split over pixel ranges.
@@ -68,10 +72,12 @@ cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, in
 struct PackJob {        // layout == b200cd_pack_job (include/b200cd.h)
   const float* w;
   void* out;
-  int mode, d0, d1, kpad;
-  long long start;      // first output element (running sum over the jobs) this job owns
+  void* out2;           // optional second operand layout (mode2) written from the same read of w
+  int mode, mode2, d0, d1, kpad, reserved;
+  long long start;      // first thread block (running sum of pack_job_blocks over the jobs) this job owns
 };
-cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total, cudaStream_t st);
+int pack_job_blocks(int mode, int d0, int d1, int kpad);
+cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total_blocks, cudaStream_t st);
 cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, cudaStream_t st);
 cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
                                    double* partial2, cudaStream_t st);

@@ -18,6 +18,7 @@ enum DevErr : int {
   DEV_ERR_FULL_TIMEOUT = 101,   // consumer waited too long for TMA bytes
   DEV_ERR_EMPTY_TIMEOUT = 102,  // producer waited too long for a free slot
   DEV_ERR_ACC_TIMEOUT = 103,    // epilogue waited too long for the accumulator
+  DEV_ERR_SMEM_LAYOUT = 104,    // dynamic shared memory window not aligned well enough for the kernel's layout
 };
 
 #ifndef B200CD_WAIT_TIMEOUT_CYCLES
@@ -61,21 +62,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 }
 // Bounded wait: a wrong byte count or descriptor must not hang the GPU. On time-out (or when
 // another CTA has already reported an error) record the code and fall through; the host checks
-// the flag after the launch and fails loudly.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
+// the flag after the launch and fails loudly. The spin loop is out of line so that the issue loops of the
+// single-warp MMA / TMA roles stay short (they are instruction-issue bound otherwise).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* err, int code) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0) {
-      if (*reinterpret_cast<volatile int*>(err) != 0) return false;
+      if (*reinterpret_cast<volatile int*>(err) != 0) return;
       if (clock64() - t0 > B200CD_WAIT_TIMEOUT_CYCLES) {
         atomicCAS(err, 0, code);
-        return false;
+        return;
       }
     }
   }
-  return true;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,6 +109,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -135,6 +139,71 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The same with the descriptors split into (low word, shared high word): the low word carries the start address
+// (>> 4) and the leading byte offset, the high word (stride offset, version, swizzle) is a kernel constant, so
+// advancing an operand is one 32-bit add.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, bool accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_bf16_2cta_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                  uint32_t idesc, bool accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);  // version 1 (bit 46), SWIZZLE_128B (bits 61..63)
 }
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
@@ -200,6 +269,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  // default semantics (.release.cta): a cluster-scope release compiles to MEMBAR.ALL.GPU, ~1000 cycles per arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {  // same warp id in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -242,6 +318,22 @@ __device__ __forceinline__ void tma_load_5d_2cta(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// One lane of a fully active warp (the same one every time). The MMA-issuing warps run their loops warp-uniformly and
+// elect only around the tcgen05 instructions: with `if (lane == 0)` around the whole loop the compiler cannot keep the
+// descriptors in uniform registers and wraps every MMA in an ELECT / R2UR.BROADCAST loop (~35 instructions, ~150
+// cycles per MMA from one thread — more than a 128 x 64 x 16 MMA takes).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {

@@ -326,7 +326,7 @@ class StepEngine:
             wflat = conv.weight.view(-1)
             for i, s in enumerate(dec_stages):
                 s.srcs.append({"kind": 3, "t": hd.dz, "w": wflat[i * C:(i + 1) * C]})
-            self._ws_need["colsum"] = max(self._ws_need["colsum"], 296 * C)
+            self._ws_need["colsum"] = max(self._ws_need["colsum"], 1184 * C)
         self.heads.append(hd)
         return hd
 
@@ -377,17 +377,17 @@ class StepEngine:
             self.outputs = [(hf, None), (h1, None), (h2, None)]
         else:
             raise ValueError(f"Unknown network ({t}).")
-        self._pack_specs_fwd, self._pack_specs_bwd = [], []
+        self._pack_specs = []
         self._emit_forward()
         if self.train:
             self._emit_backward()
-        # every weight of the step is converted to its bf16 GEMM operand layout by ONE launch (the fp32 master
-        # weights belong to the optimizer and change every step)
-        if self.device.type == "cuda":
-            for specs, dst in ((self._pack_specs_fwd, self.pack_fwd), (self._pack_specs_bwd, self.pack_bwd)):
-                if specs:
-                    tab, nj, tot = ops.make_pack_jobs(specs, self.device)
-                    dst.append(lambda tab=tab, nj=nj, tot=tot: ops.pack_weights_batched(tab, nj, tot))
+        # every weight of the step is converted to its bf16 GEMM operand layouts (forward and, when training, input
+        # gradient) by ONE launch at the start of the forward pass: the fp32 master weights belong to the optimizer and
+        # change every step, and they are read once
+        if self.device.type == "cuda" and self._pack_specs:
+            tab, nj, blocks, elems = ops.make_pack_jobs(self._pack_specs, self.device)
+            src = sum(sp[1].numel() for sp in self._pack_specs)
+            self.pack_fwd.append(lambda: ops.pack_weights_batched(tab, nj, blocks, elems, src))
 
     # ------------------------------------------------------------------------------------------------
     def _alloc_ws(self) -> None:
@@ -408,11 +408,11 @@ class StepEngine:
         tiles = ops.conv_gemm_tiles(st.H, st.W)
         C = st.cout
         if st.first:
-            eng._pack_specs_fwd.append((2, conv.weight, st.Wf, st.in_view.shape[3]))
+            eng._pack_specs.append((2, conv.weight, st.Wf, st.in_view.shape[3]))
+        elif eng.train:
+            eng._pack_specs.append((0, conv.weight, st.Wf, 0, 1, st.Wd))
         else:
-            eng._pack_specs_fwd.append((0, conv.weight, st.Wf, 0))
-            if eng.train:
-                eng._pack_specs_bwd.append((1, conv.weight, st.Wd, 0))
+            eng._pack_specs.append((0, conv.weight, st.Wf, 0))
         mode = 1 if st.first else 0
         train = eng.train
         count = (st.n_img // st.G) * st.H * st.W
@@ -436,9 +436,10 @@ class StepEngine:
         for st in self.stages:
             uc = up_by_first_stage.get(id(st))
             if uc is not None:
-                self._pack_specs_fwd.append((3, uc.up.weight, uc.Wf, 0))
                 if self.train:
-                    self._pack_specs_bwd.append((4, uc.up.weight, uc.Wd, 0))
+                    self._pack_specs.append((3, uc.up.weight, uc.Wf, 0, 4, uc.Wd))
+                else:
+                    self._pack_specs.append((3, uc.up.weight, uc.Wf, 0))
                 self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
             self._emit_stage_fwd(st)
         for hd in self.heads:
@@ -511,7 +512,7 @@ class StepEngine:
         splits = max(1, min(total, max(1, (148 * 2) // ctas)))
         self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 4 * c * c)
         npix = nb * 4 * h * w
-        nblk = max(1, min(296, npix // 512))
+        nblk = max(1, min(1184, npix // 64))
         self._ws_need["colsum"] = max(self._ws_need["colsum"], nblk * c)
 
         def run():
@@ -539,7 +540,7 @@ class StepEngine:
         for hd in self.heads:
             C = hd.inputs[0].shape[3]
             npix = hd.logits.numel()
-            nblk = max(1, min(296, npix // 512))
+            nblk = max(1, min(1184, npix // 64))
             gw, gb = g.view_of(hd.conv.weight).view(-1), g.view_of(hd.conv.bias)
 
             def run(hd=hd, C=C, npix=npix, nblk=nblk, gw=gw, gb=gb):

@@ -135,30 +135,41 @@ def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.
 _PACK_JOB_DTYPE = None
 
 
-def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int]:
-    """specs: (mode, weight fp32 tensor, out bf16 tensor, kpad). Returns (device job table, njobs, total elements)
-    for pack_weights_batched (b200cd_pack_job layout: two pointers, four int32, one int64 = 40 bytes)."""
+def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int, int]:
+    """specs: (mode, weight fp32 tensor, out bf16 tensor, kpad[, mode2, out2 bf16 tensor]). Returns (device job table,
+    njobs, total thread blocks, packed elements) for pack_weights_batched (b200cd_pack_job layout: three pointers,
+    six int32, one int64 = 56 bytes)."""
     import numpy as np
     global _PACK_JOB_DTYPE
     if _PACK_JOB_DTYPE is None:
-        _PACK_JOB_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("mode", "<i4"), ("d0", "<i4"), ("d1", "<i4"),
-                                    ("kpad", "<i4"), ("start", "<i8")], align=True)
-        assert _PACK_JOB_DTYPE.itemsize == 40
+        _PACK_JOB_DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("out2", "<u8"), ("mode", "<i4"), ("mode2", "<i4"),
+                                    ("d0", "<i4"), ("d1", "<i4"), ("kpad", "<i4"), ("reserved", "<i4"), ("start", "<i8")],
+                                   align=True)
+        assert _PACK_JOB_DTYPE.itemsize == 56
+    lib = _lib.load()
     arr = np.zeros(len(specs), dtype=_PACK_JOB_DTYPE)
-    total = 0
-    for i, (mode, w, out, kpad) in enumerate(specs):
+    blocks = 0
+    elems = 0
+    for i, spec in enumerate(specs):
+        mode, w, out, kpad = spec[:4]
+        mode2, out2 = (spec[4], spec[5]) if len(spec) > 4 else (0, None)
         assert w.dtype == torch.float32 and w.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
-        arr[i] = (w.data_ptr(), out.data_ptr(), mode, w.shape[0], w.shape[1], kpad, total)
-        total += out.numel()
+        assert out2 is None or (out2.dtype == torch.bfloat16 and out2.is_contiguous() and out2.numel() == out.numel())
+        arr[i] = (w.data_ptr(), out.data_ptr(), 0 if out2 is None else out2.data_ptr(), mode, mode2, w.shape[0],
+                  w.shape[1], kpad, 0, blocks)
+        nb = lib.b200cd_pack_job_blocks(mode, w.shape[0], w.shape[1], kpad)
+        assert nb > 0
+        blocks += nb
+        elems += out.numel() * (1 if out2 is None else 2)
     table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
-    return table, len(specs), total
+    return table, len(specs), blocks, elems
 
 
-def pack_weights_batched(table: torch.Tensor, njobs: int, total: int) -> None:
+def pack_weights_batched(table: torch.Tensor, njobs: int, blocks: int, elems: int = 0, src_elems: int = 0) -> None:
     _require_cuda(table)
     _count(1)
-    with _Prof("pack_weights", 0.0, 6.0 * total):
-        _lib.check(_lib.load().b200cd_pack_weights_batched(table.data_ptr(), njobs, total, _stream()))
+    with _Prof("pack_weights", 0.0, 2.0 * elems + 4.0 * src_elems):
+        _lib.check(_lib.load().b200cd_pack_weights_batched(table.data_ptr(), njobs, blocks, _stream()))
 
 
 def conv_gemm_tiles(H: int, W: int) -> int:
@@ -167,11 +178,12 @@ def conv_gemm_tiles(H: int, W: int) -> int:
 
 FPROP_HALO_POLICY = "auto"  # 3x3 convs using the halo variant: "auto" (N % 128 != 0 or K-chunk count >= 8), "n64", "all", "none"
 FPROP_WIDE_TILES = True     # 128 x 256 output tiles where N % 256 == 0 and the halo variant is not used
+FPROP_PAIR = True           # 3x3 convs on CTA pairs (cta_group::2, persistent, gemm_fprop2.cu)
 
 
 def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              halo: Optional[bool] = None, wide: Optional[bool] = None) -> None:
+              halo: Optional[bool] = None, wide: Optional[bool] = None, pair: Optional[bool] = None) -> None:
     """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x)."""
     _require_cuda(A, Bw, out)
     n, Ha, Wa, ka, a_ld = _nhwc(A)
@@ -188,13 +200,16 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
         cout = 0
     # tile policy (measured on B200, profiles/r01_probe_kernels_call7.json): 128x256 tiles where N % 256 == 0;
     # otherwise the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)
+    if pair is None:
+        pair = FPROP_PAIR and mode == 0 and out_mode == 0 and halo is None and wide is None
+    pair = bool(pair) and mode == 0 and out_mode == 0
     if wide is None:
         wide = FPROP_WIDE_TILES and N % 256 == 0 and halo is not True
     if halo is None:
         pol = FPROP_HALO_POLICY
         halo = mode == 0 and not wide and (pol == "all" or (pol in ("n64", "auto") and N % 128 != 0) or
                                            (pol == "auto" and ka >= 512))
-    flags = (1 if (halo and mode == 0) else 0) | (2 if wide else 0)
+    flags = 4 if pair else ((1 if (halo and mode == 0) else 0) | (2 if wide else 0))
     _count(1)
     fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
     with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode} halo{flags}"):

@@ -76,6 +76,21 @@ def check_pack_weights() -> dict:
     p4 = ops.pack_weights(4, wt)
     ref4 = wt.permute(0, 2, 3, 1).reshape(128, 4 * 64).to(torch.bfloat16)
     out["m4"] = bool(torch.equal(p4, ref4))
+    # every job of a network in one launch, forward + input-gradient layouts written from one read of the weights
+    w_big = torch.randn(256, 128, 3, 3, device=DEV, generator=g)
+    b0, b1 = torch.empty_like(p0), torch.empty_like(p1)
+    b3, b4 = torch.empty_like(p3), torch.empty_like(p4)
+    b2 = torch.empty_like(p2)
+    bb0 = torch.empty(256, 9 * 128, device=DEV, dtype=torch.bfloat16)
+    bb1 = torch.empty(128, 9 * 256, device=DEV, dtype=torch.bfloat16)
+    only1 = torch.empty_like(p1)
+    tab, nj, blocks, elems = ops.make_pack_jobs([(0, w, b0, 0, 1, b1), (2, w1, b2, 64), (3, wt, b3, 0, 4, b4),
+                                                 (0, w_big, bb0, 0, 1, bb1), (1, w, only1, 0)], DEV)
+    ops.pack_weights_batched(tab, nj, blocks, elems)
+    out["batched"] = bool(torch.equal(b0, ref0) and torch.equal(b1, ref1) and torch.equal(b2, ref2.to(torch.bfloat16)) and
+                          torch.equal(b3, ref3) and torch.equal(b4, ref4) and torch.equal(only1, ref1) and
+                          torch.equal(bb0, w_big.permute(0, 2, 3, 1).reshape(256, 9 * 128).to(torch.bfloat16)) and
+                          torch.equal(bb1, w_big.flip(2, 3).permute(1, 2, 3, 0).reshape(128, 9 * 256).to(torch.bfloat16)))
     out["ok"] = all(out.values())
     return out
 
@@ -110,7 +125,7 @@ def check_pack_input() -> dict:
 
 # ----------------------------------------------------------------------------------------------------
 def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, slice_out=False, seed=3,
-                  tol=6e-3, halo=None, wide=None) -> dict:
+                  tol=6e-3, halo=None, wide=None, pair=None, compare_single=False) -> dict:
     """conv_gemm mode 0 vs F.conv2d (fp32 math on the bf16-rounded operands); output is bf16 so the bound is
     one bf16 ulp (2^-8 relative) plus accumulation-order noise."""
     g = _gen(seed)
@@ -132,10 +147,16 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
     tiles = ops.conv_gemm_tiles(H, W)
     stats = torch.zeros(n * tiles, cout, 2, device=DEV)
     Bw = ops.pack_weights(0, w)
-    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats, halo=halo, wide=wide)
+    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats, halo=halo, wide=wide, pair=pair)
     ops.device_status()
     ref = F.conv2d(x, w, b, padding=1)
     res = err(nchw(out.float()), ref, bf16_out=True)
+    if compare_single:  # the CTA-pair kernel runs the K loop in the same order as the single-CTA halo kernel
+        out1 = torch.empty(n, H, W, cout, device=DEV, dtype=torch.bfloat16)
+        stats1 = torch.zeros_like(stats)
+        ops.conv_gemm(0, 0, A, Bw, out1, bias=b, stats=stats1, halo=True, wide=False, pair=False)
+        ops.device_status()
+        res["same_as_single"] = bool(torch.equal(out1, out.contiguous()) and torch.equal(stats1, stats))
     got_sum = stats[..., 0].sum(0)
     got_sq = stats[..., 1].sum(0)
     o32 = out.float()
@@ -143,8 +164,11 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
     res["stats_sq_rel"] = ((got_sq - (o32 * o32).sum((0, 1, 2))).norm() / (o32 * o32).sum((0, 1, 2)).norm()).item()
     if obuf is not None:
         res["untouched"] = bool((obuf[..., cout:] == 7.0).all().item())
+    # the share of outputs that land on the other side of a bf16 rounding boundary than the fp32 reference grows with
+    # the reduction length (fp32 summation-order noise): 5e-3 up to K = 4608, proportionally more beyond
+    res["ulp_tol"] = 5e-3 * max(1.0, 9 * cin / 4608)
     res["ok"] = res["finite"] and res["rel_l2"] < tol and res["stats_sum_rel"] < 1e-3 and res["stats_sq_rel"] < 1e-3 \
-        and res.get("untouched", True)
+        and res.get("untouched", True) and res.get("same_as_single", True)
     return res
 
 
@@ -556,6 +580,18 @@ ALL_CHECKS = {
     "conv3x3_halo_ragged_8x8": lambda: check_conv3x3(3, 8, 8, 128, 64, seed=38, halo=True),
     "conv3x3_halo_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36, halo=True),
     "conv3x3_halo_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37, halo=True),
+    "conv3x3_pair_64_64": lambda: check_conv3x3(2, 32, 32, 64, 64, pair=True, compare_single=True),
+    "conv3x3_pair_64_64_many": lambda: check_conv3x3(16, 64, 64, 64, 64, seed=43, pair=True, compare_single=True),
+    "conv3x3_pair_128_64_resident": lambda: check_conv3x3(8, 64, 64, 128, 64, seed=44, pair=True, compare_single=True),
+    "conv3x3_pair_64_128_resident": lambda: check_conv3x3(8, 64, 64, 64, 128, seed=45, pair=True, compare_single=True),
+    "conv3x3_pair_128_128": lambda: check_conv3x3(4, 32, 32, 128, 128, seed=31, pair=True, compare_single=True),
+    "conv3x3_pair_256_256_many": lambda: check_conv3x3(16, 32, 32, 256, 256, seed=46, pair=True),
+    "conv3x3_pair_slices_192_512": lambda: check_conv3x3(2, 16, 16, 192, 512, slice_in=True, slice_out=True, seed=40, pair=True),
+    "conv3x3_pair_512_512_16": lambda: check_conv3x3(2, 16, 16, 512, 512, seed=34, pair=True),
+    "conv3x3_pair_odd_tiles_8x8": lambda: check_conv3x3(3, 8, 8, 128, 64, seed=38, pair=True, compare_single=True),
+    "conv3x3_pair_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36, pair=True),
+    "conv3x3_pair_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37, pair=True, compare_single=True),
+    "conv3x3_pair_1024_256": lambda: check_conv3x3(4, 32, 32, 1024, 256, seed=47, pair=True),
     "conv3x3_dgrad": check_conv3x3_dgrad,
     "conv3x3_dgrad_ragged_8x8": lambda: check_conv3x3_dgrad(3, 8, 8, 128, 128, seed=42),
     "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),
@@ -573,6 +609,7 @@ ALL_CHECKS = {
     "wgrad3x3_neg": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=0, seed=71),
     "wgrad3x3_neg_halo": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=1, seed=71),
     "wgrad3x3_64_64_halo": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, seed=72),
+    "wgrad3x3_64_64_many_splits": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, splits=27, seed=76),
     "wgrad3x3_512_512_halo": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=8, seed=73),
     "wgrad3x3_tiny_4x4": lambda: check_wgrad3x3(3, 4, 4, 512, 512, sign=1, halo=1, splits=2, seed=74),
     "wgrad3x3_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 128, sign=1, halo=1, splits=7, seed=75),

@@ -64,6 +64,13 @@ def perf() -> dict:
             for halo, wide in ((False, False), (True, False), (False, True)):
                 ms = time_fn(lambda: ops.conv_gemm(0, 0, A, Bw, o, stats=stats, halo=halo, wide=wide))
                 rec[f"fprop_halo{int(halo)}_wide{int(wide)}_tflops"] = flops / ms / 1e9
+            ms = time_fn(lambda: ops.conv_gemm(0, 0, A, Bw, o, stats=stats, pair=True))
+            rec["fprop_pair_tflops"] = flops / ms / 1e9
+            rec["fprop_pair_us"] = ms * 1e3
+            if "--fprop-only" in sys.argv:
+                out[name] = rec
+                print(json.dumps({name: rec}), flush=True)
+                continue
             dr = torch.randn(n, H, H, cout, device=dev).to(torch.bfloat16)
             total = ops.wgrad_tiles(n, H, H)
             for halo in (0, 1):
@@ -93,6 +100,7 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--perf", action="store_true")
+    ap.add_argument("--fprop-only", action="store_true")
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "probe.json"))
     args = ap.parse_args()
     names = [n for n in args.only.split(",") if n] or list(gc.ALL_CHECKS)
