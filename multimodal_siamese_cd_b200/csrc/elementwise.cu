@@ -440,6 +440,109 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
   }
 }
 
+// Window variant for even H, W (every training shape): a thread keeps its 8 channels (scale/shift in registers) and
+// walks over 2x2 windows of its stat-group with 32-bit index arithmetic; the four (eight with DIFF) 16-byte loads of a
+// window are issued before any of them is used. Same arithmetic as bn_apply_kernel (bit-identical outputs).
+//   DIFF: grid.y = 1, the block handles window w of image n (timestamp 1) and of image n + n_img/2 (timestamp 2)
+//   else: grid.y = G, the block handles the images of one stat-group
+template <bool DIFF>
+__global__ void __launch_bounds__(256, 3) bn_apply_win_kernel(const ApplyArgs p) {
+  const int cvecs = p.C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int c = cv << 3;
+  const int H2 = p.H >> 1, W2 = p.W >> 1;
+  const int per_group = p.n_img / p.G;
+  const int n_units = DIFF ? p.n_img / 2 : per_group;
+  const int img0 = DIFF ? 0 : blockIdx.y * per_group;
+  const int nwin = n_units * H2 * W2;
+  const int wb = static_cast<int>(static_cast<long long>(nwin) * blockIdx.x / gridDim.x);
+  const int we = static_cast<int>(static_cast<long long>(nwin) * (blockIdx.x + 1) / gridDim.x);
+  constexpr int REPS = DIFF ? 2 : 1;
+  float sc[REPS][8], sh[REPS][8];
+#pragma unroll
+  for (int rep = 0; rep < REPS; ++rep) {
+    const int g = DIFF ? rep : blockIdx.y;
+    load8f(p.scale + g * p.C + c, sc[rep]);
+    load8f(p.shift + g * p.C + c, sh[rep]);
+  }
+  for (int w = wb + l; w < we; w += lanes) {
+    const int x2 = w % W2;
+    const int t = w / W2;
+    const int y2 = t % H2;
+    const int n = img0 + t / H2;
+    uint4 rv[REPS][4];
+    long long pix[REPS];
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+      const int nn = n + rep * n_units;
+      pix[rep] = (static_cast<long long>(nn) * p.H + 2 * y2) * p.W + 2 * x2;
+      const __nv_bfloat16* base = p.r + pix[rep] * p.ld_r + c;
+      rv[rep][0] = ldg16(base);
+      rv[rep][1] = ldg16(base + p.ld_r);
+      rv[rep][2] = ldg16(base + static_cast<long long>(p.W) * p.ld_r);
+      rv[rep][3] = ldg16(base + static_cast<long long>(p.W + 1) * p.ld_r);
+    }
+    float av[REPS][4][8];
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+      const int nn = n + rep * n_units;
+      float amax[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) amax[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float r8[8];
+        unpack8(rv[rep][k], r8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = fmaxf(fmaf(r8[j], sc[rep][j], sh[rep][j]), 0.f);
+          av[rep][k][j] = v;
+          amax[j] = fmaxf(amax[j], v);
+        }
+        const long long px = pix[rep] + (k & 1) + (k >> 1) * p.W;
+        const uint4 o = pack8(av[rep][k]);
+        if (p.a) *reinterpret_cast<uint4*>(p.a + px * p.ld_a + c) = o;
+        if (p.a2) *reinterpret_cast<uint4*>(p.a2 + px * p.ld_a2 + c) = o;
+      }
+      if (p.pool) {
+        const long long ppix = (static_cast<long long>(nn) * H2 + y2) * W2 + x2;
+        *reinterpret_cast<uint4*>(p.pool + ppix * p.ld_p + c) = pack8(amax);
+        if (p.pidx) {
+          // first maximum in row-major order of the STORED (bf16) activations, as ATen's max_pool2d_with_indices
+          unsigned long long packed = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int arg = 0;
+            float best = round_bf16(av[rep][0][j]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+              const float v = round_bf16(av[rep][k][j]);
+              if (v > best) {
+                best = v;
+                arg = k;
+              }
+            }
+            packed |= static_cast<unsigned long long>(arg) << (8 * j);
+          }
+          *reinterpret_cast<unsigned long long*>(p.pidx + ppix * p.C + c) = packed;
+        }
+      }
+    }
+    if (DIFF && p.dif) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = av[REPS - 1][k][j] - av[0][k][j];
+        const long long px = pix[0] + (k & 1) + (k >> 1) * p.W;
+        *reinterpret_cast<uint4*>(p.dif + px * p.ld_d + c) = pack8(d);
+      }
+    }
+  }
+}
+
 // Per-pixel variant (no pooling, no difference): a thread keeps its 8 channels, so scale/shift stay in registers;
 // four independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256, 4) bn_apply_px_kernel(const ApplyArgs p) {
@@ -505,14 +608,24 @@ struct BwdArgs {
   int n_img, H, W, C, G;
 };
 
+// The kernels are instantiated for the source-kind triples the networks produce (K0, K1, K2 >= 0: known at compile
+// time, the dead branches and their registers disappear) plus a generic variant (K < 0: kinds read at run time).
+template <int K0, int K1, int K2>
+__device__ __forceinline__ int src_kind(const BwdArgs& p, int si) {
+  const int k = si == 0 ? K0 : (si == 1 ? K1 : K2);
+  return k >= 0 ? k : p.srcs.s[si].kind;
+}
+
 // sum of the gradient sources at global pixel `gpix` (= n*H*W + y*W + x) -> dy[8] (unmasked)
+template <int K0, int K1, int K2>
 __device__ __forceinline__ void gather_px(const BwdArgs& p, int gpix, int hw, int c, float (&dy)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) dy[j] = 0.f;
 #pragma unroll
   for (int si = 0; si < 3; ++si) {
     const GradSrc& s = p.srcs.s[si];
-    if (s.kind == 0) continue;
+    const int kind = src_kind<K0, K1, K2>(p, si);
+    if (kind == 0) continue;
     int sp = gpix;  // pixel index in the source tensor
     float scale = 1.f;
     if (s.n_mod > 0) {
@@ -520,12 +633,12 @@ __device__ __forceinline__ void gather_px(const BwdArgs& p, int gpix, int hw, in
       scale = n < s.n_mod ? s.scale_lo : s.scale_hi;
       sp = gpix - (n - n % s.n_mod) * hw;
     }
-    if (s.kind == 1) {
+    if (kind == 1) {
       float gv[8];
       unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(s.ptr) + static_cast<long long>(sp) * s.ld + c), gv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dy[j] = fmaf(scale, gv[j], dy[j]);
-    } else if (s.kind == 2) {
+    } else if (kind == 2) {
       const int n = sp / hw, pix = sp - n * hw;
       const int y = pix / p.W, x = pix - y * p.W;
       const int H2 = p.H >> 1, W2 = p.W >> 1;
@@ -554,6 +667,7 @@ constexpr int kBwdUnroll = 4;
 
 // The same for kBwdUnroll pixels at once, source by source, with all loads of a source issued before any is used
 // (memory-level parallelism: the kernels are pure streaming).
+template <int K0, int K1, int K2>
 __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)[kBwdUnroll], int hw, int c,
                                              float (&dy)[kBwdUnroll][8]) {
 #pragma unroll
@@ -563,7 +677,8 @@ __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)
 #pragma unroll
   for (int si = 0; si < 3; ++si) {
     const GradSrc& s = p.srcs.s[si];
-    if (s.kind == 0) continue;
+    const int kind = src_kind<K0, K1, K2>(p, si);
+    if (kind == 0) continue;
     int sp[kBwdUnroll];
     float scale[kBwdUnroll];
 #pragma unroll
@@ -576,7 +691,7 @@ __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)
         sp[u] = gpix[u] - (n - n % s.n_mod) * hw;
       }
     }
-    if (s.kind == 1) {
+    if (kind == 1) {
       uint4 g[kBwdUnroll];
 #pragma unroll
       for (int u = 0; u < kBwdUnroll; ++u)
@@ -588,7 +703,7 @@ __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dy[u][j] = fmaf(scale[u], gv[j], dy[u][j]);
       }
-    } else if (s.kind == 2) {
+    } else if (kind == 2) {
       const int H2 = p.H >> 1, W2 = p.W >> 1;
       uint4 g[kBwdUnroll];
       unsigned long long idx[kBwdUnroll];
@@ -627,6 +742,7 @@ __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)
 }
 
 // grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) pixel lanes
+template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
   extern __shared__ float shred[];  // [lanes][C][2]
   const int cvecs = p.C >> 3;
@@ -656,7 +772,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, 
       gp[u] = gbase + i + u * lanes;
     }
     float d[kBwdUnroll][8];
-    gather_multi(p, gp, hw, c, d);
+    gather_multi<K0, K1, K2>(p, gp, hw, c, d);
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       float v[8];
@@ -672,7 +788,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, 
   for (; i < pe; i += lanes) {
     float d[8], v[8];
     unpack8(ldg16(rbase + static_cast<long long>(i) * p.ld_r), v);
-    gather_px(p, gbase + i, hw, c, d);
+    gather_px<K0, K1, K2>(p, gbase + i, hw, c, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
@@ -695,6 +811,192 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, 
     float* o = partial + ((static_cast<long long>(g) * gridDim.x + blockIdx.x) * p.C + ch) * 2;
     o[0] = a;
     o[1] = b;
+  }
+}
+
+// Window variants for layers whose first gradient source is a max-pool (kind 2; H, W even): a thread walks over 2x2
+// windows, so the pooled gradient and its arg-max index are loaded once per window instead of once per pixel, index
+// arithmetic is per window and 32-bit, and all loads of a window (4 x r, pooled gradient, index, 4 per direct source)
+// are in flight together. K1, K2 in {0, 1}. Same arithmetic per element as the per-pixel kernels.
+template <int K1, int K2>
+__device__ __forceinline__ void gather_window(const BwdArgs& p, int n, int y2, int x2, int c, const uint4 (&rr)[4],
+                                              const float (&sc)[8], const float (&sh)[8], float (&m)[4][8]) {
+  const int H2 = p.H >> 1, W2 = p.W >> 1;
+  const int hw = p.H * p.W;
+  // issue every load first
+  const GradSrc& s0 = p.srcs.s[0];
+  int n0 = n;
+  float scale0 = 1.f;
+  if (s0.n_mod > 0) {
+    scale0 = n < s0.n_mod ? s0.scale_lo : s0.scale_hi;
+    n0 = n % s0.n_mod;
+  }
+  const long long pp = (static_cast<long long>(n0) * H2 + y2) * W2 + x2;
+  const unsigned long long idx =
+      __ldg(reinterpret_cast<const unsigned long long*>(reinterpret_cast<const unsigned char*>(s0.w) + pp * p.C + c));
+  const uint4 g0 = ldg16(reinterpret_cast<const __nv_bfloat16*>(s0.ptr) + pp * s0.ld + c);
+  uint4 g1[4], g2[4];
+  float scale1 = 1.f, scale2 = 1.f;
+  if (K1 == 1) {
+    const GradSrc& s = p.srcs.s[1];
+    int nn = n;
+    if (s.n_mod > 0) {
+      scale1 = n < s.n_mod ? s.scale_lo : s.scale_hi;
+      nn = n % s.n_mod;
+    }
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(s.ptr) +
+                             (static_cast<long long>(nn) * hw + 2 * y2 * p.W + 2 * x2) * s.ld + c;
+    g1[0] = ldg16(b);
+    g1[1] = ldg16(b + s.ld);
+    g1[2] = ldg16(b + static_cast<long long>(p.W) * s.ld);
+    g1[3] = ldg16(b + static_cast<long long>(p.W + 1) * s.ld);
+  }
+  if (K2 == 1) {
+    const GradSrc& s = p.srcs.s[2];
+    int nn = n;
+    if (s.n_mod > 0) {
+      scale2 = n < s.n_mod ? s.scale_lo : s.scale_hi;
+      nn = n % s.n_mod;
+    }
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(s.ptr) +
+                             (static_cast<long long>(nn) * hw + 2 * y2 * p.W + 2 * x2) * s.ld + c;
+    g2[0] = ldg16(b);
+    g2[1] = ldg16(b + s.ld);
+    g2[2] = ldg16(b + static_cast<long long>(p.W) * s.ld);
+    g2[3] = ldg16(b + static_cast<long long>(p.W + 1) * s.ld);
+  }
+  float gp[8];
+  unpack8(g0, gp);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float dy[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dy[j] = 0.f;
+    // same accumulation order as gather_multi: source 0 (pool), then 1, then 2
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dy[j] += (((idx >> (8 * j)) & 0xffull) == static_cast<unsigned>(k)) ? scale0 * gp[j] : 0.f;
+    if (K1 == 1) {
+      float gv[8];
+      unpack8(g1[k], gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy[j] = fmaf(scale1, gv[j], dy[j]);
+    }
+    if (K2 == 1) {
+      float gv[8];
+      unpack8(g2[k], gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy[j] = fmaf(scale2, gv[j], dy[j]);
+    }
+    float v[8];
+    unpack8(rr[k], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[k][j] = fmaf(v[j], sc[j], sh[j]) > 0.f ? dy[j] : 0.f;
+  }
+}
+
+template <int K1, int K2>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_win_kernel(const BwdArgs p, float* __restrict__ partial) {
+  extern __shared__ float shred[];  // [lanes][C][2]
+  const int cvecs = p.C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int g = blockIdx.y;
+  const int c = cv << 3;
+  const int H2 = p.H >> 1, W2 = p.W >> 1;
+  const int per_group = p.n_img / p.G;
+  const int nwin = per_group * H2 * W2;
+  const int wb = static_cast<int>(static_cast<long long>(nwin) * blockIdx.x / gridDim.x);
+  const int we = static_cast<int>(static_cast<long long>(nwin) * (blockIdx.x + 1) / gridDim.x);
+  float sc[8], sh[8], s1[8], s2[8];
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (int w = wb + l; w < we; w += lanes) {
+    const int x2 = w % W2;
+    const int t = w / W2;
+    const int y2 = t % H2;
+    const int n = g * per_group + t / H2;
+    const __nv_bfloat16* rb = p.r + ((static_cast<long long>(n) * p.H + 2 * y2) * p.W + 2 * x2) * p.ld_r + c;
+    uint4 rr[4];
+    rr[0] = ldg16(rb);
+    rr[1] = ldg16(rb + p.ld_r);
+    rr[2] = ldg16(rb + static_cast<long long>(p.W) * p.ld_r);
+    rr[3] = ldg16(rb + static_cast<long long>(p.W + 1) * p.ld_r);
+    float m[4][8];
+    gather_window<K1, K2>(p, n, y2, x2, c, rr, sc, sh, m);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(rr[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += m[k][j];
+        s2[j] = fmaf(m[k][j], v[j], s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    shred[(l * p.C + c + j) * 2] = s1[j];
+    shred[(l * p.C + c + j) * 2 + 1] = s2[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < p.C; ch += 256) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < lanes; ++k) {
+      a += shred[(k * p.C + ch) * 2];
+      b += shred[(k * p.C + ch) * 2 + 1];
+    }
+    float* o = partial + ((static_cast<long long>(g) * gridDim.x + blockIdx.x) * p.C + ch) * 2;
+    o[0] = a;
+    o[1] = b;
+  }
+}
+
+template <int K1, int K2>
+__global__ void __launch_bounds__(256, 2) bn_bwd_dx_win_kernel(const BwdArgs p, const float* __restrict__ coefA,
+                                                               const float* __restrict__ coefB,
+                                                               __nv_bfloat16* __restrict__ dr, long long ld_dr) {
+  const int cvecs = p.C >> 3;
+  const int lanes = 256 / cvecs;
+  const int cv = threadIdx.x % cvecs;
+  const int l = threadIdx.x / cvecs;
+  const int g = blockIdx.y;
+  const int c = cv << 3;
+  const int H2 = p.H >> 1, W2 = p.W >> 1;
+  const int per_group = p.n_img / p.G;
+  const int nwin = per_group * H2 * W2;
+  const int wb = static_cast<int>(static_cast<long long>(nwin) * blockIdx.x / gridDim.x);
+  const int we = static_cast<int>(static_cast<long long>(nwin) * (blockIdx.x + 1) / gridDim.x);
+  float sc[8], sh[8], ca[8], cb[8];
+  load8f(p.scale + g * p.C + c, sc);
+  load8f(p.shift + g * p.C + c, sh);
+  load8f(coefA + g * p.C + c, ca);
+  load8f(coefB + g * p.C + c, cb);
+  for (int w = wb + l; w < we; w += lanes) {
+    const int x2 = w % W2;
+    const int t = w / W2;
+    const int y2 = t % H2;
+    const int n = g * per_group + t / H2;
+    const long long pix = (static_cast<long long>(n) * p.H + 2 * y2) * p.W + 2 * x2;
+    const __nv_bfloat16* rb = p.r + pix * p.ld_r + c;
+    uint4 rr[4];
+    rr[0] = ldg16(rb);
+    rr[1] = ldg16(rb + p.ld_r);
+    rr[2] = ldg16(rb + static_cast<long long>(p.W) * p.ld_r);
+    rr[3] = ldg16(rb + static_cast<long long>(p.W + 1) * p.ld_r);
+    float m[4][8];
+    gather_window<K1, K2>(p, n, y2, x2, c, rr, sc, sh, m);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8], o[8];
+      unpack8(rr[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], m[k][j], fmaf(v[j], ca[j], cb[j]));
+      *reinterpret_cast<uint4*>(dr + (pix + (k & 1) + (k >> 1) * p.W) * ld_dr + c) = pack8(o);
+    }
   }
 }
 
@@ -759,6 +1061,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   }
 }
 
+template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
                                                            const float* __restrict__ coefB,
                                                            __nv_bfloat16* __restrict__ dr, long long ld_dr) {
@@ -790,7 +1093,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, cons
       gp[u] = gbase + i + u * lanes;
     }
     float d[kBwdUnroll][8];
-    gather_multi(p, gp, hw, c, d);
+    gather_multi<K0, K1, K2>(p, gp, hw, c, d);
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       float v[8], o[8];
@@ -806,7 +1109,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, cons
   for (; i < pe; i += lanes) {
     float d[8], v[8], o[8];
     unpack8(ldg16(rbase + static_cast<long long>(i) * p.ld_r), v);
-    gather_px(p, gbase + i, hw, c, d);
+    gather_px<K0, K1, K2>(p, gbase + i, hw, c, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float m = fmaf(v[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
@@ -1235,6 +1538,17 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
     bn_apply_px_kernel<<<dim3(static_cast<unsigned>(nblk), G), 256, 0, st>>>(p);
     return cudaGetLastError();
   }
+  if (H % 2 == 0 && W % 2 == 0 && C % 64 == 0 && 256 % (C / 8) == 0 &&
+      static_cast<long long>(n_img) * H * W < (1ll << 31)) {
+    const int lanes = 256 / (C / 8);
+    const long long nwin = static_cast<long long>(diff ? n_img / 2 : n_img / G) * (H / 2) * (W / 2);
+    long long nblk = nwin / (static_cast<long long>(lanes) * 4);
+    const long long cap = (148 * 3 * 4) / (diff ? 1 : G);
+    nblk = nblk > cap ? cap : (nblk < 1 ? 1 : nblk);
+    if (diff) bn_apply_win_kernel<true><<<dim3(static_cast<unsigned>(nblk), 1), 256, 0, st>>>(p);
+    else bn_apply_win_kernel<false><<<dim3(static_cast<unsigned>(nblk), G), 256, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   const long long total = static_cast<long long>(diff ? n_img / 2 : n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
   return cudaGetLastError();
@@ -1251,6 +1565,26 @@ static BwdArgs make_bwd_args(const void* r, long long ld_r, const float* scale, 
   return p;
 }
 
+// first source a max-pool, the others direct (or absent), even H and W: the 2x2-window kernels apply
+static bool bn_bwd_use_windows(const GradSrcs& srcs, int H, int W) {
+  const int k1 = srcs.s[1].kind, k2 = srcs.s[2].kind;
+  return srcs.s[0].kind == 2 && H % 2 == 0 && W % 2 == 0 && (k1 == 0 || k1 == 1) && (k2 == 0 || (k2 == 1 && k1 == 1));
+}
+
+// source-kind triples with their own instantiation (everything the six network types produce); others run generic
+#define B200CD_BWD_DISPATCH(CALL)                                  \
+  do {                                                             \
+    const int k0 = srcs.s[0].kind, k1 = srcs.s[1].kind, k2 = srcs.s[2].kind; \
+    if (k0 == 1 && k1 == 0 && k2 == 0) { CALL(1, 0, 0); }          \
+    else if (k0 == 1 && k1 == 1 && k2 == 0) { CALL(1, 1, 0); }     \
+    else if (k0 == 2 && k1 == 1 && k2 == 0) { CALL(2, 1, 0); }     \
+    else if (k0 == 2 && k1 == 1 && k2 == 1) { CALL(2, 1, 1); }     \
+    else if (k0 == 1 && k1 == 3 && k2 == 0) { CALL(1, 3, 0); }     \
+    else if (k0 == 3 && k1 == 0 && k2 == 0) { CALL(3, 0, 0); }     \
+    else if (k0 == 3 && k1 == 3 && k2 == 0) { CALL(3, 3, 0); }     \
+    else { CALL(-1, -1, -1); }                                     \
+  } while (0)
+
 cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* scale, const float* shift,
                                  const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk, float* partial,
                                  cudaStream_t st) {
@@ -1258,7 +1592,16 @@ cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* sca
   const int lanes = 256 / (C / 8);
   const size_t smem = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
   dim3 grid(nblk, G);
-  bn_bwd_reduce_kernel<<<grid, 256, smem, st>>>(p, partial);
+  if (bn_bwd_use_windows(srcs, H, W)) {
+    const int k1 = srcs.s[1].kind, k2 = srcs.s[2].kind;
+    if (k1 == 1 && k2 == 1) bn_bwd_reduce_win_kernel<1, 1><<<grid, 256, smem, st>>>(p, partial);
+    else if (k1 == 1) bn_bwd_reduce_win_kernel<1, 0><<<grid, 256, smem, st>>>(p, partial);
+    else bn_bwd_reduce_win_kernel<0, 0><<<grid, 256, smem, st>>>(p, partial);
+    return cudaGetLastError();
+  }
+#define B200CD_CALL(A, B, Cc) bn_bwd_reduce_kernel<A, B, Cc><<<grid, 256, smem, st>>>(p, partial)
+  B200CD_BWD_DISPATCH(B200CD_CALL);
+#undef B200CD_CALL
   return cudaGetLastError();
 }
 
@@ -1275,7 +1618,18 @@ cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, 
                              void* dr, long long ld_dr, cudaStream_t st) {
   const BwdArgs p = make_bwd_args(r, ld_r, scale, shift, srcs, n_img, H, W, C, G);
   dim3 grid(nblk, G);
-  bn_bwd_dx_kernel<<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr);
+  if (bn_bwd_use_windows(srcs, H, W)) {
+    const int k1 = srcs.s[1].kind, k2 = srcs.s[2].kind;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dr);
+    if (k1 == 1 && k2 == 1) bn_bwd_dx_win_kernel<1, 1><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
+    else if (k1 == 1) bn_bwd_dx_win_kernel<1, 0><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
+    else bn_bwd_dx_win_kernel<0, 0><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
+    return cudaGetLastError();
+  }
+#define B200CD_CALL(A, B, Cc) \
+  bn_bwd_dx_kernel<A, B, Cc><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr)
+  B200CD_BWD_DISPATCH(B200CD_CALL);
+#undef B200CD_CALL
   return cudaGetLastError();
 }
 

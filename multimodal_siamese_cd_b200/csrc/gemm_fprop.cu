@@ -96,69 +96,78 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1, p.err, DEV_ERR_EMPTY_TIMEOUT);
-        uint8_t* a_dst = smem + s * L::kStageBytes;
-        uint8_t* b_dst = a_dst + L::kABuf;
-        const int tap = it / p.kchunks;  // HALO: tap == kx
-        const int kc = it - tap * p.kchunks;
+    // ---------------- TMA producer (whole warp runs the loop, one elected lane issues) ----------------
+    uint32_t s = 0, ph = 1;
+    int tap = 0, kc = 0;  // HALO: tap == kx
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&empty[s], ph, p.err, DEV_ERR_EMPTY_TIMEOUT);
+      uint8_t* a_dst = smem + s * L::kStageBytes;
+      uint8_t* b_dst = a_dst + L::kABuf;
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full[s], p.rows * 128 + L::kBBytes);
         if (HALO) {
           tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + tap - 1, y0 - 1, img, 0);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
             tma_load_2d(b_dst + ky * L::kBTile, &mapB, &full[s], (ky * 3 + tap) * p.ka + kc * 64, n0);
-          continue;
-        }
-        if (p.mode == 0) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, img, 0);
-        } else if (p.mode == 1) {
-          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0, y0, img, 0);
         } else {
-          const int dy = tap >> 1, dx = tap & 1;
-          tma_load_5d(a_dst, &mapA, &full[s], kc * 64, dx, x0, dy, img * p.H + y0);
+          if (p.mode == 0) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, img, 0);
+          } else if (p.mode == 1) {
+            tma_load_5d(a_dst, &mapA, &full[s], kc * 64, x0, y0, img, 0);
+          } else {
+            const int dy = tap >> 1, dx = tap & 1;
+            tma_load_5d(a_dst, &mapA, &full[s], kc * 64, dx, x0, dy, img * p.H + y0);
+          }
+          tma_load_2d(b_dst, &mapB, &full[s], tap * p.ka + kc * 64, n0);
         }
-        tma_load_2d(b_dst, &mapB, &full[s], tap * p.ka + kc * 64, n0);
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+      if (++kc == p.kchunks) {
+        kc = 0;
+        ++tap;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABuf;
+    // ---------------- MMA issuer (whole warp runs the loop, one elected lane issues) ----------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t desc_hi = smem_desc_hi(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+    const uint32_t ky_step = static_cast<uint32_t>(p.tw * 128) >> 4;
+    uint32_t s = 0, ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + s * (L::kStageBytes >> 4);
+      const uint32_t b_lo = a_lo + (L::kABuf >> 4);
+      if (elect_one_sync()) {
         if (HALO) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t adesc = make_smem_desc(a_addr + ky * p.tw * 128, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(b_addr + ky * L::kBTile, 16, 1024);
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || ky > 0 || k > 0) ? 1u : 0u);
-          }
+            for (int k = 0; k < 4; ++k)  // +32 bytes along K inside the swizzled 128-byte row: +2 in the >>4 field
+              umma_bf16_lo(tmem_base, a_lo + ky * ky_step + 2 * k, b_lo + ky * (L::kBTile >> 4) + 2 * k, desc_hi, idesc,
+                           it > 0 || ky > 0 || k > 0);
         } else {
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 bytes (= 16 bf16) along K inside the 128-byte swizzled row: +2 in the >>4 address field
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, it > 0 || k > 0);
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(accbar);
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (elect_one_sync()) umma_commit(accbar);
+    __syncwarp();
   } else {
     // ---------------- epilogue (128 threads) ----------------
     const int q = warp & 3;

@@ -88,19 +88,18 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1, p.err, DEV_ERR_EMPTY_TIMEOUT);
-        const int tile = t_begin + it;
-        const int tx = tile % p.tiles_x;
-        const int ty = (tile / p.tiles_x) % p.tiles_y;
-        const int img = tile / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * 8, y0 = ty * 8;
-        uint8_t* u_dst = smem + s * C::kStageBytes;
-        uint8_t* v_dst = u_dst + kUBytes;
+    // ---------------- TMA producer (whole warp runs the loop, one elected lane issues) ----------------
+    uint32_t s = 0, ph = 1;
+    int tile = t_begin;
+    int tx = tile % p.tiles_x;
+    int ty = (tile / p.tiles_x) % p.tiles_y;
+    int img = tile / (p.tiles_x * p.tiles_y);
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&empty[s], ph, p.err, DEV_ERR_EMPTY_TIMEOUT);
+      const int x0 = tx * 8, y0 = ty * 8;
+      uint8_t* u_dst = smem + s * C::kStageBytes;
+      uint8_t* v_dst = u_dst + kUBytes;
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full[s], C::kStageBytes);
 #pragma unroll
         for (int slab = 0; slab < 2; ++slab)
@@ -132,34 +131,50 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
                           j >> 1, img * p.H + y0);
         }
       }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+      if (++tx == p.tiles_x) {
+        tx = 0;
+        if (++ty == p.tiles_y) {
+          ty = 0;
+          ++img;
+        }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
-        tc_fence_after();
-        const uint32_t u_addr = smem_u32(smem + s * C::kStageBytes);
-        const uint32_t v_addr = u_addr + kUBytes;
+    // ---------------- MMA issuer (whole warp runs the loop, one elected lane issues) ----------------
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    const uint32_t desc_hi = smem_desc_hi(1024);
+    const uint32_t u_lo0 = smem_desc_lo(smem_u32(smem), 8192);
+    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem) + kUBytes, C::kVSlab);
+    uint32_t s = 0, ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
+      tc_fence_after();
+      const uint32_t u_lo = u_lo0 + s * (C::kStageBytes >> 4);
+      const uint32_t v_lo = v_lo0 + s * (C::kStageBytes >> 4);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int j = 0; j < C::kTaps; ++j) {
           // HALO: tap j = rows [8j, 8j+64) of the 80-row box (whole 1024-byte swizzle atoms)
-          const uint32_t vj = HALO ? v_addr + j * 1024 : v_addr + j * (BN / 64) * C::kVSlab;
+          const uint32_t vj = HALO ? v_lo + j * (1024 >> 4) : v_lo + j * (((BN / 64) * C::kVSlab) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixels (K) per MMA = 16 rows of 128 bytes
-            const uint64_t adesc = make_smem_desc(u_addr + k * 2048, 8192, 1024);
-            const uint64_t bdesc = make_smem_desc(vj + k * 2048, C::kVSlab, 1024);
-            umma_bf16(tmem_base + j * BN, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)  // 16 pixels (K) per MMA = 16 rows of 128 bytes
+            umma_bf16_lo(tmem_base + j * BN, u_lo + k * (2048 >> 4), vj + k * (2048 >> 4), desc_hi, idesc, it > 0 || k > 0);
         }
         umma_commit(&empty[s]);
       }
-      umma_commit(accbar);
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (elect_one_sync()) umma_commit(accbar);
+    __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> fp32 workspace ----------------
     const int q = warp & 3;

@@ -24,6 +24,10 @@ from . import ops
 
 BF16 = torch.bfloat16
 
+# weight-gradient kernels split the pixel dimension until about this many CTAs are in flight (the per-split partial
+# results are summed by wgrad_reduce in a fixed order); measured on B200 in profiles/
+WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
+
 
 def _kpad(cin: int) -> int:
     k = 9 * cin
@@ -458,7 +462,7 @@ class StepEngine:
         if st.first:
             kp = st.in_view.shape[3]
             ctas = max(1, kp // 128)
-            splits = max(1, min(total, (148 * 2) // ctas))
+            splits = max(1, min(total, WGRAD_CTA_TARGET // ctas))
             self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * cout * kp)
             return ("first", splits)
         if cout >= 128 or cin < 128:
@@ -467,7 +471,7 @@ class StepEngine:
         else:
             role = "neg"   # M <-> cin (U = input), N <-> cout
             ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
-        splits = max(1, min(total, max(1, (148 * 2) // ctas)))
+        splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
         self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 9 * cout * cin)
         return (role, splits)
 
@@ -509,7 +513,7 @@ class StepEngine:
         nb, h, w, _ = uc.x.shape
         total = ops.wgrad_tiles(nb, h, w)
         ctas = ((c + 127) // 128) * (c // 128 if c % 128 == 0 else c // 64)
-        splits = max(1, min(total, max(1, (148 * 2) // ctas)))
+        splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
         self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 4 * c * c)
         npix = nb * 4 * h * w
         nblk = max(1, min(1184, npix // 64))

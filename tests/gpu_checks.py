@@ -363,24 +363,29 @@ def check_bn_apply(n=4, H=16, W=32, Cc=64, seed=10) -> dict:
     return res
 
 
-def check_bn_bwd(n=4, H=16, W=32, Cc=64, seed=11) -> dict:
-    """BN+ReLU backward with three gradient sources: skip (+/- by timestamp), max-pool routing, direct."""
-    G = 2
+def check_bn_bwd(n=4, H=16, W=32, Cc=64, seed=11, order=("skip", "pool", "dir"), G=2) -> dict:
+    """BN+ReLU backward with up to four kinds of gradient source, in any order: `skip` (concat-buffer gradient of the
+    t2 - t1 difference: +/- by timestamp), `pool` (max-pool routing through the stored arg-max), `dir` (direct),
+    `head` (dz * w of a 1x1 head). The source order selects the kernel variant (generic / per-kind / 2x2-window)."""
     g, r, gamma, beta = _bn_setup(n, H, W, Cc, G, seed)
     mean, invstd, scale, shift, *_ = _bn_forward_cuda(r, gamma, beta, G)
     h = n // 2
     d_skip = bf16r(torch.randn(h, H, W, 2 * Cc, device=DEV, generator=g))  # concat-buffer gradient, first C = skip
     d_pool = bf16r(torch.randn(n, H // 2, W // 2, Cc, device=DEV, generator=g))
     d_dir = bf16r(torch.randn(n, H, W, Cc, device=DEV, generator=g))
+    dz = torch.randn(n, 1, H, W, device=DEV, generator=g)
+    w_head = torch.randn(Cc, device=DEV, generator=g)
     d_skip_b = d_skip.to(torch.bfloat16)
     pidx = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.uint8)
     ops.bn_apply(r, scale, shift, G, False, pool=torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.bfloat16),
                  pool_idx=pidx)
-    srcs = ops.make_srcs([
-        {"kind": 1, "t": d_skip_b[..., :Cc], "n_mod": h, "scale_lo": -1.0, "scale_hi": 1.0},
-        {"kind": 2, "t": d_pool.to(torch.bfloat16), "w": pidx},
-        {"kind": 1, "t": d_dir.to(torch.bfloat16)},
-    ])
+    table = {
+        "skip": {"kind": 1, "t": d_skip_b[..., :Cc], "n_mod": h, "scale_lo": -1.0, "scale_hi": 1.0},
+        "pool": {"kind": 2, "t": d_pool.to(torch.bfloat16), "w": pidx},
+        "dir": {"kind": 1, "t": d_dir.to(torch.bfloat16)},
+        "head": {"kind": 3, "t": dz, "w": w_head},
+    }
+    srcs = ops.make_srcs([table[k] for k in order])
     ws = torch.empty(ops.bn_bwd_ws_floats(n, H, W, Cc, G), device=DEV)
     dgamma = torch.empty(Cc, device=DEV)
     dbeta = torch.empty(Cc, device=DEV)
@@ -392,17 +397,51 @@ def check_bn_bwd(n=4, H=16, W=32, Cc=64, seed=11) -> dict:
     ga = gamma.clone().requires_grad_(True)
     be = beta.clone().requires_grad_(True)
     ys = []
-    for gi in range(2):
-        xs = x[gi * h:(gi + 1) * h]
+    per = n // G
+    for gi in range(G):
+        xs = x[gi * per:(gi + 1) * per]
         ys.append(F.relu(F.batch_norm(xs, None, None, ga, be, True, 0.1, 1e-5)))
     aa = torch.cat(ys, 0)
     # forward stores a in bf16 and pools the rounded values: route through the same rounding for the arg-max
     aq = aa + (bf16r(aa.detach()) - aa.detach())
-    loss = ((aa[h:] - aa[:h]) * nchw(d_skip[..., :Cc])).sum() + (F.max_pool2d(aq, 2) * nchw(d_pool)).sum() + \
-        (aa * nchw(d_dir)).sum()
+    loss = 0.0
+    if "skip" in order:
+        loss = loss + ((aa[h:] - aa[:h]) * nchw(d_skip[..., :Cc])).sum()
+    if "pool" in order:
+        loss = loss + (F.max_pool2d(aq, 2) * nchw(d_pool)).sum()
+    if "dir" in order:
+        loss = loss + (aa * nchw(d_dir)).sum()
+    if "head" in order:
+        loss = loss + ((aa * w_head.view(1, Cc, 1, 1)).sum(1, keepdim=True) * dz).sum()
     loss.backward()
     res = {"dr": err(nchw(dr.float()), x.grad), "dgamma": err(dgamma, ga.grad), "dbeta": err(dbeta, be.grad)}
     res["ok"] = res["dr"]["rel_l2"] < 8e-3 and res["dgamma"]["rel_l2"] < 2e-3 and res["dbeta"]["rel_l2"] < 2e-3
+    return res
+
+
+def check_bn_apply_pool(n=4, H=16, W=32, Cc=64, G=2, seed=14) -> dict:
+    """BN-apply + ReLU + MaxPool2d without the t2 - t1 difference (plain encoders), one or two stat-groups, with a second
+    copy into a concat slice: the 2x2-window kernel."""
+    g, r, gamma, beta = _bn_setup(n, H, W, Cc, G, seed)
+    mean, invstd, scale, shift, *_ = _bn_forward_cuda(r, gamma, beta, G)
+    a = torch.empty(n, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+    cat = torch.zeros(n, H, W, 2 * Cc, device=DEV, dtype=torch.bfloat16)
+    pool = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.bfloat16)
+    pidx = torch.empty(n, H // 2, W // 2, Cc, device=DEV, dtype=torch.uint8)
+    ops.bn_apply(r, scale, shift, G, False, a=a, a2=cat[..., :Cc], pool=pool, pool_idx=pidx)
+    torch.cuda.synchronize()
+    per = n // G
+    x = nchw(r.float())
+    ys = [F.relu(F.batch_norm(x[gi * per:(gi + 1) * per], None, None, gamma, beta, True, 0.1, 1e-5)) for gi in range(G)]
+    ref_a = torch.cat(ys, 0)
+    res = {"a": err(nchw(a.float()), ref_a), "pool": err(nchw(pool.float()), F.max_pool2d(ref_a, 2))}
+    res["a2_same"] = bool(torch.equal(cat[..., :Cc], a) and (cat[..., Cc:] == 0).all().item())
+    win = a.float().view(n, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 5, 2, 4).reshape(n, H // 2, W // 2, Cc, 4)
+    res["pool_idx_ok"] = bool(torch.equal(pidx.long(), win.argmax(-1)) or
+                              torch.equal(win.gather(-1, pidx.long().unsqueeze(-1)).squeeze(-1), win.max(-1).values))
+    res["pool_is_max_of_stored"] = bool(torch.equal(pool.float(), win.max(-1).values))
+    res["ok"] = (res["a"]["rel_l2"] < 4e-3 and res["pool"]["rel_l2"] < 4e-3 and res["a2_same"] and res["pool_idx_ok"] and
+                 res["pool_is_max_of_stored"])
     return res
 
 
@@ -562,6 +601,18 @@ ALL_CHECKS = {
     "head": check_head,
     "bn_apply": check_bn_apply,
     "bn_bwd": check_bn_bwd,
+    "bn_bwd_dir": lambda: check_bn_bwd(order=("dir",), seed=15),
+    "bn_bwd_dir_G1_128": lambda: check_bn_bwd(2, 16, 16, 128, order=("dir",), G=1, seed=16),
+    "bn_bwd_skip_dir": lambda: check_bn_bwd(order=("skip", "dir"), seed=17),
+    "bn_bwd_pool_dir_window": lambda: check_bn_bwd(order=("pool", "dir"), seed=18),
+    "bn_bwd_pool_dir_window_G1_256": lambda: check_bn_bwd(2, 16, 16, 256, order=("pool", "dir"), G=1, seed=19),
+    "bn_bwd_pool_skip_window": lambda: check_bn_bwd(order=("pool", "skip"), seed=20),
+    "bn_bwd_pool_skip_dir_window": lambda: check_bn_bwd(order=("pool", "skip", "dir"), seed=21),
+    "bn_bwd_pool_only_window": lambda: check_bn_bwd(order=("pool",), seed=22),
+    "bn_bwd_head": lambda: check_bn_bwd(order=("head",), G=1, seed=23),
+    "bn_bwd_dir_head": lambda: check_bn_bwd(order=("dir", "head"), seed=24),
+    "bn_apply_pool_G2": check_bn_apply_pool,
+    "bn_apply_pool_G1_512": lambda: check_bn_apply_pool(2, 16, 16, 512, G=1, seed=25),
     "conv3x3_64_64": lambda: check_conv3x3(2, 32, 32, 64, 64),
     "conv3x3_128_128_16": lambda: check_conv3x3(2, 16, 16, 128, 128, seed=31),
     "conv3x3_64_128_64": lambda: check_conv3x3(1, 64, 64, 64, 128, bias=False, seed=32),
