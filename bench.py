@@ -182,8 +182,8 @@ def profile_step(ts, steps: int = 2) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="dualstream", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the config's)")
@@ -268,47 +268,64 @@ def main() -> None:
     if not args.no_e2e:
         crit = loss_functions.get_criterion("PowerJaccardLoss")
 
-        def e2e_step():
-            x1 = host["x_t1"].to(dev, non_blocking=True)
-            x2 = host["x_t2"].to(dev, non_blocking=True)
+        from multimodal_siamese_cd_b200.data import DevicePrefetcher, LossReader
+
+        def e2e_step(b, reader):
+            # the body of the reference loop (train_supervised.py:63-79 and its dual-task / semi-supervised variants)
             for p in net.parameters():
                 p.grad = None
-            outs = net(x1, x2)
+            outs = net(b["x_t1"], b["x_t2"])
             if kind == "supervised":
-                loss = crit(outs, host["y_change"].to(dev, non_blocking=True))
+                loss = crit(outs, b["y_change"])
             elif kind == "dualtask":
                 c, s1, s2 = outs
-                loss = (crit(c, host["y_change"].to(dev, non_blocking=True)) +
-                        (crit(s1, host["y_sem_t1"].to(dev, non_blocking=True)) +
-                         crit(s2, host["y_sem_t2"].to(dev, non_blocking=True))) / 2) / 2
+                loss = (crit(c, b["y_change"]) + (crit(s1, b["y_sem_t1"]) + crit(s2, b["y_sem_t2"])) / 2) / 2
             else:
                 f, s1, s2 = outs
-                y = host["y_change"].to(dev, non_blocking=True)
-                lab = is_labeled
+                y = b["y_change"]
+                lab = b["is_labeled"]
                 p2 = torch.sigmoid(s2)
                 loss = alpha * (crit(f[lab,], y[lab,]) + crit(s1[lab,], y[lab,]) + crit(s2[lab,], y[lab,])) / 3 + \
                     (1 - alpha) * crit(s1[~lab,], p2[~lab,])
             loss.backward()
-            return loss.item()  # device -> host read of the step's result (train_supervised.py:79)
+            return reader.push(loss)  # device -> host read of every step's loss (train_supervised.py:79), one step late
 
-        for _ in range(W_):
-            e2e_step()
+        keys = {"supervised": ["y_change"], "dualtask": ["y_change", "y_sem_t1", "y_sem_t2"], "mmcr": ["y_change"]}[kind]
+        host_batch = {"x_t1": host["x_t1"], "x_t2": host["x_t2"], "is_labeled": is_labeled, **{k: host[k] for k in keys}}
+
+        def host_batches(n):           # the pinned host batch, staged host -> device again for every step
+            for _ in range(n):
+                yield host_batch
+
+        reader = LossReader(dev)
+        for b in DevicePrefetcher(host_batches(W_), dev):
+            e2e_step(b, reader)
+        reader.drain()
         barrier()
-        t0 = time.perf_counter()
+        pf = DevicePrefetcher(host_batches(K), dev)
+        reader = LossReader(dev)
+        e2e_losses = []
         e0.record()
-        for _ in range(K):
-            e2e_step()
+        for b in pf:
+            v = e2e_step(b, reader)
+            if v is not None:
+                e2e_losses.append(v)
+        e2e_losses += reader.drain()
         e1.record()
         barrier()
+        assert len(e2e_losses) == K and all(x == x for x in e2e_losses), "every step's loss must have been read back"
         ems = e0.elapsed_time(e1) / K
         t = torch.tensor([ems], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = t.item()
-        n_t = {"supervised": 1, "dualtask": 3, "mmcr": 1}[kind]
-        h2d = 2 * B * xc * H * W * 4 + n_t * B * H * W * 4
-        e2e = {"value": B * world / ems * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ems, "api": "networks.create_network(cfg)(x_t1, x_t2) -> get_criterion('PowerJaccardLoss') -> backward()"}
+        h2d = pf.bytes_staged // K      # counted from the tensors copied host -> device in the timed region
+        e2e = {"value": B * world / ems * 1e3, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": reader.bytes_read // K, "ms_per_step": ems, "last_loss": e2e_losses[-1],
+               "api": "for batch in data.DevicePrefetcher(loader, device): net = networks.create_network(cfg); "
+                      "loss = get_criterion('PowerJaccardLoss')(net(x_t1, x_t2), y); loss.backward(); "
+                      "data.LossReader.push(loss)  # pinned-host inputs staged one step ahead on a side stream, every "
+                      "step's loss copied to pinned host memory and read one step later"}
 
     if rank != 0:
         if world > 1:

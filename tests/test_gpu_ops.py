@@ -17,3 +17,30 @@ def test_kernel(name):
     assert res["ok"], res
     if "ulp_frac" in res:
         assert res["ulp_frac"] < res.get("ulp_tol", 5e-3) and res["rel_l2_rounded"] < 5e-4, res
+
+
+def test_device_prefetcher_order_and_contents():
+    """data.DevicePrefetcher yields every batch once, in order, with the host contents, while reusing two buffer sets."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multimodal_siamese_cd_b200.data import DevicePrefetcher
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    host = [{"x_t1": torch.rand(2, 6, 32, 32, generator=g).pin_memory(), "x_t2": torch.rand(2, 6, 32, 32, generator=g),
+             "y_change": (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float(), "is_labeled": torch.tensor([True, False]),
+             "aoi_id": f"aoi{i}"} for i in range(7)]
+    pf = DevicePrefetcher(iter(host), dev)
+    seen = 0
+    acc = []
+    for i, b in enumerate(pf):
+        assert b["x_t1"].is_cuda and b["x_t2"].is_cuda and b["y_change"].is_cuda
+        assert not b["is_labeled"].is_cuda and b["aoi_id"] == f"aoi{i}"
+        acc.append((b["x_t1"] * 2).sum())          # queue work on the batch before the next one is staged
+        assert torch.equal(b["x_t1"].cpu(), host[i]["x_t1"]) and torch.equal(b["y_change"].cpu(), host[i]["y_change"])
+        seen += 1
+    assert seen == 7
+    for i, a in enumerate(acc):
+        assert abs(a.item() - 2 * host[i]["x_t1"].sum().item()) < 1e-2
+    assert pf.bytes_staged == sum(v.numel() * 4 for h in host for k, v in h.items() if k in ("x_t1", "x_t2", "y_change"))
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher(iter(host), torch.device("cpu"))
