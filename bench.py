@@ -119,7 +119,7 @@ def cpu_step_rate(cfgname: str, sample_pairs: int, steps: int, warmup: int, thre
                       f"median step {med:.2f} s", "sec_per_step": med, "pairs": n}
 
 
-def run_reference_arm(args) -> None:
+def run_reference_arm(args, out) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -136,7 +136,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -179,7 +179,17 @@ def profile_step(ts, steps: int = 2) -> dict:
     return fam
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else a library prints there (NCCL's version banner, ...) goes to
+    stderr. Returns a file object on the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 def main() -> None:
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -191,7 +201,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch
@@ -384,7 +394,7 @@ def main() -> None:
                           "frac_of_tensor_peak": value / world * gf_pair / 1e3 / pk["tensor"]},
         "loss": loss_val,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
