@@ -2,6 +2,7 @@
 // Everything exported is extern "C" with plain pointers and sizes; kernels live in the other .cu files.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -128,6 +129,16 @@ bool chan_ok(int C) { return C >= 64 && C % 64 == 0 && 256 % (C / 8) == 0; }
 
 }  // namespace
 
+namespace b200cd {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200CD_PDL");
+    return e != nullptr && e[0] == '1';  // measured neutral-to-slightly-negative inside CUDA graphs: off by default
+  }();
+  return on;
+}
+}  // namespace b200cd
+
 extern "C" {
 
 int b200cd_abi_version(void) { return B200CD_ABI_VERSION; }
@@ -252,7 +263,8 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   p.err = err;
   // N tile: 64 when the width is not a multiple of 128; 256 on request (flags bit 1) when it divides the width —
   // a 128 x 256 tile reads 96 B/clk of operands from shared memory per MMA instead of 128 B/clk (the SM's limit).
-  const int width = out_mode == 1 ? cout : N;
+  // out_mode 1: every 64-channel slab of the tile belongs to one (dy, dx) tap (cout % 64 == 0), so the tile may span taps
+  const int width = N;
   int bn = (width % 128 == 0) ? 128 : 64;
   if ((flags & 2) && width % 256 == 0 && !halo) bn = 256;
   if (pair && width % 256 == 0) bn = 256;

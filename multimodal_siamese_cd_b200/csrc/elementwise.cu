@@ -48,6 +48,8 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret
 __global__ void __launch_bounds__(128) pack_input_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                                          int csrc, int c_lo, int nc, int cat_mode, int B, int H, int W,
                                                          int kpad, __nv_bfloat16* __restrict__ out, long long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint32_t sm32[];
   const int rowwords = kpad / 2 + 1;  // odd word stride -> conflict-free
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(sm32);
@@ -140,6 +142,8 @@ __device__ __forceinline__ float pack_weight_value(int mode, const float* __rest
 
 __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
                                     int d1, int kpad, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   out[i] = __float2bfloat16_rn(pack_weight_value(mode, w, d0, d1, kpad, i));
@@ -179,6 +183,8 @@ __device__ __forceinline__ void pack_tile_store(int mode, const float* tile, int
 }
 
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[kPackTile * (kPackTile * 9 + 1)];
   const long long b = blockIdx.x;
   int lo = 0, hi = njobs - 1;
@@ -229,6 +235,8 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
 __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float2* __restrict__ partial, int ld, int C,
                                                               int tiles_per_group, int spl,
                                                               double* __restrict__ partial2) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double sh[8][32][2];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int l = threadIdx.x >> 5;
@@ -282,6 +290,8 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
                                                           float momentum, float eps, int train, int order_rev,
                                                           float* __restrict__ mean, float* __restrict__ invstd,
                                                           float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;  // whole warp
@@ -351,6 +361,8 @@ struct ApplyArgs {
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = p.C >> 3;
   const int H2 = (p.H + 1) >> 1, W2 = (p.W + 1) >> 1;
   const int n_units = p.diff ? p.n_img / 2 : p.n_img;
@@ -447,6 +459,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs p) {
 //   else: grid.y = G, the block handles the images of one stat-group
 template <bool DIFF>
 __global__ void __launch_bounds__(256, 3) bn_apply_win_kernel(const ApplyArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
   const int cv = threadIdx.x % cvecs;
@@ -546,6 +560,8 @@ __global__ void __launch_bounds__(256, 3) bn_apply_win_kernel(const ApplyArgs p)
 // Per-pixel variant (no pooling, no difference): a thread keeps its 8 channels, so scale/shift stay in registers;
 // four independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256, 4) bn_apply_px_kernel(const ApplyArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
   const int cv = threadIdx.x % cvecs;
@@ -744,6 +760,8 @@ __device__ __forceinline__ void gather_multi(const BwdArgs& p, const int (&gpix)
 // grid = (nblk, G); block = 256 threads = (C/8 channel vectors) x (256/(C/8)) pixel lanes
 template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const BwdArgs p, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float shred[];  // [lanes][C][2]
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
@@ -896,6 +914,8 @@ __device__ __forceinline__ void gather_window(const BwdArgs& p, int n, int y2, i
 
 template <int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_win_kernel(const BwdArgs p, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float shred[];  // [lanes][C][2]
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
@@ -959,6 +979,8 @@ template <int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_dx_win_kernel(const BwdArgs p, const float* __restrict__ coefA,
                                                                const float* __restrict__ coefB,
                                                                __nv_bfloat16* __restrict__ dr, long long ld_dr) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
   const int cv = threadIdx.x % cvecs;
@@ -1007,6 +1029,8 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
                                                              const float* __restrict__ scale, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, float* __restrict__ coefA,
                                                              float* __restrict__ coefB) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double sh[32][33][2];
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -1065,6 +1089,8 @@ template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, const float* __restrict__ coefA,
                                                            const float* __restrict__ coefB,
                                                            __nv_bfloat16* __restrict__ dr, long long ld_dr) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = p.C >> 3;
   const int lanes = 256 / cvecs;
   const int cv = threadIdx.x % cvecs;
@@ -1126,6 +1152,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
                                                        const __nv_bfloat16* __restrict__ a1, long long ld1, int C,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        long long npix, float* __restrict__ logits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long pix = gid >> 3;
   const int sub = static_cast<int>(gid & 7);
@@ -1162,6 +1190,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int C,
                                                      const float* __restrict__ wgt, long long npix,
                                                      float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float shred[];
   const long long pb = npix * blockIdx.x / gridDim.x, pe = npix * (blockIdx.x + 1) / gridDim.x;
   if (x == nullptr) {
@@ -1221,6 +1251,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 
 __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
                                                              float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double sh[32][33];
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -1254,6 +1286,8 @@ __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, int layout,
                                     int d0, int d1, int taps, float* __restrict__ grad, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   // i enumerates the workspace order (coalesced reads); writes are the strided side
@@ -1287,52 +1321,69 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, lo
   grad[dst] = (a0 + a1) + (a2 + a3);
 }
 
-// Many splits, few weights (the 64-channel layers: 98 splits of 36 864 weights): block = 32 consecutive workspace
-// elements x 8 parts; part p sums splits p, p+8, ... (two chains), then a fixed-order sum over the parts in shared
-// memory. Same result on every run.
-__global__ void __launch_bounds__(256) wgrad_reduce_wide_kernel(const float* __restrict__ ws, int splits,
-                                                                long long split_stride, int layout, int d0, int d1,
-                                                                int taps, float* __restrict__ grad, long long total) {
-  __shared__ float sh[8][33];
+// Vectorised variant (total % 4 == 0, 16-byte aligned workspace): block = 32 lanes x 8 parts; a lane owns four
+// consecutive workspace elements (one 16-byte load per split), part p sums splits p, p+8, ... in two chains, then a
+// fixed-order sum over the parts in shared memory. Same result on every run.
+__global__ void __launch_bounds__(256) wgrad_reduce_v4_kernel(const float* __restrict__ ws, int splits,
+                                                              long long split_stride, int layout, int d0, int d1,
+                                                              int taps, float* __restrict__ grad, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 sh[8][33];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
-  const long long i = static_cast<long long>(blockIdx.x) * 32 + e;
-  float acc = 0.f;
-  long long dst = 0;
+  const long long i = (static_cast<long long>(blockIdx.x) * 32 + e) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long src = 0;
   if (i < total) {
-    long long src;
     if (layout == 0) {
-      const int b = static_cast<int>(i % d1);
-      const int a = static_cast<int>((i / d1) % d0);
-      const int tap = static_cast<int>(i / (static_cast<long long>(d1) * d0));
       src = i;
-      dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
     } else {
       const int k = static_cast<int>(i % (taps * d1));
       const int a = static_cast<int>(i / (taps * d1));
-      const int tap = k / d1, b = k - tap * d1;
-      const long long ld1 = split_stride / d0;
-      src = static_cast<long long>(a) * ld1 + k;
-      dst = (static_cast<long long>(a) * d1 + b) * taps + tap;
+      src = static_cast<long long>(a) * (split_stride / d0) + k;
     }
     const float* q = ws + src;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     int sp = part;
-    for (; sp + 24 < splits; sp += 32) {
-      a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
-      a1 += __ldg(q + static_cast<long long>(sp + 8) * split_stride);
-      a2 += __ldg(q + static_cast<long long>(sp + 16) * split_stride);
-      a3 += __ldg(q + static_cast<long long>(sp + 24) * split_stride);
+    for (; sp + 8 < splits; sp += 16) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * split_stride));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 8) * split_stride));
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
     }
-    for (; sp < splits; sp += 8) a0 += __ldg(q + static_cast<long long>(sp) * split_stride);
-    acc = (a0 + a1) + (a2 + a3);
+    if (sp < splits) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * split_stride));
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+    }
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
   }
   sh[part][e] = acc;
   __syncthreads();
   if (part == 0 && i < total) {
-    float r = sh[0][e];
+    float4 r = sh[0][e];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) r += sh[k][e];
-    grad[dst] = r;
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = sh[k][e];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long iu = i + u;
+      long long dst;
+      if (layout == 0) {
+        const int bb = static_cast<int>(iu % d1);
+        const int a = static_cast<int>((iu / d1) % d0);
+        const int tap = static_cast<int>(iu / (static_cast<long long>(d1) * d0));
+        dst = (static_cast<long long>(a) * d1 + bb) * taps + tap;
+      } else {
+        const int k = static_cast<int>(iu % (taps * d1));
+        const int a = static_cast<int>(iu / (taps * d1));
+        const int tap = k / d1, bb = k - tap * d1;
+        dst = (static_cast<long long>(a) * d1 + bb) * taps + tap;
+      }
+      grad[dst] = rr[u];
+    }
   }
 }
 
@@ -1349,6 +1400,8 @@ __global__ void __launch_bounds__(256) pj_reduce_kernel(const float* __restrict_
                                                         int t_is_logit, const unsigned char* __restrict__ rowmask,
                                                         int sel, int rows, long long per_row,
                                                         double* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[3][256];
   const long long total = static_cast<long long>(rows) * per_row;
   float a = 0.f, b = 0.f, c = 0.f;
@@ -1389,6 +1442,8 @@ __global__ void __launch_bounds__(256) pj_reduce_kernel(const float* __restrict_
 }
 
 __global__ void pj_finalize_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x < 3) {
     double a = 0.0;
     for (int i = 0; i < nblk; ++i) a += partial[i * 3 + threadIdx.x];
@@ -1397,6 +1452,8 @@ __global__ void pj_finalize_kernel(const double* __restrict__ partial, int nblk,
 }
 
 __global__ void pj_loss_kernel(const double* __restrict__ sums, float* __restrict__ loss) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double I = sums[0];
   const double D = sums[1] + sums[2] - I + 1e-6;
   *loss = static_cast<float>(1.0 - I / D);
@@ -1407,6 +1464,8 @@ __global__ void __launch_bounds__(256) pj_bwd_kernel(const float* __restrict__ z
                                                      int rows, long long per_row, const double* __restrict__ sums,
                                                      const float* __restrict__ gptr, float gmul, int accumulate,
                                                      float* __restrict__ dz, float* __restrict__ dt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * per_row;
   const float I = static_cast<float>(sums[0]);
   const float D = static_cast<float>(sums[1] + sums[2] - sums[0] + 1e-6);
@@ -1469,8 +1528,8 @@ cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, in
   const long long npix = static_cast<long long>(n_img) * H * W;
   const int grid = static_cast<int>((npix + 127) / 128);
   const size_t smem = 128 * (kpad / 2 + 1) * 4;
-  pack_input_kernel<<<grid, 128, smem, st>>>(src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad,
-                                             reinterpret_cast<__nv_bfloat16*>(out), npix);
+  launch_k(pack_input_kernel, dim3(grid), dim3(128), smem, st, src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad,
+           reinterpret_cast<__nv_bfloat16*>(out), npix);
   return cudaGetLastError();
 }
 
@@ -1479,7 +1538,7 @@ cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int
   if (mode == 0 || mode == 1) total = 9ll * d0 * d1;
   else if (mode == 2) total = static_cast<long long>(d0) * kpad;
   else total = 4ll * d0 * d1;
-  pack_weights_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(
+  launch_k(pack_weights_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, 
       mode, w, reinterpret_cast<__nv_bfloat16*>(out), d0, d1, kpad, total);
   return cudaGetLastError();
 }
@@ -1494,14 +1553,14 @@ int pack_job_blocks(int mode, int d0, int d1, int kpad) {
 }
 
 cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long long total_blocks, cudaStream_t st) {
-  pack_weights_batched_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, st>>>(jobs, njobs);
+  launch_k(pack_weights_batched_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, st, jobs, njobs);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
                                    double* partial2, cudaStream_t st) {
   dim3 grid((C + 31) / 32, G, spl);
-  bn_stats_reduce_kernel<<<grid, 256, 0, st>>>(partial, ld, C, tiles_per_group, spl, partial2);
+  launch_k(bn_stats_reduce_kernel, dim3(grid), dim3(256), 0, st, partial, ld, C, tiles_per_group, spl, partial2);
   return cudaGetLastError();
 }
 
@@ -1509,7 +1568,7 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
                                const float* beta, float* running_mean, float* running_var, long long* nbt,
                                float momentum, float eps, int train, int order_rev, float* mean, float* invstd,
                                float* scale, float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial2, spl, C, G, count, gamma, beta, running_mean,
+  launch_k(bn_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial2, spl, C, G, count, gamma, beta, running_mean,
                                                       running_var, nbt, momentum, eps, train, order_rev, mean, invstd,
                                                       scale, shift);
   return cudaGetLastError();
@@ -1535,7 +1594,7 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
     long long nblk = npx / ((256 / (C / 8)) * 16);
     const long long cap = (148 * 4 * 4) / G;
     nblk = nblk > cap ? cap : (nblk < 1 ? 1 : nblk);
-    bn_apply_px_kernel<<<dim3(static_cast<unsigned>(nblk), G), 256, 0, st>>>(p);
+    launch_k(bn_apply_px_kernel, dim3(dim3(static_cast<unsigned>(nblk), G)), dim3(256), 0, st, p);
     return cudaGetLastError();
   }
   if (H % 2 == 0 && W % 2 == 0 && C % 64 == 0 && 256 % (C / 8) == 0 &&
@@ -1545,12 +1604,12 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
     long long nblk = nwin / (static_cast<long long>(lanes) * 4);
     const long long cap = (148 * 3 * 4) / (diff ? 1 : G);
     nblk = nblk > cap ? cap : (nblk < 1 ? 1 : nblk);
-    if (diff) bn_apply_win_kernel<true><<<dim3(static_cast<unsigned>(nblk), 1), 256, 0, st>>>(p);
-    else bn_apply_win_kernel<false><<<dim3(static_cast<unsigned>(nblk), G), 256, 0, st>>>(p);
+    if (diff) launch_k(bn_apply_win_kernel<true>, dim3(dim3(static_cast<unsigned>(nblk), 1)), dim3(256), 0, st, p);
+    else launch_k(bn_apply_win_kernel<false>, dim3(dim3(static_cast<unsigned>(nblk), G)), dim3(256), 0, st, p);
     return cudaGetLastError();
   }
   const long long total = static_cast<long long>(diff ? n_img / 2 : n_img) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(p);
+  launch_k(bn_apply_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, p);
   return cudaGetLastError();
 }
 
@@ -1594,12 +1653,12 @@ cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* sca
   dim3 grid(nblk, G);
   if (bn_bwd_use_windows(srcs, H, W)) {
     const int k1 = srcs.s[1].kind, k2 = srcs.s[2].kind;
-    if (k1 == 1 && k2 == 1) bn_bwd_reduce_win_kernel<1, 1><<<grid, 256, smem, st>>>(p, partial);
-    else if (k1 == 1) bn_bwd_reduce_win_kernel<1, 0><<<grid, 256, smem, st>>>(p, partial);
-    else bn_bwd_reduce_win_kernel<0, 0><<<grid, 256, smem, st>>>(p, partial);
+    if (k1 == 1 && k2 == 1) launch_k(bn_bwd_reduce_win_kernel<1, 1>, dim3(grid), dim3(256), smem, st, p, partial);
+    else if (k1 == 1) launch_k(bn_bwd_reduce_win_kernel<1, 0>, dim3(grid), dim3(256), smem, st, p, partial);
+    else launch_k(bn_bwd_reduce_win_kernel<0, 0>, dim3(grid), dim3(256), smem, st, p, partial);
     return cudaGetLastError();
   }
-#define B200CD_CALL(A, B, Cc) bn_bwd_reduce_kernel<A, B, Cc><<<grid, 256, smem, st>>>(p, partial)
+#define B200CD_CALL(A, B, Cc) launch_k(bn_bwd_reduce_kernel<A, B, Cc>, dim3(grid), dim3(256), smem, st, p, partial)
   B200CD_BWD_DISPATCH(B200CD_CALL);
 #undef B200CD_CALL
   return cudaGetLastError();
@@ -1608,7 +1667,7 @@ cudaError_t launch_bn_bwd_reduce(const void* r, long long ld_r, const float* sca
 cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int C, int G, double count, const float* mean,
                                    const float* invstd, const float* scale, float* dgamma, float* dbeta, float* coefA,
                                    float* coefB, cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta,
+  launch_k(bn_bwd_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta,
                                                          coefA, coefB);
   return cudaGetLastError();
 }
@@ -1621,13 +1680,13 @@ cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, 
   if (bn_bwd_use_windows(srcs, H, W)) {
     const int k1 = srcs.s[1].kind, k2 = srcs.s[2].kind;
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dr);
-    if (k1 == 1 && k2 == 1) bn_bwd_dx_win_kernel<1, 1><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
-    else if (k1 == 1) bn_bwd_dx_win_kernel<1, 0><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
-    else bn_bwd_dx_win_kernel<0, 0><<<grid, 256, 0, st>>>(p, coefA, coefB, o, ld_dr);
+    if (k1 == 1 && k2 == 1) launch_k(bn_bwd_dx_win_kernel<1, 1>, dim3(grid), dim3(256), 0, st, p, coefA, coefB, o, ld_dr);
+    else if (k1 == 1) launch_k(bn_bwd_dx_win_kernel<1, 0>, dim3(grid), dim3(256), 0, st, p, coefA, coefB, o, ld_dr);
+    else launch_k(bn_bwd_dx_win_kernel<0, 0>, dim3(grid), dim3(256), 0, st, p, coefA, coefB, o, ld_dr);
     return cudaGetLastError();
   }
 #define B200CD_CALL(A, B, Cc) \
-  bn_bwd_dx_kernel<A, B, Cc><<<grid, 256, 0, st>>>(p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr)
+  launch_k(bn_bwd_dx_kernel<A, B, Cc>, dim3(grid), dim3(256), 0, st, p, coefA, coefB, reinterpret_cast<__nv_bfloat16*>(dr), ld_dr)
   B200CD_BWD_DISPATCH(B200CD_CALL);
 #undef B200CD_CALL
   return cudaGetLastError();
@@ -1636,7 +1695,7 @@ cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, 
 cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
                             const float* b, long long npix, float* logits, cudaStream_t st) {
   const long long threads = npix * 8;
-  head_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(
+  launch_k(head_fwd_kernel, dim3(static_cast<int>((threads + 255) / 256)), dim3(256), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(a0), ld0, reinterpret_cast<const __nv_bfloat16*>(a1), ld1, C, w, b, npix,
       logits);
   return cudaGetLastError();
@@ -1646,40 +1705,42 @@ cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, 
                           float* partial, cudaStream_t st) {
   size_t smem = 256 * sizeof(float);
   if (x != nullptr) smem = static_cast<size_t>(256 / (C / 8)) * C * sizeof(float);
-  colsum_kernel<<<nblk, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, C, wgt, npix, partial);
+  launch_k(colsum_kernel, dim3(nblk), dim3(256), smem, st, reinterpret_cast<const __nv_bfloat16*>(x), ld, C, wgt, npix, partial);
   return cudaGetLastError();
 }
 
 cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float* out, cudaStream_t st) {
-  colsum_finalize_kernel<<<(C + 31) / 32, 1024, 0, st>>>(partial, nblk, C, out);
+  launch_k(colsum_finalize_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, partial, nblk, C, out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_wgrad_reduce(const float* ws, int splits, long long split_stride, int layout, int d0, int d1,
                                 int taps, float* grad, cudaStream_t st) {
   const long long total = static_cast<long long>(d0) * d1 * taps;
-  if (splits >= 16 && total <= (1ll << 20))
-    wgrad_reduce_wide_kernel<<<static_cast<int>((total + 31) / 32), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
-                                                                                  taps, grad, total);
+  const bool v4 = total % 4 == 0 && split_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0 &&
+                  (layout == 0 || ((static_cast<long long>(taps) * d1) % 4 == 0 && (split_stride / d0) % 4 == 0));
+  if (v4 && splits >= 16)
+    launch_k(wgrad_reduce_v4_kernel, dim3(static_cast<unsigned>((total / 4 + 31) / 32)), dim3(256), 0, st, ws, splits,
+             split_stride, layout, d0, d1, taps, grad, total);
   else
-    wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(ws, splits, split_stride, layout, d0, d1,
-                                                                               taps, grad, total);
+    launch_k(wgrad_reduce_kernel, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, st, ws, splits, split_stride,
+             layout, d0, d1, taps, grad, total);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pj_reduce(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel,
                              int rows, long long per_row, int nblk, double* partial, cudaStream_t st) {
-  pj_reduce_kernel<<<nblk, 256, 0, st>>>(z, t, t_is_logit, rowmask, sel, rows, per_row, partial);
+  launch_k(pj_reduce_kernel, dim3(nblk), dim3(256), 0, st, z, t, t_is_logit, rowmask, sel, rows, per_row, partial);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pj_finalize(const double* partial, int nblk, double* sums, cudaStream_t st) {
-  pj_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, sums);
+  launch_k(pj_finalize_kernel, dim3(1), dim3(32), 0, st, partial, nblk, sums);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pj_loss(const double* sums, float* loss, cudaStream_t st) {
-  pj_loss_kernel<<<1, 1, 0, st>>>(sums, loss);
+  launch_k(pj_loss_kernel, dim3(1), dim3(1), 0, st, sums, loss);
   return cudaGetLastError();
 }
 
@@ -1687,7 +1748,7 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
                           int rows, long long per_row, const double* sums, const float* gptr, float gmul,
                           int accumulate, float* dz, float* dt, cudaStream_t st) {
   const long long total = static_cast<long long>(rows) * per_row;
-  pj_bwd_kernel<<<grid_for(total / 4, 256), 256, 0, st>>>(z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr,
+  launch_k(pj_bwd_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, st, z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr,
                                                           gmul, accumulate, dz, dt);
   return cudaGetLastError();
 }

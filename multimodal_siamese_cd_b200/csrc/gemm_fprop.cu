@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap mapO,
                                                          const FpropParams p) {
   using L = FpropSmem<BN, STAGES, HALO>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kThreads) fprop_kernel(const __grid_constant__
     tmem_alloc(tmem_slot, BN);
     tmem_relinquish();
   }
+  pdl_wait();  // everything above is independent of the predecessor kernel's output
   if (threadIdx.x >= 64) {
     for (int t = threadIdx.x - 64; t < BN; t += 128) {
       float b = 0.f;
@@ -277,7 +279,7 @@ cudaError_t launch_one(const CUtensorMap& mapA, const CUtensorMap& mapB, const C
     attr_set = true;
   }
   dim3 grid(num_tiles, p.N / BN, 1);
-  fprop_kernel<BN, STAGES, HALO><<<grid, kThreads, L::kDynamic, stream>>>(mapA, mapB, mapO, p);
+  launch_k(fprop_kernel<BN, STAGES, HALO>, dim3(grid), dim3(kThreads), L::kDynamic, stream, mapA, mapB, mapO, p);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap mapO,
                                                                  const FpropParams p, const int num_tiles) {
   using L = PairCfg<BN>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t align_pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   if (align_pad + L::kTotal > static_cast<uint32_t>(L::kDynamic)) {  // uniform over the grid: nobody touches a barrier
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above is independent of the predecessor kernel's output
 
   if (warp == 0) {
     // ---------------- TMA producer (one warp per CTA, one elected lane issues; full barriers live in the leader) ------
@@ -419,13 +421,15 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::kDynamic;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = 2;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT>, mapA, mapB, mapO, p, num_tiles);
 }
 

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
                                                          const WgradParams p) {
   using C = WgradCfg<BN, MODE, HALO>;
   constexpr int STAGES = C::kStages;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above is independent of the predecessor kernel's output
 
   if (warp == 0) {
     // ---------------- TMA producer (whole warp runs the loop, one elected lane issues) ----------------
@@ -227,7 +229,7 @@ cudaError_t launch_one(const CUtensorMap& mapU, const CUtensorMap& mapV, const W
     attr_set = true;
   }
   dim3 grid((p.cu + 127) / 128, p.cv / BN, (MODE == 0 ? 3 : 1) * p.splits);
-  wgrad_kernel<BN, MODE, HALO><<<grid, kThreads, C::kDynamic, stream>>>(mapU, mapV, p);
+  launch_k(wgrad_kernel<BN, MODE, HALO>, dim3(grid), dim3(kThreads), C::kDynamic, stream, mapU, mapV, p);
   return cudaGetLastError();
 }
 

@@ -5,7 +5,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace b200cd {
+
+// Launch helper. With B200CD_PDL=1 in the environment kernels are launched with the programmatic-dependent-launch
+// attribute (see ptx.cuh: pdl_wait); by default they are plain stream-ordered launches and the kernels'
+// griddepcontrol instructions are no-ops (measured on B200: PDL does not shorten the graph-replayed step).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ----------------------------------------------------------------------------------------------
 // G1: implicit-GEMM "fprop-like" kernel.  D[pixel, n] = sum_{tap, k} A_tap[pixel, k] * B[n, tap*ka + k]
