@@ -211,6 +211,26 @@ int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned
                   int64_t per_row, const double* sums, const float* gptr, float gmul, int accumulate, float* dz,
                   float* dt, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * AdamW step over every parameter tensor in ONE launch — optim.AdamW(net.parameters(), lr=cfg.TRAINER.LR,
+ * weight_decay=0.01) train_supervised.py:32 (decoupled weight decay, betas (0.9, 0.999), eps 1e-8, no amsgrad).
+ * `jobs_dev` is a DEVICE array; job j owns thread blocks [start_j, start_j + ceil(n_j / 1024)). Parameters without a
+ * gradient (grad is None in the reference: outc_sem_change) get no job. step_count is the 1-based step number t
+ * used for the bias corrections 1 - beta^t.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  int64_t start;
+  int32_t vec4;      /* 1 when all four pointers are 16-byte aligned */
+  int32_t reserved;
+} b200cd_adamw_job;
+int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total_blocks, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, int64_t step_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200cd_colsum": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "b200cd_pj_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "b200cd_pj_loss": (_i, [_vp, _vp, _vp]),
+    "b200cd_adamw_step": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _vp]),
     "b200cd_pj_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp, _vp, _f, _i, _vp, _vp, _vp]),
 }
 

@@ -1,5 +1,6 @@
 // C-ABI layer (include/b200cd.h): argument validation, TMA tensor-map construction, error codes.
 // Everything exported is extern "C" with plain pointers and sizes; kernels live in the other .cu files.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -467,6 +468,23 @@ int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned
   if (!aligned16(z) || !aligned16(t) || !aligned16(dz) || !aligned16(dt)) return fail(B200CD_ERR_ALIGN, "pj_bwd: alignment");
   CUDA_TRY(b200cd::launch_pj_bwd(z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr, gmul, accumulate, dz, dt,
                                  reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total_blocks, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, int64_t step_count, void* stream) {
+  static_assert(sizeof(b200cd_adamw_job) == sizeof(b200cd::AdamWJob), "adamw job layout");
+  if (jobs_dev == nullptr || njobs < 1 || total_blocks < 1 || total_blocks > 0x7fffffffll || step_count < 1)
+    return fail(B200CD_ERR_SHAPE, "adamw_step: empty job table or step_count < 1");
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0))
+    return fail(B200CD_ERR_SHAPE, "adamw_step: betas must be in [0, 1) and eps >= 0");
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step_count));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step_count));
+  CUDA_TRY(b200cd::launch_adamw(reinterpret_cast<const b200cd::AdamWJob*>(jobs_dev), njobs, total_blocks,
+                                static_cast<float>(1.0 - lr * weight_decay), static_cast<float>(lr / bc1),
+                                static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+                                static_cast<float>(1.0 - beta2), static_cast<float>(eps), static_cast<float>(sqrt(bc2)),
+                                reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

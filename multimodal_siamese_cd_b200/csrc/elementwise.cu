@@ -1513,6 +1513,63 @@ __global__ void __launch_bounds__(256) pj_bwd_kernel(const float* __restrict__ z
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW as constructed at train_supervised.py:32: decoupled weight decay, no amsgrad), every
+// parameter tensor of the network in ONE launch. Job j owns thread blocks [start_j, start_{j+1}), 1024 elements per
+// block; parameters whose gradient is None (outc_sem_change) simply have no job.
+//   p <- p * (1 - lr * wd);  m <- m + (1 - b1)(g - m);  v <- b2 v + (1 - b2) g^2
+//   p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// The scalar factors are formed in double precision on the host, as torch forms them from Python floats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamWJob* __restrict__ jobs, int njobs, float decay,
+                                                    float step_size, float omb1, float b2, float omb2, float eps,
+                                                    float sqrt_bc2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long b = blockIdx.x;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].start <= b) lo = mid;
+    else hi = mid - 1;
+  }
+  const AdamWJob j = jobs[lo];
+  const long long i0 = (b - j.start) * 1024 + threadIdx.x * 4;
+  if (i0 + 3 < j.n && j.vec4) {
+    float4 pv = *reinterpret_cast<float4*>(j.p + i0);
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(j.g + i0));
+    float4 mv = *reinterpret_cast<float4*>(j.m + i0);
+    float4 vv = *reinterpret_cast<float4*>(j.v + i0);
+    float* pp = &pv.x;
+    const float* gg = &gv.x;
+    float* mm = &mv.x;
+    float* vq = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float g = gg[k];
+      const float pd = pp[k] * decay;
+      const float m = mm[k] + omb1 * (g - mm[k]);  // torch: exp_avg.lerp_(grad, 1 - beta1)
+      const float v = b2 * vq[k] + omb2 * g * g;
+      mm[k] = m;
+      vq[k] = v;
+      pp[k] = pd - step_size * (m / (sqrtf(v) / sqrt_bc2 + eps));
+    }
+    *reinterpret_cast<float4*>(j.p + i0) = pv;
+    *reinterpret_cast<float4*>(j.m + i0) = mv;
+    *reinterpret_cast<float4*>(j.v + i0) = vv;
+  } else {
+    for (long long i = i0; i < i0 + 4 && i < j.n; ++i) {
+      const float g = j.g[i];
+      const float pd = j.p[i] * decay;
+      const float m = j.m[i] + omb1 * (g - j.m[i]);
+      const float v = b2 * j.v[i] + omb2 * g * g;
+      j.m[i] = m;
+      j.v[i] = v;
+      j.p[i] = pd - step_size * (m / (sqrtf(v) / sqrt_bc2 + eps));
+    }
+  }
+}
+
 inline int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -1750,6 +1807,13 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
   const long long total = static_cast<long long>(rows) * per_row;
   launch_k(pj_bwd_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, st, z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr,
                                                           gmul, accumulate, dz, dt);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw(const AdamWJob* jobs, int njobs, long long total_blocks, float decay, float step_size, float omb1,
+                         float b2, float omb2, float eps, float sqrt_bc2, cudaStream_t st) {
+  launch_k(adamw_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, st, jobs, njobs, decay, step_size, omb1,
+           b2, omb2, eps, sqrt_bc2);
   return cudaGetLastError();
 }
 

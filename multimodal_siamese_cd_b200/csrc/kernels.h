@@ -133,4 +133,17 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
                           int rows, long long per_row, const double* sums, const float* gptr, float gmul,
                           int accumulate, float* dz, float* dt, cudaStream_t st);
 
+struct AdamWJob {       // layout == b200cd_adamw_job (include/b200cd.h)
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  long long start;      // first thread block (1024 elements per block)
+  int vec4;             // all four pointers 16-byte aligned
+  int reserved;
+};
+cudaError_t launch_adamw(const AdamWJob* jobs, int njobs, long long total_blocks, float decay, float step_size, float omb1,
+                         float b2, float omb2, float eps, float sqrt_bc2, cudaStream_t st);
+
 }  // namespace b200cd

@@ -44,3 +44,43 @@ def test_device_prefetcher_order_and_contents():
     assert pf.bytes_staged == sum(v.numel() * 4 for h in host for k, v in h.items() if k in ("x_t1", "x_t2", "y_change"))
     with pytest.raises(RuntimeError):
         DevicePrefetcher(iter(host), torch.device("cpu"))
+
+
+def test_fused_adamw_matches_torch():
+    """optim.FusedAdamW (one kernel over all parameters) against torch.optim.AdamW on the same parameters and
+    gradients for several steps, including a parameter without gradient and a state_dict round trip."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multimodal_siamese_cd_b200.optim import FusedAdamW
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    shapes = [(64, 6, 3, 3), (64,), (128, 64, 3, 3), (1, 128, 1, 1), (1,), (37,), (512, 512, 2, 2)]
+    ours = [torch.nn.Parameter(torch.randn(s, device=dev, generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    frozen_o, frozen_r = torch.nn.Parameter(torch.ones(3, device=dev)), torch.nn.Parameter(torch.ones(3, device=dev))
+    o1 = FusedAdamW(ours + [frozen_o], lr=1e-2, weight_decay=0.01)
+    o2 = torch.optim.AdamW(ref + [frozen_r], lr=1e-2, weight_decay=0.01)
+    for step in range(5):
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, device=dev, generator=g) * (0.1 + step)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        o1.step()
+        o2.step()
+        if step == 2:   # checkpoint round trip through torch's format (utils/networks.py:30-56)
+            sd = o1.state_dict()
+            o1 = FusedAdamW(ours + [frozen_o], lr=1e-2, weight_decay=0.01)
+            o1.load_state_dict(sd)
+    torch.cuda.synchronize()
+    assert torch.equal(frozen_o, frozen_r) and len(o1.state[frozen_o]) == 0
+    for a, b in zip(ours, ref):
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel < 2e-6, (tuple(a.shape), rel)
+        sa, sb = o1.state[a], o2.state[b]
+        assert float(sa["step"]) == float(sb["step"]) == 5.0
+        assert ((sa["exp_avg"] - sb["exp_avg"]).norm() / sb["exp_avg"].norm()).item() < 2e-6
+        assert ((sa["exp_avg_sq"] - sb["exp_avg_sq"]).norm() / sb["exp_avg_sq"].norm()).item() < 2e-6
+    cpu_p = torch.nn.Parameter(torch.ones(3))
+    cpu_p.grad = torch.ones(3)
+    with pytest.raises(Exception, match="CUDA parameters only"):
+        FusedAdamW([cpu_p], lr=1e-3).step()
