@@ -169,6 +169,8 @@ def synthetic_cfg(model_type: str, in_channels: int = 6, topology=(64, 128, 256,
     cfg.DATALOADER.S2_BANDS = list(s2_bands)
     cfg.CONSISTENCY_TRAINER.LOSS_FACTOR = 0.5
     cfg.CONSISTENCY_TRAINER.LOSS_TYPE = "PowerJaccardLoss"
+    cfg.TRAINER.LR = 1e-4            # configs/base.yaml:8 (read by load_checkpoint, utils/networks.py:47)
+    cfg.TRAINER.BATCH_SIZE = 8       # configs/base.yaml:9
     for k, v in extra.items():
         cfg[k] = v
     return cfg
