@@ -127,3 +127,41 @@ def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alph
     res["n_pixels"] = got_outs[0].numel()
     net.module.release_engines()
     return res
+
+
+def run_eval_case(mtype: str, cin: int, topo, B: int, H: int, W: int, warm_steps: int = 1) -> dict:
+    """Inference path of utils/evaluation.py:7-23: net.eval(), no_grad, sigmoid(logits) > 0.5, F1 — after `warm_steps`
+    training steps so that the BatchNorm running statistics are not the initial (0, 1)."""
+    dev = torch.device("cuda", 0)
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    xc = 6 if mtype in TWO_STREAM else cin
+    batch = O.synthetic_batch(B, xc, H, W, seed=7)
+    net.to(dev)
+    gb = {k: v.to(dev) for k, v in batch.items() if k != "is_labeled"}
+    sd = O.clone_state(sd0, requires_grad=False)
+    net.train()
+    for _ in range(warm_steps):                      # forward only: updates the running statistics on both sides
+        with torch.no_grad():
+            net(gb["x_t1"], gb["x_t2"])
+            O.forward(mtype, sd, batch["x_t1"], batch["x_t2"], train=True, q=True)
+    net.eval()
+    with torch.no_grad():
+        out = net(gb["x_t1"], gb["x_t2"])
+        out_again = net(gb["x_t1"], gb["x_t2"])      # second call replays the CUDA graph
+        ref_q = O.forward(mtype, sd, batch["x_t1"], batch["x_t2"], train=False, q=True)
+        ref_x = O.forward(mtype, sd, batch["x_t1"], batch["x_t2"], train=False, q=False)
+    torch.cuda.synchronize()
+    assert torch.is_tensor(out), "eval returns a single tensor for every network type but dtsiamese"
+    res = {"logits_q": rel(out, ref_q), "logits_x": rel(out, ref_x), "replay_equal": bool(torch.equal(out, out_again))}
+    gm, gf1 = O.change_mask_f1(out.cpu(), batch["y_change"])
+    pm, rf1 = O.change_mask_f1(ref_x, batch["y_change"])
+    res["margin_flips_x"] = int(((pm != gm) & (ref_x.abs() >= 0.05)).sum())
+    res["f1_diff_x"] = abs(gf1.item() - rf1.item())
+    sd_after = {k[len("module."):]: v.detach().cpu() for k, v in net.state_dict().items()}
+    res["bn_unchanged_in_eval"] = all(
+        torch.allclose(sd_after[k], v, atol=2e-3) for k, v in sd.items() if k.endswith(("running_mean", "running_var")))
+    net.module.release_engines()
+    return res

@@ -48,3 +48,21 @@ def test_step_parity(name):
     assert r["prebn_bias_grad_max"] == 0.0, r
     assert r["bn_running_maxabs"] <= 2e-3, r
     assert r["margin_flips_x"] == 0 and r["f1_diff_x"] <= 2e-2, r
+
+
+EVAL_CASES = {
+    "siamese_eval": dict(mtype="siameseunet", cin=4, topo=SMALL, B=2, H=64, W=48),
+    "dualstream_eval_full": dict(mtype="dualstreamunet", cin=6, topo=FULL, B=1, H=128, W=128),
+    "whatevernet_eval_fusion_only": dict(mtype="whatevernet", cin=6, topo=SMALL, B=2, H=32, W=32),
+}
+
+
+@pytest.mark.parametrize("name", list(EVAL_CASES))
+def test_eval_parity(name):
+    """Inference with running-statistics BatchNorm (utils/evaluation.py:7-23), batch 1 or 2, non-square tiles."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = E.run_eval_case(**EVAL_CASES[name])
+    assert r["logits_q"] <= 1.5e-2 and r["logits_x"] <= 3e-2, r
+    assert r["replay_equal"] and r["bn_unchanged_in_eval"], r
+    assert r["margin_flips_x"] == 0 and r["f1_diff_x"] <= 2e-2, r
