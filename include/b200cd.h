@@ -212,6 +212,25 @@ int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned
                   float* dt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * The split reduction of b200cd_wgrad_reduce for MANY layers in one launch (each layer has its own workspace region).
+ * `jobs_dev` is a DEVICE array; job j owns thread blocks [start_j, start_j + b200cd_reduce_job_blocks(splits, d0, d1,
+ * taps)); parts must be b200cd_reduce_job_parts(splits, d1, taps) (0 selects the row-transposing path used for few
+ * splits: coalesced gradient stores). Layout 0 only (ws[split][tap][d0][d1] -> grad[d0][d1][tap]); requires
+ * d1 % 4 == 0, split_stride % 4 == 0 and 16-byte aligned workspace and gradient pointers.
+ * Deterministic: fixed summation order.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* ws;
+  float* grad;
+  int64_t split_stride;
+  int64_t start;
+  int32_t splits, layout, d0, d1, taps, parts;
+} b200cd_reduce_job;
+int b200cd_reduce_job_parts(int splits, int d1, int taps);
+int64_t b200cd_reduce_job_blocks(int splits, int d0, int d1, int taps);
+int b200cd_wgrad_reduce_batched(const b200cd_reduce_job* jobs_dev, int njobs, int64_t total_blocks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * AdamW step over every parameter tensor in ONE launch — optim.AdamW(net.parameters(), lr=cfg.TRAINER.LR,
  * weight_decay=0.01) train_supervised.py:32 (decoupled weight decay, betas (0.9, 0.999), eps 1e-8, no amsgrad).
  * `jobs_dev` is a DEVICE array; job j owns thread blocks [start_j, start_j + ceil(n_j / 1024)). Parameters without a

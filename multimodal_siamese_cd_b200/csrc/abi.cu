@@ -471,6 +471,24 @@ int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned
   return 0;
 }
 
+int b200cd_reduce_job_parts(int splits, int d1, int taps) {
+  return (splits < 1 || d1 < 4 || taps < 1) ? -1 : b200cd::reduce_job_parts(splits, d1, taps);
+}
+
+int64_t b200cd_reduce_job_blocks(int splits, int d0, int d1, int taps) {
+  if (splits < 1 || d0 < 1 || d1 < 4 || d1 % 4 != 0 || taps < 1) return 0;
+  return b200cd::reduce_job_blocks(splits, d0, d1, taps);
+}
+
+int b200cd_wgrad_reduce_batched(const b200cd_reduce_job* jobs_dev, int njobs, int64_t total_blocks, void* stream) {
+  static_assert(sizeof(b200cd_reduce_job) == sizeof(b200cd::ReduceJob), "reduce job layout");
+  if (jobs_dev == nullptr || njobs < 1 || total_blocks < 1 || total_blocks > 0x7fffffffll)
+    return fail(B200CD_ERR_SHAPE, "wgrad_reduce_batched: empty job table");
+  CUDA_TRY(b200cd::launch_wgrad_reduce_batched(reinterpret_cast<const b200cd::ReduceJob*>(jobs_dev), njobs, total_blocks,
+                                               reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total_blocks, double lr, double beta1,
                       double beta2, double eps, double weight_decay, int64_t step_count, void* stream) {
   static_assert(sizeof(b200cd_adamw_job) == sizeof(b200cd::AdamWJob), "adamw job layout");

@@ -1387,6 +1387,153 @@ __global__ void __launch_bounds__(256) wgrad_reduce_v4_kernel(const float* __res
   }
 }
 
+// Batched split reduction: the per-layer kernels above run for ~15 us each, too short to reach the HBM roofline
+// (~2 TB/s measured), and there are 44 of them per step. Here every layer of a backward segment is one job of ONE
+// launch: job j owns thread blocks [start_j, start_{j+1}); a block is (256 / parts) lanes x parts, a lane owns four
+// consecutive workspace elements (16-byte loads), part p sums splits p, p + parts, ... in two chains and the parts are
+// summed in a fixed order in shared memory (deterministic). parts = min(8, largest power of two <= splits).
+constexpr int kRedIter = 4;  // element groups per lane: 2 * kRedIter independent 16-byte loads in flight per thread
+constexpr int kRedRowSplits = 16;  // jobs with fewer splits use the row-transposing path (coalesced gradient stores)
+
+// row path tiling: a block owns `rows` d0 rows x `bch` d1 columns x all taps; the [rows][bch][taps] tile fits the
+// kernel's 16 KB of shared memory. Whole rows when they fit (then several rows per block), else 256-column chunks.
+__host__ __device__ inline int reduce_bchunk(int d1, int taps) {
+  if (d1 * taps <= 4096) return d1;
+  return (d1 % 256 == 0 && 256 * taps <= 4096) ? 256 : 0;
+}
+__host__ __device__ inline int reduce_rows_per_block(int bch, int taps) {
+  const int r = 4096 / (bch * taps);
+  return r < 1 ? 1 : (r > 8 ? 8 : r);
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const ReduceJob* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 sh[kRedIter][256];
+  const long long b = blockIdx.x;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].start <= b) lo = mid;
+    else hi = mid - 1;
+  }
+  const ReduceJob j = jobs[lo];
+  if (j.parts == 0) {
+    // Few splits: the strided 4-byte gradient stores of the path below would dominate (a 32-byte sector per element).
+    // Here a block owns `rows` consecutive d0 rows with ALL taps: a thread sums one (row, tap, 4 x d1) unit over the
+    // splits (four loads in flight), the block transposes through shared memory and writes the rows' contiguous
+    // [d1][taps] gradient run with 16-byte stores.
+    float* tile = reinterpret_cast<float*>(&sh[0][0]);          // [rows][bch][taps], <= 4096 floats
+    const int bch = reduce_bchunk(j.d1, j.taps);                // d1 columns per block (whole rows when they fit)
+    const int rows = reduce_rows_per_block(bch, j.taps);
+    const int nchunks = j.d1 / bch;
+    const int lb = static_cast<int>(b - j.start);
+    const int a0 = (lb / nchunks) * rows;
+    const int b0 = (lb % nchunks) * bch;
+    const int q4 = bch >> 2;
+    const int units = rows * j.taps * q4;
+    const long long plane = static_cast<long long>(j.d0) * j.d1;
+    for (int u = threadIdx.x; u < units; u += 256) {
+      const int b4 = u % q4;
+      const int rt = u / q4;
+      const int tap = rt % j.taps, r = rt / j.taps;
+      if (a0 + r >= j.d0) continue;
+      const float* q = j.ws + tap * plane + static_cast<long long>(a0 + r) * j.d1 + b0 + b4 * 4;
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+      int sp = 0;
+      for (; sp + 3 < j.splits; sp += 4) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * j.split_stride));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 1) * j.split_stride));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 2) * j.split_stride));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 3) * j.split_stride));
+        s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+        s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+        s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+        s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
+      }
+      for (; sp < j.splits; ++sp) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * j.split_stride));
+        s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+      }
+      float* t = tile + (static_cast<long long>(r) * bch + b4 * 4) * j.taps + tap;
+      t[0] = (s0.x + s1.x) + (s2.x + s3.x);
+      t[j.taps] = (s0.y + s1.y) + (s2.y + s3.y);
+      t[2 * j.taps] = (s0.z + s1.z) + (s2.z + s3.z);
+      t[3 * j.taps] = (s0.w + s1.w) + (s2.w + s3.w);
+    }
+    __syncthreads();
+    const int nrows = min(rows, j.d0 - a0);                      // rows > 1 only when bch == d1: one contiguous run
+    const int n4 = (nrows * bch * j.taps) >> 2;
+    float4* dst = reinterpret_cast<float4*>(j.grad + (static_cast<long long>(a0) * j.d1 + b0) * j.taps);
+    const float4* src = reinterpret_cast<const float4*>(tile);
+    for (int k = threadIdx.x; k < n4; k += 256) dst[k] = src[k];
+    return;
+  }
+  const int parts = j.parts;
+  const int lanes = 256 / parts;
+  const int e = threadIdx.x % lanes, part = threadIdx.x / lanes;
+  const long long total = static_cast<long long>(j.d0) * j.d1 * j.taps;
+  const long long i0 = ((b - j.start) * kRedIter * lanes + e) * 4;  // group it: i0 + it * lanes * 4
+  float4 acc[kRedIter], c[kRedIter];
+#pragma unroll
+  for (int it = 0; it < kRedIter; ++it) acc[it] = c[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sp = part;
+  for (; sp + parts < j.splits; sp += 2 * parts) {
+    float4 v0[kRedIter], v1[kRedIter];
+#pragma unroll
+    for (int it = 0; it < kRedIter; ++it) {
+      const long long i = i0 + static_cast<long long>(it) * lanes * 4;
+      if (i < total) {
+        v0[it] = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp) * j.split_stride));
+        v1[it] = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp + parts) * j.split_stride));
+      } else {
+        v0[it] = v1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kRedIter; ++it) {
+      acc[it].x += v0[it].x; acc[it].y += v0[it].y; acc[it].z += v0[it].z; acc[it].w += v0[it].w;
+      c[it].x += v1[it].x; c[it].y += v1[it].y; c[it].z += v1[it].z; c[it].w += v1[it].w;
+    }
+  }
+  if (sp < j.splits) {
+#pragma unroll
+    for (int it = 0; it < kRedIter; ++it) {
+      const long long i = i0 + static_cast<long long>(it) * lanes * 4;
+      if (i < total) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp) * j.split_stride));
+        acc[it].x += v.x; acc[it].y += v.y; acc[it].z += v.z; acc[it].w += v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kRedIter; ++it) {
+    acc[it].x += c[it].x; acc[it].y += c[it].y; acc[it].z += c[it].z; acc[it].w += c[it].w;
+    sh[it][threadIdx.x] = acc[it];
+  }
+  __syncthreads();
+  if (part == 0) {
+#pragma unroll
+    for (int it = 0; it < kRedIter; ++it) {
+      const long long i = i0 + static_cast<long long>(it) * lanes * 4;
+      if (i >= total) continue;
+      float4 r = acc[it];
+      for (int k = 1; k < parts; ++k) {
+        const float4 v = sh[it][k * lanes + e];
+        r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+      }
+      const float rr[4] = {r.x, r.y, r.z, r.w};
+      // layout 0 only: ws[tap][d0][d1] -> grad[d0][d1][tap]
+      const int bb = static_cast<int>(i % j.d1);
+      const int a = static_cast<int>((i / j.d1) % j.d0);
+      const int tap = static_cast<int>(i / (static_cast<long long>(j.d1) * j.d0));
+      float* dst = j.grad + (static_cast<long long>(a) * j.d1 + bb) * j.taps + tap;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dst[static_cast<long long>(u) * j.taps] = rr[u];  // d1 % 4 == 0: same (a, tap)
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Power-Jaccard loss (utils/loss_functions.py:141-150): p = sigmoid(z); I = sum p*t;
 // D = sum p^2 + sum t^2 - I + 1e-6; L = 1 - I/D, over all selected batch rows at once.
@@ -1807,6 +1954,31 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
   const long long total = static_cast<long long>(rows) * per_row;
   launch_k(pj_bwd_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, st, z, t, t_is_logit, rowmask, sel, rows, per_row, sums, gptr,
                                                           gmul, accumulate, dz, dt);
+  return cudaGetLastError();
+}
+
+// parts == 0 selects the row path: few splits, d1 % 4 == 0 and a row (or a 256-column chunk of it) fits the tile
+int reduce_job_parts(int splits, int d1, int taps) {
+  if (splits < kRedRowSplits && d1 % 4 == 0 && reduce_bchunk(d1, taps) > 0) return 0;
+  int p = 1;
+  while (p < 8 && 2 * p <= splits) p *= 2;
+  return p;
+}
+
+long long reduce_job_blocks(int splits, int d0, int d1, int taps) {
+  const int parts = reduce_job_parts(splits, d1, taps);
+  if (parts == 0) {
+    const int bch = reduce_bchunk(d1, taps);
+    const int rows = reduce_rows_per_block(bch, taps);
+    return static_cast<long long>((d0 + rows - 1) / rows) * (d1 / bch);
+  }
+  const long long per_block = 4ll * kRedIter * (256 / parts);
+  const long long total = static_cast<long long>(d0) * d1 * taps;
+  return (total + per_block - 1) / per_block;
+}
+
+cudaError_t launch_wgrad_reduce_batched(const ReduceJob* jobs, int njobs, long long total_blocks, cudaStream_t st) {
+  launch_k(wgrad_reduce_batched_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, st, jobs, njobs);
   return cudaGetLastError();
 }
 

@@ -133,6 +133,17 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
                           int rows, long long per_row, const double* sums, const float* gptr, float gmul,
                           int accumulate, float* dz, float* dt, cudaStream_t st);
 
+struct ReduceJob {      // layout == b200cd_reduce_job (include/b200cd.h)
+  const float* ws;
+  float* grad;
+  long long split_stride;
+  long long start;      // first thread block of the job (reduce_job_blocks blocks)
+  int splits, layout, d0, d1, taps, parts;
+};
+int reduce_job_parts(int splits, int d1, int taps);   // 0 = row-transposing path
+long long reduce_job_blocks(int splits, int d0, int d1, int taps);
+cudaError_t launch_wgrad_reduce_batched(const ReduceJob* jobs, int njobs, long long total_blocks, cudaStream_t st);
+
 struct AdamWJob {       // layout == b200cd_adamw_job (include/b200cd.h)
   float* p;
   const float* g;

@@ -151,6 +151,8 @@ class StepEngine:
         self.x_t2 = torch.zeros(B, cin_total, H, W, device=device)
         self.grads: Optional[GradArena] = None
         self._ws_need = {"stats": 0, "stats2": 0, "wgrad": 0, "bnbwd": 0, "colsum": 0}
+        self._reduce_specs: list[tuple] = []   # (backward op index, ws offset, grad view, splits, stride, layout, d0, d1, taps)
+        self._reduce_tables: list[tuple] = []  # per flush: (device job table, njobs, blocks, bytes)
         self._build()
         self._alloc_ws()
         self._param_ptrs = self._ptr_signature()
@@ -400,6 +402,10 @@ class StepEngine:
         self.ws_stats2 = self._new(max(n["stats2"], 2), dtype=torch.float64)
         if self.train:
             self.ws_wgrad = self._new(max(n["wgrad"], 4), dtype=torch.float32)
+            for group in getattr(self, "_flush_groups", []):
+                jobs = [(self.ws_wgrad.narrow(0, off, splits * stride), gw, splits, stride, layout, d0, d1, taps)
+                        for (_, off, gw, splits, stride, layout, d0, d1, taps) in group]
+                self._reduce_tables.append(ops.make_reduce_jobs(jobs, self.device))
             self.ws_bnbwd = self._new(max(n["bnbwd"], 4), dtype=torch.float32)
             self.ws_colsum = self._new(max(n["colsum"], 4), dtype=torch.float32)
 
@@ -455,16 +461,22 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------------
     # backward emission: reverse order of the forward stages
     # ------------------------------------------------------------------------------------------------
+    def _ws_region(self, floats: int) -> int:
+        """Every layer owns a region of the split workspace: the per-split partial weight gradients of a whole
+        backward segment are summed by ONE batched launch (ops.wgrad_reduce_batched)."""
+        off = self._ws_need["wgrad"]
+        self._ws_need["wgrad"] = off + (floats + 3) // 4 * 4
+        return off
+
     def _wgrad_plan(self, st: Stage):
-        """Choose operand roles / split count for the 3x3 weight gradient and size the workspace."""
+        """Choose operand roles / split count for the 3x3 weight gradient and reserve its workspace region."""
         cin, cout = st.cin, st.cout
         total = ops.wgrad_tiles(st.n_img, st.H, st.W)
         if st.first:
             kp = st.in_view.shape[3]
             ctas = max(1, kp // 128)
             splits = max(1, min(total, WGRAD_CTA_TARGET // ctas))
-            self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * cout * kp)
-            return ("first", splits)
+            return ("first", splits, self._ws_region(splits * cout * kp))
         if cout >= 128 or cin < 128:
             role = "pos"   # M <-> cout (U = dr), N <-> cin
             ctas = ((cout + 127) // 128) * (cin // 128 if cin % 128 == 0 else cin // 64) * 3
@@ -472,25 +484,30 @@ class StepEngine:
             role = "neg"   # M <-> cin (U = input), N <-> cout
             ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
         splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
-        self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 9 * cout * cin)
-        return (role, splits)
+        return (role, splits, self._ws_region(splits * 9 * cout * cin))
 
     def _emit_stage_bwd(self, st: Stage) -> None:
         eng = self
         g = self.grads
         conv, bn = st.conv, st.bn
         gw, ggam, gbet = g.view_of(conv.weight), g.view_of(bn.weight), g.view_of(bn.bias)
-        role, splits = self._wgrad_plan(st)
+        role, splits, off = self._wgrad_plan(st)
         cin, cout = st.cin, st.cout
         srcs = st.srcs
         assert 1 <= len(srcs) <= 3, f"{st.name}: {len(srcs)} gradient sources"
+        op_index = len(eng.bwd_ops)
+        if role == "first":
+            kp = st.in_view.shape[3]
+            size = splits * cout * kp       # tiny (Cin <= 8): reduced by its own launch right away
+        else:
+            size = splits * 9 * cout * cin
+            eng._reduce_specs.append((op_index, off, gw, splits, 9 * cout * cin, 0, cout, cin, 9))
 
         def run():
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
                        st.dr)
-            ws = eng.ws_wgrad
+            ws = eng.ws_wgrad.narrow(0, off, size)
             if role == "first":
-                kp = st.in_view.shape[3]
                 ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
                 ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
             else:
@@ -498,7 +515,6 @@ class StepEngine:
                     ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1)
                 else:
                     ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin)
-                ops.wgrad_reduce(ws, splits, 9 * cout * cin, 0, cout, cin, 9, gw)
                 if st.d_in is not None:
                     ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
@@ -514,14 +530,15 @@ class StepEngine:
         total = ops.wgrad_tiles(nb, h, w)
         ctas = ((c + 127) // 128) * (c // 128 if c % 128 == 0 else c // 64)
         splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
-        self._ws_need["wgrad"] = max(self._ws_need["wgrad"], splits * 4 * c * c)
+        off = self._ws_region(splits * 4 * c * c)
+        size = splits * 4 * c * c
         npix = nb * 4 * h * w
         nblk = max(1, min(1184, npix // 64))
         self._ws_need["colsum"] = max(self._ws_need["colsum"], nblk * c)
+        eng._reduce_specs.append((len(eng.bwd_ops), off, gw, splits, 4 * c * c, 0, c, c, 4))
 
         def run():
-            ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad, splits, 4 * c * c, c * c, c, 1)
-            ops.wgrad_reduce(eng.ws_wgrad, splits, 4 * c * c, 0, c, c, 4, gw)
+            ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
             ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
             ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
 
@@ -560,6 +577,49 @@ class StepEngine:
             uc = up_by_first_stage.get(id(st))
             if uc is not None:
                 self._emit_up_bwd(uc)
+        self._plan_reduce_flushes()
+
+    def _plan_reduce_flushes(self, segments: int = 4) -> None:
+        """The split partials of consecutive layers are reduced together: a flush after the backward ops at which the
+        accumulated weight-gradient volume crosses k / segments of the total (and after the last op). Until a layer's
+        flush has run, its weight gradient is incomplete, so bwd_marks (the finished prefix of the flat gradient buffer
+        that a data-parallel caller may all-reduce) only advance at flush points."""
+        specs = self._reduce_specs
+        if not specs:
+            return
+        total = sum(sp[2].numel() for sp in specs)
+        flush_after, acc, k = [], 0, 1
+        for sp in specs:
+            acc += sp[2].numel()
+            if acc * segments >= k * total:
+                flush_after.append(sp[0])
+                while acc * segments >= k * total:
+                    k += 1
+        if flush_after[-1] != specs[-1][0]:
+            flush_after.append(specs[-1][0])
+        self._flush_groups = []
+        lo = 0
+        for fi, last_op in enumerate(flush_after):
+            group = [sp for sp in specs[lo:] if sp[0] <= last_op]
+            lo += len(group)
+            self._flush_groups.append(group)
+            orig = self.bwd_ops[last_op]
+
+            def run(orig=orig, fi=fi):
+                orig()
+                tab, nj, blocks, nbytes = self._reduce_tables[fi]
+                ops.wgrad_reduce_batched(tab, nj, blocks, nbytes)
+
+            self.bwd_ops[last_op] = run
+        # marks: heads are complete as produced; stage ops only complete the prefix up to the last flushed layer
+        first_stage_op = specs[0][0]
+        flushed = self.bwd_marks[first_stage_op - 1] if first_stage_op > 0 else 0
+        done = set(flush_after)
+        for i in range(first_stage_op, len(self.bwd_ops)):
+            if i in done:
+                flushed = self.bwd_marks[i]
+            self.bwd_marks[i] = flushed
+        self.bwd_marks[-1] = self.grads.flat.numel()   # the last flush is not after the last op: everything is complete
 
     # ------------------------------------------------------------------------------------------------
     # execution

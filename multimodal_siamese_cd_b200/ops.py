@@ -248,6 +248,45 @@ def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, 
                                                    grad.data_ptr(), _stream()))
 
 
+_REDUCE_JOB_DTYPE = None
+
+
+def make_reduce_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int, float]:
+    """specs: (ws fp32 view, grad fp32 tensor, splits, split_stride, layout, d0, d1, taps). Returns (device job table,
+    njobs, total thread blocks, algorithmic bytes) for wgrad_reduce_batched (b200cd_reduce_job: 56 bytes)."""
+    import numpy as np
+    global _REDUCE_JOB_DTYPE
+    if _REDUCE_JOB_DTYPE is None:
+        _REDUCE_JOB_DTYPE = np.dtype([("ws", "<u8"), ("grad", "<u8"), ("split_stride", "<i8"), ("start", "<i8"),
+                                      ("splits", "<i4"), ("layout", "<i4"), ("d0", "<i4"), ("d1", "<i4"), ("taps", "<i4"),
+                                      ("parts", "<i4")], align=True)
+        assert _REDUCE_JOB_DTYPE.itemsize == 56
+    lib = _lib.load()
+    arr = np.zeros(len(specs), dtype=_REDUCE_JOB_DTYPE)
+    blocks = 0
+    nbytes = 0.0
+    for i, (ws, grad, splits, split_stride, layout, d0, d1, taps) in enumerate(specs):
+        total = d0 * d1 * taps
+        assert ws.dtype == torch.float32 and grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == total
+        assert layout == 0 and d1 % 4 == 0 and split_stride % 4 == 0 and ws.data_ptr() % 16 == 0 and \
+            grad.data_ptr() % 16 == 0
+        nb = lib.b200cd_reduce_job_blocks(splits, d0, d1, taps)
+        assert nb > 0
+        arr[i] = (ws.data_ptr(), grad.data_ptr(), split_stride, blocks, splits, layout, d0, d1, taps,
+                  lib.b200cd_reduce_job_parts(splits, d1, taps))
+        blocks += nb
+        nbytes += 4.0 * (splits + 1) * total
+    table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    return table, len(specs), blocks, nbytes
+
+
+def wgrad_reduce_batched(table: torch.Tensor, njobs: int, blocks: int, nbytes: float = 0.0) -> None:
+    _require_cuda(table)
+    _count(1)
+    with _Prof("wgrad_reduce", 0.0, nbytes):
+        _lib.check(_lib.load().b200cd_wgrad_reduce_batched(table.data_ptr(), njobs, blocks, _stream()))
+
+
 def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group: int, G: int, count: float, spl: int,
              ws: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, running_mean: torch.Tensor,
              running_var: torch.Tensor, nbt: Optional[torch.Tensor], momentum: float, eps: float, train: bool,

@@ -1,4 +1,4 @@
-"""Generates tests/golden/ref_checkpoint_siamese_tiny.pt: a checkpoint WRITTEN BY THE UNMODIFIED REFERENCE
+"""Generates tests/golden/ckpt/ref_checkpoint_siamese_tiny.pt: a checkpoint WRITTEN BY THE UNMODIFIED REFERENCE
 (utils/networks.py:30-38 save_checkpoint, after one real AdamW step) for a deliberately narrow network
 (TOPOLOGY [8, 16], so the file stays ~100 KB). Run in the build container only (/root/reference is not on the GPU box).
 The drop-in `networks.load_checkpoint` must read this file as is (tests/test_checkpoint_cpu.py).
@@ -47,7 +47,7 @@ def main() -> None:
     opt.step()
     ref_networks.save_checkpoint(net, opt, 3, 17, cfg)                                 # epoch 3, global step 17
     src = tmp / "networks" / "tiny_checkpoint3.pt"
-    dst = ROOT / "tests" / "golden" / "ref_checkpoint_siamese_tiny.pt"
+    dst = ROOT / "tests" / "golden" / "ckpt" / "ref_checkpoint_siamese_tiny.pt"
     shutil.copy(src, dst)
     print(dst, dst.stat().st_size, "bytes; loss", float(loss))
 

@@ -1,5 +1,5 @@
 """N4: checkpoint files round-trip between the reference and the drop-in modules.
-tests/golden/ref_checkpoint_siamese_tiny.pt was written by the UNMODIFIED reference's save_checkpoint
+tests/golden/ckpt/ref_checkpoint_siamese_tiny.pt was written by the UNMODIFIED reference's save_checkpoint
 (utils/networks.py:30-38) after one AdamW step (oracle/make_checkpoint_golden.py). Pure CPU: the drop-in modules are
 ordinary nn.Modules until forward() is called."""
 from pathlib import Path
@@ -9,7 +9,7 @@ import torch
 from multimodal_siamese_cd_b200 import networks
 from multimodal_siamese_cd_b200.config import synthetic_cfg
 
-FIX = Path(__file__).parent / "golden" / "ref_checkpoint_siamese_tiny.pt"
+FIX = Path(__file__).parent / "golden" / "ckpt" / "ref_checkpoint_siamese_tiny.pt"
 
 
 def _cfg(tmp_path):

@@ -135,3 +135,26 @@ for name, fn in TESTS.items():
     if only is None or name in only:
         fn()
 ops.device_status()
+
+
+def run_reduce_batched(cout, cin, splits, reps=1):
+    specs = []
+    keep = []
+    for _ in range(reps):
+        ws = torch.randn(splits, 9, cout, cin, device=DEV)
+        grad = torch.empty(cout, cin, 3, 3, device=DEV)
+        keep.append((ws, grad))
+        specs.append((ws.view(-1), grad, splits, 9 * cout * cin, 0, cout, cin, 9))
+    tab, nj, blocks, nbytes = ops.make_reduce_jobs(specs, DEV)
+    us = timeit(lambda: ops.wgrad_reduce_batched(tab, nj, blocks, nbytes))
+    report(f"reduce_batched_{cout}x{cin}_s{splits}_x{reps}", us, nbytes)
+
+
+if only is not None and "reduce_batched" in only:
+    run_reduce_batched(64, 64, 49, 16)
+    run_reduce_batched(128, 128, 49, 8)
+    run_reduce_batched(256, 256, 12, 8)
+    run_reduce_batched(512, 512, 3, 8)
+    run_reduce_batched(512, 512, 8, 4)
+    run_reduce_batched(512, 512, 16, 2)
+    ops.device_status()
