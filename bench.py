@@ -38,6 +38,33 @@ CONFIGS = {
 H = W = 256
 
 
+def ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/): mean over the captured launches. None when no capture is committed."""
+    import csv
+    for name in ("r01_ncu_full_fprop_pair_kernel.csv",):
+        f = ROOT / "profiles" / name
+        if not f.exists():
+            continue
+        rows = list(csv.reader(open(f)))
+        hdr = rows[0]
+        try:
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[2:]:
+            if len(r) > max(ir, iw) and kernel_substr in r[ik]:
+                try:
+                    vals.append(float(r[ir]) * unit.get(rows[1][ir], 1.0) + float(r[iw]) * unit.get(rows[1][iw], 1.0))
+                except ValueError:
+                    pass
+        if vals:
+            return {"bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals), "source": f"profiles/{name}"}
+    return None
+
+
 def peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -356,7 +383,9 @@ def main() -> None:
     else:
         ach = d["bytes"] / d["ms"] / 1e6
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    roof.update({"kernel": dom, "traffic": None, "share_of_step": d["ms"] / total_ms, "peak_source": pk["src"] +
+    tr = ncu_traffic("fprop_pair_kernel") if dom == "fprop3x3" else None
+    roof.update({"kernel": dom, "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr,
+                 "share_of_step": d["ms"] / total_ms, "peak_source": pk["src"] +
                  (" bf16_tflops_sustained" if roof["bound"] == "tensor" else " hbm_gbs"),
                  "launches_per_step": d["calls"], "ms_per_step": d["ms"]})
     breakdown = {}

@@ -169,7 +169,10 @@ class StepEngine:
         return cfg.MODEL.IN_CHANNELS
 
     def _ptr_signature(self):
-        return tuple(p.data_ptr() for p in self.net.parameters()) + tuple(b.data_ptr() for b in self.net.buffers())
+        # the module tree is walked once; afterwards only the storage addresses are compared (this runs every forward)
+        if getattr(self, "_sig_tensors", None) is None:
+            self._sig_tensors = list(self.net.parameters()) + list(self.net.buffers())
+        return tuple(t.data_ptr() for t in self._sig_tensors)
 
     def params_moved(self) -> bool:
         return self._ptr_signature() != self._param_ptrs

@@ -1,0 +1,4 @@
+for c in "siamese 32" "dtsiamese 8" "dtsiamese_ssl 8" "mmcr 64" "siamese 8"; do set -- $c
+python bench.py --config $1 --batch $2 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_l_$1_$2.json 2> gpurun_out/bench_l.err; tail -c 300 gpurun_out/bench_l.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_l_$1_$2.json')); print('$1 B=$2', 'VALUE', round(d['value'],1), 'E2E', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],3), 'step_roofline', round(d['step_roofline']['frac_of_tensor_peak'],3), 'dom', d['roofline']['kernel'], round(d['roofline']['frac'],3), 'loss', d['loss'])"
+done
