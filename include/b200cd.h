@@ -126,10 +126,13 @@ int b200cd_conv_gemm_tiles(int H, int W);
  *   ws element (split, tap, m, n) at split*split_stride + tap*tap_stride + m*m_stride + n*n_stride.
  *   requires cv % 64 == 0, cu % 64 == 0; H, W arbitrary (out-of-image pixels read as zero).
  *   halo: 1 = load the shifted operand once per pixel tile with a one-row halo (mode 0 only).
+ *   splits2: 0, or (mode 0, halo, cv % 128 != 0) the number of CTAs per output block that own the kx = 2 taps: the
+ *           `splits` CTAs then own kx = 0 and 1 together (one U tile feeds two V boxes), so taps with tap % 3 == 2 have
+ *           splits2 partials and the others `splits` (b200cd_reduce_job.splits2). splits2 = splits / 2 balances the work.
  * ------------------------------------------------------------------------------------------------- */
 int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
-                      int cv, int n_img, int H, int W, float* ws, int splits, int64_t split_stride, int64_t tap_stride,
-                      int64_t m_stride, int64_t n_stride, void* stream);
+                      int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
+                      int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream);
 /* number of 8x8 pixel tiles (upper bound for `splits`) */
 int b200cd_wgrad_tiles(int n_img, int H, int W);
 
@@ -225,6 +228,8 @@ typedef struct {
   int64_t split_stride;
   int64_t start;
   int32_t splits, layout, d0, d1, taps, parts;
+  int32_t splits2;   /* > 0: taps with tap % 3 == 2 have splits2 partials (b200cd_wgrad_gemm splits2) */
+  int32_t reserved;
 } b200cd_reduce_job;
 int b200cd_reduce_job_parts(int splits, int d1, int taps);
 int64_t b200cd_reduce_job_blocks(int splits, int d0, int d1, int taps);

@@ -296,8 +296,8 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
 int b200cd_wgrad_tiles(int n_img, int H, int W) { return n_img * ((W + 7) / 8) * ((H + 7) / 8); }
 
 int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
-                      int cv, int n_img, int H, int W, float* ws, int splits, int64_t split_stride, int64_t tap_stride,
-                      int64_t m_stride, int64_t n_stride, void* stream) {
+                      int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
+                      int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {
   if (mode < 0 || mode > 2) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: bad mode");
   if (cu < 64 || cu % 64 != 0 || cv < 64 || cv % 64 != 0)
     return fail(B200CD_ERR_SHAPE, "wgrad_gemm: cu=%d, cv=%d must be multiples of 64", cu, cv);
@@ -307,6 +307,9 @@ int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld,
     return fail(B200CD_ERR_ALIGN, "wgrad_gemm: workspace strides must keep 16-byte alignment");
   const int total = b200cd_wgrad_tiles(n_img, H, W);
   if (splits < 1 || splits > total) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: splits=%d outside [1, %d]", splits, total);
+  if (splits2 != 0 && (mode != 0 || !halo || cv % 128 == 0 || splits2 < 1 || splits2 > total))
+    return fail(B200CD_ERR_SHAPE, "wgrad_gemm: splits2=%d needs mode 0, halo, 64-wide N tiles and 1 <= splits2 <= %d",
+                splits2, total);
   int* err = nullptr;
   if (int rc = current_err_flag(&err)) return rc;
   if (mode != 0) halo = 0;
@@ -321,6 +324,7 @@ int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld,
   p.tiles_y = (H + 7) / 8;
   p.total_tiles = total;
   p.splits = splits;
+  p.splits2 = splits2;
   p.cu = cu;
   p.cv = cv;
   p.ws = ws;

@@ -1439,9 +1439,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const ReduceJ
       const int tap = rt % j.taps, r = rt / j.taps;
       if (a0 + r >= j.d0) continue;
       const float* q = j.ws + tap * plane + static_cast<long long>(a0 + r) * j.d1 + b0 + b4 * 4;
+      const int nsp = (j.splits2 > 0 && tap % 3 == 2) ? j.splits2 : j.splits;
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
       int sp = 0;
-      for (; sp + 3 < j.splits; sp += 4) {
+      for (; sp + 3 < nsp; sp += 4) {
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * j.split_stride));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 1) * j.split_stride));
         const float4 v2 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp + 2) * j.split_stride));
@@ -1451,7 +1452,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const ReduceJ
         s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
         s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
       }
-      for (; sp < j.splits; ++sp) {
+      for (; sp < nsp; ++sp) {
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(sp) * j.split_stride));
         s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
       }
@@ -1477,18 +1478,24 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const ReduceJ
   float4 acc[kRedIter], c[kRedIter];
 #pragma unroll
   for (int it = 0; it < kRedIter; ++it) acc[it] = c[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long plane_p = static_cast<long long>(j.d0) * j.d1;
+  int nsp_it[kRedIter];  // splits of each group's tap (kx = 2 taps of a two-kx weight-gradient launch have fewer)
+#pragma unroll
+  for (int it = 0; it < kRedIter; ++it) {
+    const long long i = i0 + static_cast<long long>(it) * lanes * 4;
+    nsp_it[it] = (j.splits2 > 0 && i < total && (i / plane_p) % 3 == 2) ? j.splits2 : j.splits;
+  }
   int sp = part;
   for (; sp + parts < j.splits; sp += 2 * parts) {
     float4 v0[kRedIter], v1[kRedIter];
 #pragma unroll
     for (int it = 0; it < kRedIter; ++it) {
       const long long i = i0 + static_cast<long long>(it) * lanes * 4;
-      if (i < total) {
+      v0[it] = v1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total && sp < nsp_it[it])
         v0[it] = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp) * j.split_stride));
+      if (i < total && sp + parts < nsp_it[it])
         v1[it] = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp + parts) * j.split_stride));
-      } else {
-        v0[it] = v1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
     }
 #pragma unroll
     for (int it = 0; it < kRedIter; ++it) {
@@ -1500,7 +1507,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const ReduceJ
 #pragma unroll
     for (int it = 0; it < kRedIter; ++it) {
       const long long i = i0 + static_cast<long long>(it) * lanes * 4;
-      if (i < total) {
+      if (i < total && sp < nsp_it[it]) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(j.ws + i + static_cast<long long>(sp) * j.split_stride));
         acc[it].x += v.x; acc[it].y += v.y; acc[it].z += v.z; acc[it].w += v.w;
       }

@@ -25,12 +25,16 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kUBytes = 2 * 64 * 128;  // 64 pixels x 128 channels (two 64-channel slabs)
 
-template <int BN, int MODE, bool HALO>
+// NKX (3x3 mode with HALO only): kx columns per CTA. With 64-wide N tiles an MMA lasts 32 cycles and a (U, V box) pair
+// of 26 KB feeds only 12 of them — 68 B/clk against the ~40 B/clk the L2 -> SM fabric delivers. NKX = 2 lets one U tile
+// feed two V boxes (6 accumulators, 47 B/clk): CTAs z < splits own kx 0 and 1 over 1/splits of the pixel tiles, CTAs
+// z >= splits own kx 2 over 1/splits2 of them (splits2 = splits / 2 balances the work).
+template <int BN, int MODE, bool HALO, int NKX = 1>
 struct WgradCfg {
-  static constexpr int kTaps = MODE == 0 ? 3 : (MODE == 1 ? 1 : 4);
+  static constexpr int kTaps = MODE == 0 ? 3 * NKX : (MODE == 1 ? 1 : 4);
   static constexpr int kVRows = HALO ? 80 : 64;
   static constexpr int kVSlab = kVRows * 128;
-  static constexpr int kVTiles = HALO ? 1 : kTaps;  // separately loaded tap tiles
+  static constexpr int kVTiles = HALO ? NKX : kTaps;  // separately loaded tap tiles / boxes
   static constexpr int kVBytes = kVTiles * (BN / 64) * kVSlab;
   static constexpr int kStageBytes = kUBytes + kVBytes;
   static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
@@ -45,11 +49,12 @@ struct WgradCfg {
   static_assert(kCols <= 512, "accumulators exceed TMEM");
 };
 
-template <int BN, int MODE, bool HALO>
+template <int BN, int MODE, bool HALO, int NKX>
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ CUtensorMap mapU,
                                                          const __grid_constant__ CUtensorMap mapV,
                                                          const WgradParams p) {
-  using C = WgradCfg<BN, MODE, HALO>;
+  using C = WgradCfg<BN, MODE, HALO, NKX>;
+  static_assert(NKX == 1 || (MODE == 0 && HALO), "NKX > 1 needs the 3x3 halo variant");
   constexpr int STAGES = C::kStages;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -63,10 +68,21 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * BN;
-  const int split = blockIdx.z % p.splits;
-  const int kx = blockIdx.z / p.splits;  // mode 0 only (0..2)
-  const int t_begin = static_cast<int>(static_cast<long long>(p.total_tiles) * split / p.splits);
-  const int t_end = static_cast<int>(static_cast<long long>(p.total_tiles) * (split + 1) / p.splits);
+  int split, kx, nkx, nsplit;  // this CTA: kx columns [kx, kx + nkx) over pixel-tile range split / nsplit
+  if (NKX == 2) {
+    const bool first = static_cast<int>(blockIdx.z) < p.splits;
+    split = first ? blockIdx.z : blockIdx.z - p.splits;
+    nsplit = first ? p.splits : p.splits2;
+    kx = first ? 0 : 2;
+    nkx = first ? 2 : 1;
+  } else {
+    split = blockIdx.z % p.splits;
+    kx = blockIdx.z / p.splits;  // mode 0 only (0..2)
+    nkx = 1;
+    nsplit = p.splits;
+  }
+  const int t_begin = static_cast<int>(static_cast<long long>(p.total_tiles) * split / nsplit);
+  const int t_end = static_cast<int>(static_cast<long long>(p.total_tiles) * (split + 1) / nsplit);
   const int iters = t_end - t_begin;
 
   if (warp == 0 && lane == 0) {
@@ -102,17 +118,24 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       uint8_t* u_dst = smem + s * C::kStageBytes;
       uint8_t* v_dst = u_dst + kUBytes;
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+        mbar_arrive_expect_tx(&full[s], NKX == 1 ? C::kStageBytes : kUBytes + nkx * (BN / 64) * C::kVSlab);
 #pragma unroll
         for (int slab = 0; slab < 2; ++slab)
           tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
         if (MODE == 0) {
-          const int sx = p.sign * (kx - 1);
           if (HALO) {
 #pragma unroll
-            for (int slab = 0; slab < BN / 64; ++slab)
-              tma_load_5d(v_dst + slab * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx, y0 - 1, img, 0);
+            for (int b = 0; b < NKX; ++b) {
+              if (b < nkx) {
+                const int sx = p.sign * (kx + b - 1);
+#pragma unroll
+                for (int slab = 0; slab < BN / 64; ++slab)
+                  tma_load_5d(v_dst + (b * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx,
+                              y0 - 1, img, 0);
+              }
+            }
           } else {
+            const int sx = p.sign * (kx - 1);
 #pragma unroll
             for (int j = 0; j < 3; ++j)
 #pragma unroll
@@ -158,11 +181,41 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t u_lo = u_lo0 + s * (C::kStageBytes >> 4);
       const uint32_t v_lo = v_lo0 + s * (C::kStageBytes >> 4);
-      if (elect_one_sync()) {
+      if (BN == 64 && HALO && MODE == 0) {
+        // 64-wide N tiles: an N = 64 MMA costs as much tensor-pipe time as an N = 128 one (measured: ~70 cycles either
+        // way), so two taps are issued as ONE N = 128 MMA — the B descriptor's leading byte offset is the distance
+        // between the two taps' 64-channel blocks (next ky: 1024 bytes; last ky of a box -> first ky of the next box:
+        // box size - 2048). Accumulator columns are unchanged: tap j still owns columns [64 j, 64 j + 64).
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, 128, 1, 1);
+        const uint32_t v_base = (v_lo & 0xFFFFu);  // start-address field only (the LBO field is rebuilt per pair)
+        const int ntaps = 3 * nkx;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int j = 0; j + 1 < C::kTaps; j += 2) {
+            if (j + 1 >= ntaps) break;
+            const uint32_t off0 = (j / 3) * C::kVSlab + (j % 3) * 1024;
+            const uint32_t off1 = ((j + 1) / 3) * C::kVSlab + ((j + 1) % 3) * 1024;
+            const uint32_t vp = v_base + (off0 >> 4) + (((off1 - off0) >> 4) << 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lo(tmem_base + j * BN, u_lo + k * (2048 >> 4), vp + k * (2048 >> 4), desc_hi, idesc2, it > 0 || k > 0);
+          }
+          if (ntaps & 1) {
+            const int j = ntaps - 1;
+            const uint32_t vj = v_lo + (j / 3) * (C::kVSlab >> 4) + (j % 3) * (1024 >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lo(tmem_base + j * BN, u_lo + k * (2048 >> 4), vj + k * (2048 >> 4), desc_hi, idesc, it > 0 || k > 0);
+          }
+          umma_commit(&empty[s]);
+        }
+      } else if (elect_one_sync()) {
 #pragma unroll
         for (int j = 0; j < C::kTaps; ++j) {
-          // HALO: tap j = rows [8j, 8j+64) of the 80-row box (whole 1024-byte swizzle atoms)
-          const uint32_t vj = HALO ? v_lo + j * (1024 >> 4) : v_lo + j * (((BN / 64) * C::kVSlab) >> 4);
+          if (NKX == 2 && j >= 3 * nkx) break;
+          // HALO: tap j = box j / 3, rows [8 (j % 3), 8 (j % 3) + 64) of its 80-row box (whole 1024-byte swizzle atoms)
+          const uint32_t vj = HALO ? v_lo + (j / 3) * (((BN / 64) * C::kVSlab) >> 4) + (j % 3) * (1024 >> 4)
+                                   : v_lo + j * (((BN / 64) * C::kVSlab) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 16 pixels (K) per MMA = 16 rows of 128 bytes
             umma_bf16_lo(tmem_base + j * BN, u_lo + k * (2048 >> 4), vj + k * (2048 >> 4), desc_hi, idesc, it > 0 || k > 0);
@@ -186,8 +239,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     float* base = p.ws + static_cast<long long>(split) * p.split_stride;
 #pragma unroll 1
     for (int j = 0; j < C::kTaps; ++j) {
+      if (NKX == 2 && j >= 3 * nkx) break;
       int tap = j;
-      if (MODE == 0) tap = (p.sign > 0 ? j : 2 - j) * 3 + kx;
+      if (MODE == 0) tap = (p.sign > 0 ? j % 3 : 2 - j % 3) * 3 + kx + j / 3;
       float* tbase = base + tap * p.tap_stride + static_cast<long long>(m) * p.m_stride;
 #pragma unroll 1
       for (int c32 = 0; c32 < BN / 32; ++c32) {
@@ -218,18 +272,19 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   }
 }
 
-template <int BN, int MODE, bool HALO>
+template <int BN, int MODE, bool HALO, int NKX = 1>
 cudaError_t launch_one(const CUtensorMap& mapU, const CUtensorMap& mapV, const WgradParams& p, cudaStream_t stream) {
-  using C = WgradCfg<BN, MODE, HALO>;
+  using C = WgradCfg<BN, MODE, HALO, NKX>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, MODE, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, MODE, HALO, NKX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kDynamic);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((p.cu + 127) / 128, p.cv / BN, (MODE == 0 ? 3 : 1) * p.splits);
-  launch_k(wgrad_kernel<BN, MODE, HALO>, dim3(grid), dim3(kThreads), C::kDynamic, stream, mapU, mapV, p);
+  const int z = NKX == 2 ? p.splits + p.splits2 : (MODE == 0 ? 3 : 1) * p.splits;
+  dim3 grid((p.cu + 127) / 128, p.cv / BN, z);
+  launch_k(wgrad_kernel<BN, MODE, HALO, NKX>, dim3(grid), dim3(kThreads), C::kDynamic, stream, mapU, mapV, p);
   return cudaGetLastError();
 }
 
@@ -239,6 +294,7 @@ cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const
                          cudaStream_t stream) {
   if (p.mode == 0) {
     if (bn == 128) return halo ? launch_one<128, 0, true>(mapU, mapV, p, stream) : launch_one<128, 0, false>(mapU, mapV, p, stream);
+    if (bn == 64 && halo && p.splits2 > 0) return launch_one<64, 0, true, 2>(mapU, mapV, p, stream);
     if (bn == 64) return halo ? launch_one<64, 0, true>(mapU, mapV, p, stream) : launch_one<64, 0, false>(mapU, mapV, p, stream);
   } else if (p.mode == 1) {
     if (bn == 128) return launch_one<128, 1, false>(mapU, mapV, p, stream);

@@ -65,6 +65,7 @@ cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, 
 struct WgradParams {
   int mode, sign;
   int H, W, tiles_x, tiles_y, total_tiles, splits;
+  int splits2;  // > 0 (64-wide N tiles, mode 0, halo): CTAs own two kx columns; splits2 CTAs own the third (gemm_wgrad.cu)
   int cu, cv;
   float* ws;
   long long split_stride, tap_stride, m_stride, n_stride;
@@ -139,6 +140,7 @@ struct ReduceJob {      // layout == b200cd_reduce_job (include/b200cd.h)
   long long split_stride;
   long long start;      // first thread block of the job (reduce_job_blocks blocks)
   int splits, layout, d0, d1, taps, parts;
+  int splits2, reserved;  // > 0: taps with tap % 3 == 2 (kx = 2) have only splits2 partials
 };
 int reduce_job_parts(int splits, int d1, int taps);   // 0 = row-transposing path
 long long reduce_job_blocks(int splits, int d0, int d1, int taps);

@@ -27,6 +27,10 @@ BF16 = torch.bfloat16
 # weight-gradient kernels split the pixel dimension until about this many CTAs are in flight (the per-split partial
 # results are summed by wgrad_reduce in a fixed order); measured on B200 in profiles/
 WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
+# 64-wide weight-gradient tiles: one CTA may own two kx columns (gemm_wgrad.cu, NKX = 2). Measured slower than one kx
+# per CTA once tap pairs are issued as N = 128 MMAs (the kernel is bound by MN-major operand reads from shared memory,
+# not by the L2 -> SM stream): off by default, kept for the parity tests and for re-measurement.
+WGRAD_TWO_KX = __import__("os").environ.get("B200CD_WGRAD_TWO_KX", "0") != "0"
 
 
 def _kpad(cin: int) -> int:
@@ -406,8 +410,8 @@ class StepEngine:
         if self.train:
             self.ws_wgrad = self._new(max(n["wgrad"], 4), dtype=torch.float32)
             for group in getattr(self, "_flush_groups", []):
-                jobs = [(self.ws_wgrad.narrow(0, off, splits * stride), gw, splits, stride, layout, d0, d1, taps)
-                        for (_, off, gw, splits, stride, layout, d0, d1, taps) in group]
+                jobs = [(self.ws_wgrad.narrow(0, off, splits * stride), gw, splits, stride, layout, d0, d1, taps, s2)
+                        for (_, off, gw, splits, stride, layout, d0, d1, taps, s2) in group]
                 self._reduce_tables.append(ops.make_reduce_jobs(jobs, self.device))
             self.ws_bnbwd = self._new(max(n["bnbwd"], 4), dtype=torch.float32)
             self.ws_colsum = self._new(max(n["colsum"], 4), dtype=torch.float32)
@@ -479,22 +483,29 @@ class StepEngine:
             kp = st.in_view.shape[3]
             ctas = max(1, kp // 128)
             splits = max(1, min(total, WGRAD_CTA_TARGET // ctas))
-            return ("first", splits, self._ws_region(splits * cout * kp))
+            return ("first", splits, self._ws_region(splits * cout * kp), 0)
         if cout >= 128 or cin < 128:
             role = "pos"   # M <-> cout (U = dr), N <-> cin
             ctas = ((cout + 127) // 128) * (cin // 128 if cin % 128 == 0 else cin // 64) * 3
         else:
             role = "neg"   # M <-> cin (U = input), N <-> cout
             ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
+        nwide = cin if role == "pos" else cout      # width of the N side of the GEMM
+        if WGRAD_TWO_KX and nwide % 128 != 0:
+            # 64-wide N tiles: CTAs own two kx columns (splits of them) or the third one (splits2 = splits / 2)
+            per_xy = ctas // 3
+            splits2 = max(1, min(total, WGRAD_CTA_TARGET // (3 * per_xy)))
+            splits = min(total, 2 * splits2)
+            return (role, splits, self._ws_region(splits * 9 * cout * cin), splits2)
         splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
-        return (role, splits, self._ws_region(splits * 9 * cout * cin))
+        return (role, splits, self._ws_region(splits * 9 * cout * cin), 0)
 
     def _emit_stage_bwd(self, st: Stage) -> None:
         eng = self
         g = self.grads
         conv, bn = st.conv, st.bn
         gw, ggam, gbet = g.view_of(conv.weight), g.view_of(bn.weight), g.view_of(bn.bias)
-        role, splits, off = self._wgrad_plan(st)
+        role, splits, off, splits2 = self._wgrad_plan(st)
         cin, cout = st.cin, st.cout
         srcs = st.srcs
         assert 1 <= len(srcs) <= 3, f"{st.name}: {len(srcs)} gradient sources"
@@ -504,7 +515,7 @@ class StepEngine:
             size = splits * cout * kp       # tiny (Cin <= 8): reduced by its own launch right away
         else:
             size = splits * 9 * cout * cin
-            eng._reduce_specs.append((op_index, off, gw, splits, 9 * cout * cin, 0, cout, cin, 9))
+            eng._reduce_specs.append((op_index, off, gw, splits, 9 * cout * cin, 0, cout, cin, 9, splits2))
 
         def run():
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
@@ -515,9 +526,9 @@ class StepEngine:
                 ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
             else:
                 if role == "pos":
-                    ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1)
+                    ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1, splits2)
                 else:
-                    ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin)
+                    ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
                 if st.d_in is not None:
                     ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
@@ -538,7 +549,7 @@ class StepEngine:
         npix = nb * 4 * h * w
         nblk = max(1, min(1184, npix // 64))
         self._ws_need["colsum"] = max(self._ws_need["colsum"], nblk * c)
-        eng._reduce_specs.append((len(eng.bwd_ops), off, gw, splits, 4 * c * c, 0, c, c, 4))
+        eng._reduce_specs.append((len(eng.bwd_ops), off, gw, splits, 4 * c * c, 0, c, c, 4, 0))
 
         def run():
             ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)

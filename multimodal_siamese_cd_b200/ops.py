@@ -222,7 +222,7 @@ def wgrad_tiles(n: int, H: int, W: int) -> int:
 
 
 def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor, ws: torch.Tensor, splits: int,
-               split_stride: int, tap_stride: int, m_stride: int, n_stride: int) -> None:
+               split_stride: int, tap_stride: int, m_stride: int, n_stride: int, splits2: int = 0) -> None:
     """G2. U: NHWC view at the GEMM resolution; V: NHWC view (mode 2: at 2x)."""
     _require_cuda(U, V, ws)
     n, H, W, cu, u_ld = _nhwc(U)
@@ -232,10 +232,10 @@ def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor
     _count(1)
     taps = 9 if mode == 0 else (1 if mode == 1 else 4)
     with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) + 4.0 * splits * taps * cu * cv,
-               f"{n}x{H}x{W} m{cu} n{cv} mode{mode} sign{sign} splits{splits}"):
+               f"{n}x{H}x{W} m{cu} n{cv} mode{mode} sign{sign} splits{splits}+{splits2}"):
         _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
-                                                 ws.data_ptr(), splits, split_stride, tap_stride, m_stride, n_stride,
-                                                 _stream()))
+                                                 ws.data_ptr(), splits, splits2, split_stride, tap_stride, m_stride,
+                                                 n_stride, _stream()))
 
 
 def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, d0: int, d1: int, taps: int,
@@ -252,20 +252,22 @@ _REDUCE_JOB_DTYPE = None
 
 
 def make_reduce_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int, float]:
-    """specs: (ws fp32 view, grad fp32 tensor, splits, split_stride, layout, d0, d1, taps). Returns (device job table,
-    njobs, total thread blocks, algorithmic bytes) for wgrad_reduce_batched (b200cd_reduce_job: 56 bytes)."""
+    """specs: (ws fp32 view, grad fp32 tensor, splits, split_stride, layout, d0, d1, taps[, splits2]). Returns (device
+    job table, njobs, total thread blocks, algorithmic bytes) for wgrad_reduce_batched (b200cd_reduce_job: 64 bytes)."""
     import numpy as np
     global _REDUCE_JOB_DTYPE
     if _REDUCE_JOB_DTYPE is None:
         _REDUCE_JOB_DTYPE = np.dtype([("ws", "<u8"), ("grad", "<u8"), ("split_stride", "<i8"), ("start", "<i8"),
                                       ("splits", "<i4"), ("layout", "<i4"), ("d0", "<i4"), ("d1", "<i4"), ("taps", "<i4"),
-                                      ("parts", "<i4")], align=True)
-        assert _REDUCE_JOB_DTYPE.itemsize == 56
+                                      ("parts", "<i4"), ("splits2", "<i4"), ("reserved", "<i4")], align=True)
+        assert _REDUCE_JOB_DTYPE.itemsize == 64
     lib = _lib.load()
     arr = np.zeros(len(specs), dtype=_REDUCE_JOB_DTYPE)
     blocks = 0
     nbytes = 0.0
-    for i, (ws, grad, splits, split_stride, layout, d0, d1, taps) in enumerate(specs):
+    for i, spec in enumerate(specs):
+        ws, grad, splits, split_stride, layout, d0, d1, taps = spec[:8]
+        splits2 = spec[8] if len(spec) > 8 else 0
         total = d0 * d1 * taps
         assert ws.dtype == torch.float32 and grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == total
         assert layout == 0 and d1 % 4 == 0 and split_stride % 4 == 0 and ws.data_ptr() % 16 == 0 and \
@@ -273,9 +275,9 @@ def make_reduce_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int,
         nb = lib.b200cd_reduce_job_blocks(splits, d0, d1, taps)
         assert nb > 0
         arr[i] = (ws.data_ptr(), grad.data_ptr(), split_stride, blocks, splits, layout, d0, d1, taps,
-                  lib.b200cd_reduce_job_parts(splits, d1, taps))
+                  lib.b200cd_reduce_job_parts(splits, d1, taps), splits2, 0)
         blocks += nb
-        nbytes += 4.0 * (splits + 1) * total
+        nbytes += 4.0 * (splits + 1) * total - (4.0 * (splits - splits2) * total / 3 if splits2 else 0.0)
     table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
     return table, len(specs), blocks, nbytes
 

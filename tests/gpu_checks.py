@@ -223,8 +223,11 @@ def _splits_for(total: int, want: int) -> int:
     return max(1, min(total, want))
 
 
-def check_wgrad3x3(n=2, H=32, W=32, cin=64, cout=128, sign=1, halo=0, splits=5, seed=7, tol=2e-3) -> dict:
-    """wgrad_gemm mode 0 + wgrad_reduce vs autograd's weight gradient (fp32 accumulation on both sides)."""
+def check_wgrad3x3(n=2, H=32, W=32, cin=64, cout=128, sign=1, halo=0, splits=5, seed=7, tol=2e-3, splits2=0,
+                   batched=False) -> dict:
+    """wgrad_gemm mode 0 + wgrad_reduce vs autograd's weight gradient (fp32 accumulation on both sides).
+    splits2 > 0: CTAs own two kx columns (64-wide N tiles); the kx = 2 taps then have splits2 partials and the
+    workspace slots beyond them stay NaN — the batched reduction must not touch them."""
     g = _gen(seed)
     x = bf16r(torch.randn(n, cin, H, W, device=DEV, generator=g))
     dr = bf16r(torch.randn(n, cout, H, W, device=DEV, generator=g))
@@ -233,15 +236,25 @@ def check_wgrad3x3(n=2, H=32, W=32, cin=64, cout=128, sign=1, halo=0, splits=5, 
     splits = _splits_for(ops.wgrad_tiles(n, H, W), splits)
     ws = torch.full((splits, 9, cout, cin), float("nan"), device=DEV)
     if sign == 1:   # M <-> cout (U = dOut), N <-> cin (V = input, shifted)
-        ops.wgrad_gemm(0, 1, halo, da, xa, ws, splits, 9 * cout * cin, cout * cin, cin, 1)
+        ops.wgrad_gemm(0, 1, halo, da, xa, ws, splits, 9 * cout * cin, cout * cin, cin, 1, splits2)
     else:           # M <-> cin (U = input), N <-> cout (V = dOut, shifted the other way)
-        ops.wgrad_gemm(0, -1, halo, xa, da, ws, splits, 9 * cout * cin, cout * cin, 1, cin)
+        ops.wgrad_gemm(0, -1, halo, xa, da, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
     grad = torch.empty(cout, cin, 3, 3, device=DEV)
-    ops.wgrad_reduce(ws, splits, 9 * cout * cin, 0, cout, cin, 9, grad)
+    if batched or splits2:
+        other = torch.empty(64, 64, 3, 3, device=DEV)   # a second job in the same launch
+        ws2 = torch.randn(3, 9, 64, 64, device=DEV, generator=g)
+        tab, nj, blocks, nbytes = ops.make_reduce_jobs(
+            [(ws2.view(-1), other, 3, 9 * 64 * 64, 0, 64, 64, 9), (ws.view(-1), grad, splits, 9 * cout * cin, 0, cout, cin, 9, splits2)], DEV)
+        ops.wgrad_reduce_batched(tab, nj, blocks, nbytes)
+    else:
+        ops.wgrad_reduce(ws, splits, 9 * cout * cin, 0, cout, cin, 9, grad)
     ops.device_status()
     ref = torch.nn.grad.conv2d_weight(x, (cout, cin, 3, 3), dr, padding=1)
     res = err(grad, ref)
     res["ok"] = res["finite"] and res["rel_l2"] < tol
+    if batched or splits2:
+        res["other_job"] = err(other, ws2.sum(0).permute(1, 2, 0).reshape(64, 64, 3, 3))
+        res["ok"] = res["ok"] and res["other_job"]["rel_l2"] < 1e-6
     return res
 
 
@@ -661,6 +674,12 @@ ALL_CHECKS = {
     "wgrad3x3_neg_halo": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=1, seed=71),
     "wgrad3x3_64_64_halo": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, seed=72),
     "wgrad3x3_64_64_many_splits": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, splits=27, seed=76),
+    "wgrad3x3_64_64_two_kx": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, splits=10, splits2=5, seed=77),
+    "wgrad3x3_64_128_two_kx": lambda: check_wgrad3x3(2, 32, 32, 64, 128, sign=1, halo=1, splits=24, splits2=12, seed=78),
+    "wgrad3x3_256_64_two_kx_neg": lambda: check_wgrad3x3(2, 32, 32, 256, 64, sign=-1, halo=1, splits=6, splits2=3, seed=79),
+    "wgrad3x3_two_kx_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 64, sign=1, halo=1, splits=7, splits2=2, seed=80),
+    "wgrad3x3_batched_reduce_many": lambda: check_wgrad3x3(2, 32, 32, 128, 128, sign=1, halo=1, splits=27, seed=81, batched=True),
+    "wgrad3x3_batched_reduce_few_512": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=3, seed=82, batched=True),
     "wgrad3x3_512_512_halo": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=8, seed=73),
     "wgrad3x3_tiny_4x4": lambda: check_wgrad3x3(3, 4, 4, 512, 512, sign=1, halo=1, splits=2, seed=74),
     "wgrad3x3_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 128, sign=1, halo=1, splits=7, seed=75),
