@@ -268,7 +268,13 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   const int width = N;
   int bn = (width % 128 == 0) ? 128 : 64;
   if ((flags & 2) && width % 256 == 0 && !halo) bn = 256;
-  if (pair && width % 256 == 0) bn = 256;
+  if (pair && width % 256 == 0) {
+    // 256-wide tiles unless they leave most of the 74 CTA pairs idle (deep 16x16 / 32x32 layers at small batch):
+    // then 128-wide tiles double the number of work items
+    const int tiles = n_img * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+    const int items256 = ((tiles + 1) / 2) * (width / 256);
+    bn = items256 >= 48 ? 256 : 128;
+  }
 
   CUtensorMap mapA, mapB, mapO;
   int rc;
