@@ -114,6 +114,11 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
                      void* stream);
 /* tiles_per_image for (H, W): stats has n_img * tiles_per_image rows. */
 int b200cd_conv_gemm_tiles(int H, int W);
+/* flags bit 3 (with bit 2, the CTA-pair kernel) switches the statistics to per-CTA running sums: bits 8..15 of flags hold
+ * the number G (1 or 2) of BatchNorm stat-groups (image n belongs to group n / (n_img / G)), stats is then
+ * fp32 [G][rows][N][2] with rows = b200cd_conv_gemm_stat_rows(...) (one row per CTA and epilogue group, at most 296
+ * instead of one per 128-pixel tile). Without bit 3 the function returns the per-tile row count n_img * tiles. */
+int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int H, int W, int ka, int N);
 
 /* ---------------------------------------------------------------------------------------------------
  * G2 — tcgen05 weight-gradient GEMM, ws[split][tap][m][n] = sum_{pixels in split} U[pixel, m] * V_tap[pixel, n]

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200cd_pack_weights_batched": (_i, [_vp, _i, _i64, _vp]),
     "b200cd_conv_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "b200cd_conv_gemm_tiles": (_i, [_i, _i]),
+    "b200cd_conv_gemm_stat_rows": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "b200cd_wgrad_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "b200cd_wgrad_tiles": (_i, [_i, _i, _i]),
     "b200cd_wgrad_reduce": (_i, [_vp, _i, _i64, _i, _i, _i, _i, _vp, _vp]),

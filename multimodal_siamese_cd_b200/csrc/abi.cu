@@ -224,6 +224,44 @@ int b200cd_conv_gemm_tiles(int H, int W) {
   return ((W + tw - 1) / tw) * ((H + th - 1) / th);
 }
 
+// Tile / kernel selection shared by b200cd_conv_gemm and b200cd_conv_gemm_stat_rows.
+struct ConvPlan {
+  int tw, th, pair, halo, bn, num_tiles, stat_groups;
+};
+static ConvPlan plan_conv(int mode, int out_mode, int flags, int n_img, int H, int W, int N) {
+  ConvPlan c;
+  tile_shape(W, H, mode == 2 || out_mode == 1, &c.tw, &c.th);
+  c.pair = (mode == 0 && out_mode == 0 && (flags & 4)) ? 1 : 0;
+  c.halo = (mode == 0 && ((flags & 1) || c.pair)) ? 1 : 0;
+  c.num_tiles = n_img * ((W + c.tw - 1) / c.tw) * ((H + c.th - 1) / c.th);
+  // N tile: 64 when the width is not a multiple of 128; 256 on request (flags bit 1) when it divides the width —
+  // a 128 x 256 tile reads 96 B/clk of operands from shared memory per MMA instead of 128 B/clk (the SM's limit).
+  // out_mode 1: every 64-channel slab of the tile belongs to one (dy, dx) tap (cout % 64 == 0), so the tile may span taps
+  c.bn = (N % 128 == 0) ? 128 : 64;
+  if ((flags & 2) && N % 256 == 0 && !c.halo) c.bn = 256;
+  if (c.pair && N % 256 == 0) {
+    // 256-wide tiles unless they leave most of the 74 CTA pairs idle (deep 16x16 / 32x32 layers at small batch):
+    // then 128-wide tiles double the number of work items
+    const int items256 = ((c.num_tiles + 1) / 2) * (N / 256);
+    c.bn = items256 >= 48 ? 256 : 128;
+  }
+  c.stat_groups = (c.pair && (flags & 8)) ? ((flags >> 8) & 0xff) : 0;
+  return c;
+}
+
+int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int H, int W, int ka, int N) {
+  if (mode < 0 || mode > 2 || n_img <= 0 || H <= 0 || W <= 0 || N < 64 || N % 64 != 0 || ka < 64 || ka % 64 != 0) return -1;
+  const ConvPlan c = plan_conv(mode, out_mode, flags, n_img, H, W, N);
+  if (c.stat_groups == 0) return c.num_tiles;  // per-tile rows (all groups together)
+  if (c.stat_groups > 2 || n_img % c.stat_groups != 0) return -1;
+  b200cd::FpropParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.kchunks = ka / 64;
+  const int ctas = b200cd::fprop_pair_ctas(p, c.bn, c.num_tiles);
+  return ctas < 0 ? -1 : 2 * ctas;            // rows per stat-group: one per (CTA, epilogue group)
+}
+
 int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
                      const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
                      void* stream) {
@@ -238,10 +276,10 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   int* err = nullptr;
   if (int rc = current_err_flag(&err)) return rc;
 
-  int tw, th;
-  tile_shape(W, H, mode == 2 || out_mode == 1, &tw, &th);
-  const int pair = (mode == 0 && out_mode == 0 && (flags & 4)) ? 1 : 0;
-  const int halo = (mode == 0 && ((flags & 1) || pair)) ? 1 : 0;
+  const ConvPlan cp = plan_conv(mode, out_mode, flags, n_img, H, W, N);
+  const int tw = cp.tw, th = cp.th, pair = cp.pair, halo = cp.halo, bn = cp.bn;
+  if (cp.stat_groups > 2 || (cp.stat_groups > 0 && n_img % cp.stat_groups != 0))
+    return fail(B200CD_ERR_SHAPE, "conv_gemm: stat groups must be 1 or 2 and divide n_img");
   b200cd::FpropParams p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
@@ -262,18 +300,13 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   p.stats = reinterpret_cast<float2*>(stats);
   p.ragged = (H % th != 0 || W % tw != 0) ? 1 : 0;
   p.err = err;
-  // N tile: 64 when the width is not a multiple of 128; 256 on request (flags bit 1) when it divides the width —
-  // a 128 x 256 tile reads 96 B/clk of operands from shared memory per MMA instead of 128 B/clk (the SM's limit).
-  // out_mode 1: every 64-channel slab of the tile belongs to one (dy, dx) tap (cout % 64 == 0), so the tile may span taps
-  const int width = N;
-  int bn = (width % 128 == 0) ? 128 : 64;
-  if ((flags & 2) && width % 256 == 0 && !halo) bn = 256;
-  if (pair && width % 256 == 0) {
-    // 256-wide tiles unless they leave most of the 74 CTA pairs idle (deep 16x16 / 32x32 layers at small batch):
-    // then 128-wide tiles double the number of work items
-    const int tiles = n_img * ((W + tw - 1) / tw) * ((H + th - 1) / th);
-    const int items256 = ((tiles + 1) / 2) * (width / 256);
-    bn = items256 >= 48 ? 256 : 128;
+  p.n_img = n_img;
+  p.stat_groups = cp.stat_groups;
+  const int num_tiles = cp.num_tiles;
+  if (cp.stat_groups > 0 && stats != nullptr) {
+    const int ctas = b200cd::fprop_pair_ctas(p, bn, num_tiles);
+    if (ctas < 0) return fail(B200CD_ERR_CUDA, "conv_gemm: occupancy query for the CTA-pair kernel failed");
+    p.stat_rows = 2 * ctas;
   }
 
   CUtensorMap mapA, mapB, mapO;
@@ -291,7 +324,6 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout, W, H, n_img, tw, th);
   else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);
   if (rc) return rc;
-  const int num_tiles = n_img * p.tiles_x * p.tiles_y;
   if (pair)
     CUDA_TRY(b200cd::launch_fprop_pair(mapA, mapB, mapO, p, bn, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
   else
@@ -369,6 +401,12 @@ int b200cd_bn_stats(const float* partial, int ld, int C, int tiles_per_group, in
   if (train) {
     if (spl < 1 || tiles_per_group < 1 || partial == nullptr || ws == nullptr)
       return fail(B200CD_ERR_SHAPE, "bn_stats: training mode needs partial statistics and a workspace");
+    if (tiles_per_group <= 1024) {  // few partial rows (per-CTA statistics): one kernel does reduce + finalize
+      CUDA_TRY(b200cd::launch_bn_stats_fused(reinterpret_cast<const float2*>(partial), ld, tiles_per_group, C, G, count,
+                                             gamma, beta, running_mean, running_var, reinterpret_cast<long long*>(nbt),
+                                             momentum, eps, order_rev, mean, invstd, scale, shift, st));
+      return 0;
+    }
     if (spl > tiles_per_group) spl = tiles_per_group;
     CUDA_TRY(b200cd::launch_bn_stats_reduce(reinterpret_cast<const float2*>(partial), ld, C, tiles_per_group, G, spl,
                                             ws, st));

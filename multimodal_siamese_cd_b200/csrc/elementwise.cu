@@ -345,6 +345,68 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   }
 }
 
+// Few partial rows per stat-group (the CTA-pair convolution writes one row per CTA and epilogue group, <= 296): one
+// kernel does both stages. block = 8 channels x 32 lanes; lane l sums rows l, l + 32, ... in fp64 (independent loads),
+// a fixed-order shuffle tree combines the lanes, lane 0 finishes the channel exactly as bn_finalize_kernel does.
+__global__ void __launch_bounds__(256) bn_stats_fused_kernel(const float2* __restrict__ partial, int ld, int rows, int C,
+                                                             int G, double count, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             float* __restrict__ running_mean,
+                                                             float* __restrict__ running_var, long long* __restrict__ nbt,
+                                                             float momentum, float eps, int order_rev,
+                                                             float* __restrict__ mean, float* __restrict__ invstd,
+                                                             float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;  // whole warp
+  float rm = running_mean[c], rv = running_var[c];
+  for (int gi = 0; gi < G; ++gi) {
+    const int g = order_rev ? G - 1 - gi : gi;
+    const float2* base = partial + static_cast<long long>(g) * rows * ld + c;
+    double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0;
+    int r = lane;
+    for (; r + 32 < rows; r += 64) {
+      const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
+      const float2 v1 = __ldg(base + static_cast<long long>(r + 32) * ld);
+      s += v0.x; q += v0.y;
+      s1 += v1.x; q1 += v1.y;
+    }
+    if (r < rows) {
+      const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
+      s += v0.x; q += v0.y;
+    }
+    s += s1;
+    q += q1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    const double mu = s / count;
+    double var = q / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float is = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float muf = static_cast<float>(mu);
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm = (1.f - momentum) * rm + momentum * muf;
+    rv = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
+    if (lane == 0) {
+      mean[g * C + c] = muf;
+      invstd[g * C + c] = is;
+      const float sc = gamma[c] * is;
+      scale[g * C + c] = sc;
+      shift[g * C + c] = beta[c] - muf * sc;
+    }
+  }
+  if (lane == 0) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
+    if (c == 0 && nbt != nullptr) *nbt += G;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BN-apply + ReLU, fused with MaxPool2d(2), the t2 - t1 feature difference and a second copy into a
 // concat slice. One thread = one 2x2 pixel window x 8 channels (x both timestamps when diff).
@@ -1772,6 +1834,15 @@ cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int til
                                    double* partial2, cudaStream_t st) {
   dim3 grid((C + 31) / 32, G, spl);
   launch_k(bn_stats_reduce_kernel, dim3(grid), dim3(256), 0, st, partial, ld, C, tiles_per_group, spl, partial2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_stats_fused(const float2* partial, int ld, int rows, int C, int G, double count, const float* gamma,
+                                  const float* beta, float* running_mean, float* running_var, long long* nbt,
+                                  float momentum, float eps, int order_rev, float* mean, float* invstd, float* scale,
+                                  float* shift, cudaStream_t st) {
+  launch_k(bn_stats_fused_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, ld, rows, C, G, count, gamma, beta,
+           running_mean, running_var, nbt, momentum, eps, order_rev, mean, invstd, scale, shift);
   return cudaGetLastError();
 }
 

@@ -276,6 +276,36 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
     red += grp * 4 * 64 * 2;
     uint32_t n_item = grp, n_slab = 0;
     int bias_nb = -1;
+    // per-CTA BatchNorm statistics (p.stat_groups > 0): thread t < 64 keeps the running (sum, sum of squares) of
+    // channel t of every slab of the current N block, per stat-group, and writes them once per N block
+    const bool cta_stats = p.stats != nullptr && p.stat_groups > 0;
+    const int per_group = cta_stats ? p.n_img / p.stat_groups : 1;
+    const size_t my_row = 2 * blockIdx.x + grp;
+    float acc_s[2][BN / 64], acc_q[2][BN / 64];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int sl = 0; sl < BN / 64; ++sl) acc_s[g][sl] = acc_q[g][sl] = 0.f;
+    int acc_nb = -1;
+    auto flush_stats = [&](int nb_done) {
+      if (t < 64) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g >= p.stat_groups) break;
+#pragma unroll
+          for (int sl = 0; sl < BN / 64; ++sl) {
+            p.stats[(static_cast<size_t>(g) * p.stat_rows + my_row) * p.N + nb_done * BN + sl * 64 + t] =
+                make_float2(acc_s[g][sl], acc_q[g][sl]);
+            acc_s[g][sl] = acc_q[g][sl] = 0.f;
+          }
+        }
+      }
+    };
+    if (cta_stats) {  // rows of N blocks / groups this producer never meets stay zero
+      for (int g = 0; g < p.stat_groups; ++g)
+        for (int n = t; n < p.N; n += 128)
+          p.stats[(static_cast<size_t>(g) * p.stat_rows + my_row) * p.N + n] = make_float2(0.f, 0.f);
+    }
     for (int item = cluster_id + grp * num_clusters; item < num_items; item += 2 * num_clusters, n_item += 2) {
       const int nb = item / num_pairs;
       const int tile = 2 * (item - nb * num_pairs) + static_cast<int>(rank);
@@ -285,6 +315,11 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const int x0 = tx * p.tw, y0 = ty * p.th;
       const int n0 = nb * BN;
       const bool real = tile < num_tiles;
+      if (cta_stats && nb != acc_nb) {
+        if (acc_nb >= 0) flush_stats(acc_nb);
+        acc_nb = nb;
+      }
+      const int sgrp = cta_stats ? img / per_group : 0;
       if (nb != bias_nb) {  // uniform across the 128 threads
         named_barrier_sync(bar1, 128);
         for (int i = t; i < BN; i += 128) bias_s[i] = p.bias ? p.bias[n0 + i] : 0.f;
@@ -294,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const uint32_t buf = grp;
       mbar_wait(&acc_full[buf], (n_item >> 1) & 1, p.err, DEV_ERR_ACC_TIMEOUT);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int slab = 0; slab < BN / 64; ++slab, ++n_slab) {
         uint8_t* sbuf = stg + (n_slab % L::kStg) * kStageSlab;
         // the TMA store that last used this staging buffer has finished reading it
@@ -367,12 +402,20 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
               s += red[((r4 * 64) + t) * 2];
               qq += red[((r4 * 64) + t) * 2 + 1];
             }
-            p.stats[static_cast<size_t>(tile) * p.N + n0 + slab * 64 + t] = make_float2(s, qq);
+            if (cta_stats) {
+              acc_s[0][slab] += sgrp == 0 ? s : 0.f;
+              acc_q[0][slab] += sgrp == 0 ? qq : 0.f;
+              acc_s[1][slab] += sgrp == 1 ? s : 0.f;
+              acc_q[1][slab] += sgrp == 1 ? qq : 0.f;
+            } else {
+              p.stats[static_cast<size_t>(tile) * p.N + n0 + slab * 64 + t] = make_float2(s, qq);
+            }
           }
           // `red` is rewritten only after the next slab's first named barrier, which every reader passes first
         }
       }
     }
+    if (cta_stats && acc_nb >= 0) flush_stats(acc_nb);
     if (t == 0) tma_store_wait_read0();
   }
 
@@ -387,8 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
 }
 
 template <int BN, bool RESIDENT>
-cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const FpropParams& p,
-                        int num_tiles, cudaStream_t stream) {
+cudaError_t pair_max_clusters(int* out) {
   using L = PairCfg<BN>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
@@ -414,8 +456,28 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
     if (n < 1) return cudaErrorLaunchOutOfResources;
     max_clusters = n < sms / 2 ? n : sms / 2;
   }
+  *out = max_clusters;
+  return cudaSuccess;
+}
+
+template <int BN, bool RESIDENT>
+cudaError_t pair_clusters(const FpropParams& p, int num_tiles, int* clusters) {
+  int max_clusters = 0;
+  cudaError_t e = pair_max_clusters<BN, RESIDENT>(&max_clusters);
+  if (e != cudaSuccess) return e;
   const int num_items = ((num_tiles + 1) / 2) * (p.N / BN);
-  const int clusters = num_items < max_clusters ? num_items : max_clusters;
+  *clusters = num_items < max_clusters ? num_items : max_clusters;
+  return cudaSuccess;
+}
+
+template <int BN, bool RESIDENT>
+cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const FpropParams& p,
+                        int num_tiles, cudaStream_t stream) {
+  using L = PairCfg<BN>;
+  int clusters = 0;
+  cudaError_t e = pair_clusters<BN, RESIDENT>(p, num_tiles, &clusters);
+  if (e != cudaSuccess) return e;
+  if (p.stats != nullptr && p.stat_groups > 0 && p.stat_rows != 4 * clusters) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kThreads);
@@ -433,15 +495,20 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT>, mapA, mapB, mapO, p, num_tiles);
 }
 
+static bool pair_resident(const FpropParams& p, int bn) {
+  // weights resident in shared memory when one N block covers the layer and all 9 * kchunks half-tiles fit the B ring
+  const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
+                            : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
+  return p.N == bn && 9 * p.kchunks <= cap;
+}
+
 }  // namespace
 
 cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
   if (p.mode != 0 || p.out_mode != 0) return cudaErrorInvalidValue;
-  // weights resident in shared memory when one N block covers the layer and all 9 * kchunks half-tiles fit the B ring
-  const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
-                            : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
-  const bool res = p.N == bn && 9 * p.kchunks <= cap;
+  if (p.stat_groups < 0 || p.stat_groups > 2) return cudaErrorInvalidValue;
+  const bool res = pair_resident(p, bn);
   if (bn == 256) return res ? launch_pair<256, true>(mapA, mapB, mapO, p, num_tiles, stream)
                             : launch_pair<256, false>(mapA, mapB, mapO, p, num_tiles, stream);
   if (bn == 128) return res ? launch_pair<128, true>(mapA, mapB, mapO, p, num_tiles, stream)
@@ -449,6 +516,16 @@ cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, 
   if (bn == 64) return res ? launch_pair<64, true>(mapA, mapB, mapO, p, num_tiles, stream)
                            : launch_pair<64, false>(mapA, mapB, mapO, p, num_tiles, stream);
   return cudaErrorInvalidValue;
+}
+
+int fprop_pair_ctas(const FpropParams& p, int bn, int num_tiles) {
+  const bool res = pair_resident(p, bn);
+  int c = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (bn == 256) e = res ? pair_clusters<256, true>(p, num_tiles, &c) : pair_clusters<256, false>(p, num_tiles, &c);
+  else if (bn == 128) e = res ? pair_clusters<128, true>(p, num_tiles, &c) : pair_clusters<128, false>(p, num_tiles, &c);
+  else if (bn == 64) e = res ? pair_clusters<64, true>(p, num_tiles, &c) : pair_clusters<64, false>(p, num_tiles, &c);
+  return e == cudaSuccess ? 2 * c : -1;
 }
 
 }  // namespace b200cd

@@ -46,8 +46,13 @@ struct FpropParams {
   const float* bias;      // nullable
   float2* stats;          // nullable: per (tile, n) partial (sum, sum of squares) of the bf16-rounded output
   int ragged;             // 1 when H % th or W % tw != 0 (mask rows in the statistics)
+  // CTA-pair kernel only: stat_groups > 0 switches the statistics to per-CTA running sums, stats[g][row][n] with
+  // stat_rows rows per BatchNorm stat-group g = image / (n_img / stat_groups) (row = 2 * blockIdx.x + epilogue group)
+  int stat_groups, stat_rows, n_img;
   int* err;
 };
+// CTAs the CTA-pair kernel launches for this problem (needs the current device: occupancy query on first use)
+int fprop_pair_ctas(const FpropParams& p, int bn, int num_tiles);
 cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                          const FpropParams& p, int bn, int halo, int num_tiles, cudaStream_t stream);
 
@@ -103,6 +108,10 @@ cudaError_t launch_pack_weights_batched(const PackJob* jobs, int njobs, long lon
 cudaError_t launch_pack_weights(int mode, const float* w, void* out, int d0, int d1, int kpad, cudaStream_t st);
 cudaError_t launch_bn_stats_reduce(const float2* partial, int ld, int C, int tiles_per_group, int G, int spl,
                                    double* partial2, cudaStream_t st);
+cudaError_t launch_bn_stats_fused(const float2* partial, int ld, int rows, int C, int G, double count, const float* gamma,
+                                  const float* beta, float* running_mean, float* running_var, long long* nbt,
+                                  float momentum, float eps, int order_rev, float* mean, float* invstd, float* scale,
+                                  float* shift, cudaStream_t st);
 cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, double count, const float* gamma,
                                const float* beta, float* running_mean, float* running_var, long long* nbt,
                                float momentum, float eps, int train, int order_rev, float* mean, float* invstd,

@@ -62,6 +62,8 @@ class Stage:
     invstd: torch.Tensor = None
     scale: torch.Tensor = None
     shift: torch.Tensor = None
+    stat_rows: int = 0
+    stat_per_cta: bool = False
 
     @property
     def cin(self) -> int:
@@ -206,7 +208,11 @@ class StepEngine:
         if self.train:
             st.dr = self._new(n_img, H, W, C)
         tiles = ops.conv_gemm_tiles(H, W)
-        self._ws_need["stats"] = max(self._ws_need["stats"], n_img * tiles * C * 2)
+        # statistics rows per stat-group: one per 128-pixel tile, or (CTA-pair kernel) one per CTA and epilogue group
+        st.stat_rows, st.stat_per_cta = (n_img // G) * tiles, False
+        if not first and self.device.type == "cuda":
+            st.stat_rows, st.stat_per_cta = ops.conv_stat_rows(n_img, H, W, conv.in_channels, C, G)
+        self._ws_need["stats"] = max(self._ws_need["stats"], G * st.stat_rows * C * 2)
         self._ws_need["stats2"] = max(self._ws_need["stats2"], 32 * G * C * 2)
         if self.train:
             self._ws_need["bnbwd"] = max(self._ws_need["bnbwd"], ops.bn_bwd_ws_floats(n_img, H, W, C, G))
@@ -433,13 +439,14 @@ class StepEngine:
         mode = 1 if st.first else 0
         train = eng.train
         count = (st.n_img // st.G) * st.H * st.W
-        tpg = (st.n_img // st.G) * tiles
+        tpg = st.stat_rows
         spl = max(1, min(32, tpg // 64))
+        sg = st.G if st.stat_per_cta else 0
         outs = st.outs
 
         def run():
             stats = eng.ws_stats if train else None
-            ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats)
+            ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats, stat_groups=sg)
             ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2, bn.weight, bn.bias, bn.running_mean,
                          bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
                          st.order_rev, st.mean, st.invstd, st.scale, st.shift)

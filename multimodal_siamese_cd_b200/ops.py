@@ -181,9 +181,38 @@ FPROP_WIDE_TILES = True     # 128 x 256 output tiles where N % 256 == 0 and the 
 FPROP_PAIR = True           # 3x3 convs on CTA pairs (cta_group::2, persistent, gemm_fprop2.cu)
 
 
+def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, stat_groups: int) -> int:
+    """Tile policy (measured on B200, profiles/): 3x3 convs on CTA pairs; otherwise 128x256 tiles where N % 256 == 0,
+    the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)."""
+    if pair is None:
+        pair = FPROP_PAIR and mode == 0 and out_mode == 0 and halo is None and wide is None
+    pair = bool(pair) and mode == 0 and out_mode == 0
+    if wide is None:
+        wide = FPROP_WIDE_TILES and N % 256 == 0 and halo is not True
+    if halo is None:
+        pol = FPROP_HALO_POLICY
+        halo = mode == 0 and not wide and (pol == "all" or (pol in ("n64", "auto") and N % 128 != 0) or
+                                           (pol == "auto" and ka >= 512))
+    if pair:
+        return 4 | ((8 | (stat_groups << 8)) if stat_groups > 0 else 0)
+    return (1 if (halo and mode == 0) else 0) | (2 if wide else 0)
+
+
+def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int, mode: int = 0) -> tuple[int, bool]:
+    """(rows per stat-group of the statistics buffer a 3x3 conv of this shape writes, per-CTA layout?). With the
+    CTA-pair kernel the rows are per CTA and epilogue group (<= 296); otherwise one row per 128-pixel tile."""
+    flags = _conv_flags(mode, 0, N, ka, None, None, None, stat_groups)
+    rows = _lib.load().b200cd_conv_gemm_stat_rows(mode, 0, flags, n_img, H, W, ka, N)
+    if rows < 0:
+        raise _lib.B200CDError("conv_gemm_stat_rows: unsupported shape")
+    per_cta = bool(flags & 8)
+    return (rows if per_cta else rows // stat_groups), per_cta
+
+
 def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              halo: Optional[bool] = None, wide: Optional[bool] = None, pair: Optional[bool] = None) -> None:
+              halo: Optional[bool] = None, wide: Optional[bool] = None, pair: Optional[bool] = None,
+              stat_groups: int = 0) -> None:
     """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x)."""
     _require_cuda(A, Bw, out)
     n, Ha, Wa, ka, a_ld = _nhwc(A)
@@ -198,18 +227,7 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
     else:
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
-    # tile policy (measured on B200, profiles/r01_probe_kernels_call7.json): 128x256 tiles where N % 256 == 0;
-    # otherwise the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)
-    if pair is None:
-        pair = FPROP_PAIR and mode == 0 and out_mode == 0 and halo is None and wide is None
-    pair = bool(pair) and mode == 0 and out_mode == 0
-    if wide is None:
-        wide = FPROP_WIDE_TILES and N % 256 == 0 and halo is not True
-    if halo is None:
-        pol = FPROP_HALO_POLICY
-        halo = mode == 0 and not wide and (pol == "all" or (pol in ("n64", "auto") and N % 128 != 0) or
-                                           (pol == "auto" and ka >= 512))
-    flags = 4 if pair else ((1 if (halo and mode == 0) else 0) | (2 if wide else 0))
+    flags = _conv_flags(mode, out_mode, N, ka, halo, wide, pair, stat_groups if stats is not None else 0)
     _count(1)
     fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
     with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode} halo{flags}"):

@@ -172,6 +172,52 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
     return res
 
 
+def check_conv3x3_cta_stats(n=4, H=32, W=32, cin=64, cout=128, G=2, seed=48) -> dict:
+    """CTA-pair conv with per-CTA running BatchNorm statistics (flags bit 3): stats[g][row][n] summed over the rows must
+    equal the per-group sums of the stored output, and the fused statistics kernel must reproduce BatchNorm's batch
+    statistics and running-stat update per group."""
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, cin, H, W, device=DEV, generator=g))
+    w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cin ** 0.5))
+    b = torch.randn(cout, device=DEV, generator=g)
+    A = nhwc(x).to(torch.bfloat16)
+    out = torch.empty(n, H, W, cout, device=DEV, dtype=torch.bfloat16)
+    rows, per_cta = ops.conv_stat_rows(n, H, W, cin, cout, G)
+    stats = torch.full((G, rows, cout, 2), float("nan"), device=DEV)   # the kernel must define every row it owns
+    Bw = ops.pack_weights(0, w)
+    ops.conv_gemm(0, 0, A, Bw, out, bias=b, stats=stats, stat_groups=G)
+    ops.device_status()
+    res = {"per_cta": per_cta, "rows": rows, "finite": bool(torch.isfinite(stats).all().item())}
+    o32 = out.float().view(G, n // G, H, W, cout)
+    ref_sum = o32.sum((1, 2, 3))
+    ref_sq = (o32 * o32).sum((1, 2, 3))
+    res["sum_rel"] = ((stats[..., 0].sum(1) - ref_sum).norm() / ref_sum.norm()).item()
+    res["sq_rel"] = ((stats[..., 1].sum(1) - ref_sq).norm() / ref_sq.norm()).item()
+    gamma = torch.rand(cout, device=DEV, generator=g) + 0.5
+    beta = torch.randn(cout, device=DEV, generator=g) * 0.2
+    mean = torch.empty(G, cout, device=DEV)
+    invstd, scale, shift = torch.empty_like(mean), torch.empty_like(mean), torch.empty_like(mean)
+    rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    nbt = torch.zeros((), device=DEV, dtype=torch.int64)
+    ws = torch.empty(4, G, cout, 2, device=DEV, dtype=torch.float64)
+    ops.bn_stats(stats, cout, cout, rows, G, (n // G) * H * W, 4, ws, gamma, beta, rm, rv, nbt, 0.1, 1e-5, True, False,
+                 mean, invstd, scale, shift)
+    torch.cuda.synchronize()
+    bn = torch.nn.BatchNorm2d(cout).to(DEV).train()
+    xs = nchw(out.float())
+    for gi in range(G):
+        bn(xs[gi * (n // G):(gi + 1) * (n // G)])
+        mu = xs[gi * (n // G):(gi + 1) * (n // G)].mean((0, 2, 3))
+        res[f"mean_g{gi}"] = (mean[gi] - mu).abs().max().item()
+    res["running_mean"] = (rm - bn.running_mean).abs().max().item()
+    res["running_var"] = (rv - bn.running_var).abs().max().item()
+    res["nbt"] = int(nbt.item())
+    res["ok"] = (res["per_cta"] and res["finite"] and res["sum_rel"] < 1e-5 and res["sq_rel"] < 1e-5 and
+                 res["running_mean"] < 1e-5 and res["running_var"] < 1e-4 and res["nbt"] == G and
+                 all(res[f"mean_g{gi}"] < 1e-5 for gi in range(G)))
+    return res
+
+
 def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> dict:
     g = _gen(seed)
     w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cout ** 0.5))
@@ -656,6 +702,10 @@ ALL_CHECKS = {
     "conv3x3_pair_ragged_4x4": lambda: check_conv3x3(3, 4, 4, 512, 512, seed=36, pair=True),
     "conv3x3_pair_ragged_24x40": lambda: check_conv3x3(2, 24, 40, 64, 64, seed=37, pair=True, compare_single=True),
     "conv3x3_pair_1024_256": lambda: check_conv3x3(4, 32, 32, 1024, 256, seed=47, pair=True),
+    "conv3x3_cta_stats_G2": check_conv3x3_cta_stats,
+    "conv3x3_cta_stats_G1_many": lambda: check_conv3x3_cta_stats(16, 64, 64, 64, 64, G=1, seed=49),
+    "conv3x3_cta_stats_G2_512": lambda: check_conv3x3_cta_stats(4, 16, 16, 256, 512, G=2, seed=50),
+    "conv3x3_cta_stats_odd_tiles": lambda: check_conv3x3_cta_stats(6, 8, 8, 128, 64, G=2, seed=51),
     "conv3x3_dgrad": check_conv3x3_dgrad,
     "conv3x3_dgrad_ragged_8x8": lambda: check_conv3x3_dgrad(3, 8, 8, 128, 128, seed=42),
     "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),
