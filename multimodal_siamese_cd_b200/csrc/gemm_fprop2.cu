@@ -29,12 +29,14 @@ constexpr int kThreads = 320;  // producer warp, MMA warp, two epilogue warpgrou
 constexpr int kABox = 160 * 128;  // tw x (th + 2) <= 160 pixels x 64 bf16 (16 x 10 or 8 x 18 boxes)
 constexpr int kStageSlab = 128 * 128;  // one 64-channel slab of the output tile
 
-template <int BN>
+// NKY = filter rows served by one A box: 3 for the 3x3 convolution (halo box), 1 for the single-tap GEMMs (first-layer
+// conv on im2col rows, transposed-conv forward with the 2x2 scatter epilogue).
+template <int BN, int NKY = 3>
 struct PairCfg {
   static constexpr int kBTile = (BN / 2) * 128;  // this CTA's half of a weight tile: BN/2 rows x 64 bf16
   // weight tiles per B-ring slot (= per barrier): with 64-wide tiles an MMA lasts 32 cycles, so the three ky tiles of a
   // step travel together and the issuer handles one barrier per 12 MMAs
-  static constexpr int kG = BN == 64 ? 3 : 1;
+  static constexpr int kG = (BN == 64 && NKY == 3) ? 3 : 1;
   static constexpr int kBSlot = kG * kBTile;
   static constexpr int kStg = BN == 64 ? 1 : 2;                   // staging slabs per epilogue group
   static constexpr int kSA = BN == 64 ? 5 : 3;
@@ -55,12 +57,12 @@ struct PairCfg {
   static_assert(kTotal + 16 <= 232448, "shared memory budget");
 };
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int NKY>
 __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ CUtensorMap mapO,
                                                                  const FpropParams p, const int num_tiles) {
-  using L = PairCfg<BN>;
+  using L = PairCfg<BN, NKY>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t align_pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   const int num_pairs = (num_tiles + 1) >> 1;
   const int n_blocks = p.N / BN;
   const int num_items = num_pairs * n_blocks;  // item = n_block * num_pairs + pair (pairs fastest: all pairs share B)
-  const int steps = 3 * p.kchunks;             // A boxes per item
+  const int steps = NKY * p.kchunks;           // A boxes per item (3x3: one per kx and 64-channel chunk)
   constexpr bool resident = RESIDENT;  // host: n_blocks == 1 and all 3 * steps weight tiles fit in the B ring
 
   if (warp == 0 && lane == 0) {
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
-          tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
+          if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
+          else tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
         }
         __syncwarp();
         if (++sa == L::kSA) {
@@ -162,11 +165,12 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
             }
           } else {
 #pragma unroll 1
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < NKY; ++ky) {
               if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
               if (elect_one_sync()) {
                 if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
-                tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb], (ky * 3 + kx) * p.ka + kc * 64, nrow);
+                tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb],
+                                 (NKY == 3 ? (ky * 3 + kx) * p.ka : 0) + kc * 64, nrow);
               }
               __syncwarp();
               if (++sb == L::kSB) {  // resident: the layer's tiles fill at most kSB slots, once, in order
@@ -211,15 +215,14 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
             if (L::kG == 3) {
               if (!resident || n_item == 0) mbar_wait(&b_full[sb], resident ? 0u : pb, p.err, DEV_ERR_FULL_TIMEOUT);
             } else if (n_item == 0) {
-              mbar_wait(&b_full[sb], 0, p.err, DEV_ERR_FULL_TIMEOUT);
-              mbar_wait(&b_full[sb + 1], 0, p.err, DEV_ERR_FULL_TIMEOUT);
-              mbar_wait(&b_full[sb + 2], 0, p.err, DEV_ERR_FULL_TIMEOUT);
+#pragma unroll
+              for (int ky = 0; ky < NKY; ++ky) mbar_wait(&b_full[sb + ky], 0, p.err, DEV_ERR_FULL_TIMEOUT);
             }
             tc_fence_after();
             const uint32_t b_lo = b_lo0 + sb * (L::kBSlot >> 4);
             if (elect_one_sync()) {
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky)
+              for (int ky = 0; ky < NKY; ++ky)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // +32 bytes along K inside the swizzled 128-byte row: +2 in the >>4 field
                   umma_bf16_2cta_lo(tmem_d, a_lo + ky * ky_step + 2 * k, b_lo + ky * (L::kBTile >> 4) + 2 * k, desc_hi,
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
               umma_commit_2cta(&a_empty[sa], 3);
             }
             __syncwarp();
-            sb += L::kG == 3 ? 1 : 3;
+            sb += L::kG == 3 ? 1 : NKY;
             if (!resident && sb == L::kSB) {
               sb = 0;
               pb ^= 1;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           } else {
             tc_fence_after();
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < NKY; ++ky) {
               mbar_wait(&b_full[sb], pb, p.err, DEV_ERR_FULL_TIMEOUT);
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + sb * (L::kBSlot >> 4);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
                   umma_bf16_2cta_lo(tmem_d, a_lo + ky * ky_step + 2 * k, b_lo + 2 * k, desc_hi, idesc,
                                     st > 0 || ky > 0 || k > 0);
                 umma_commit_2cta(&b_empty[sb], 3);
-                if (ky == 2) umma_commit_2cta(&a_empty[sa], 3);
+                if (ky == NKY - 1) umma_commit_2cta(&a_empty[sa], 3);
               }
               __syncwarp();
               if (++sb == L::kSB) {
@@ -322,7 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const int sgrp = cta_stats ? img / per_group : 0;
       if (nb != bias_nb) {  // uniform across the 128 threads
         named_barrier_sync(bar1, 128);
-        for (int i = t; i < BN; i += 128) bias_s[i] = p.bias ? p.bias[n0 + i] : 0.f;
+        for (int i = t; i < BN; i += 128)
+          bias_s[i] = p.bias ? p.bias[p.out_mode == 1 ? (n0 + i) % p.cout : n0 + i] : 0.f;
         named_barrier_sync(bar1, 128);
         bias_nb = nb;
       }
@@ -367,7 +371,13 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         fence_proxy_async_smem();
         named_barrier_sync(bar1, 128);
         if (t == 0) {
-          tma_store_5d(&mapO, sbuf, n0 + slab * 64, x0, y0, img, 0);  // clipped at the tensor bounds
+          if (p.out_mode == 0) {
+            tma_store_5d(&mapO, sbuf, n0 + slab * 64, x0, y0, img, 0);  // clipped at the tensor bounds
+          } else {  // 2x2 / stride-2 scatter of the transposed convolution: slab = 64 channels of one (dy, dx) tap
+            const int n = n0 + slab * 64;
+            const int tap = n / p.cout, co = n - tap * p.cout;
+            tma_store_5d(&mapO, sbuf, co, tap & 1, x0, tap >> 1, img * p.H + y0);
+          }
           tma_store_commit();
         }
         if (p.stats != nullptr) {
@@ -429,12 +439,12 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   }
 }
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int NKY>
 cudaError_t pair_max_clusters(int* out) {
-  using L = PairCfg<BN>;
+  using L = PairCfg<BN, NKY>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
-    cudaError_t e = cudaFuncSetAttribute(fprop_pair_kernel<BN, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    cudaError_t e = cudaFuncSetAttribute(fprop_pair_kernel<BN, RESIDENT, NKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -451,7 +461,7 @@ cudaError_t pair_max_clusters(int* out) {
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, fprop_pair_kernel<BN, RESIDENT>, &qc);
+    e = cudaOccupancyMaxActiveClusters(&n, fprop_pair_kernel<BN, RESIDENT, NKY>, &qc);
     if (e != cudaSuccess) return e;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     max_clusters = n < sms / 2 ? n : sms / 2;
@@ -460,22 +470,22 @@ cudaError_t pair_max_clusters(int* out) {
   return cudaSuccess;
 }
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int NKY>
 cudaError_t pair_clusters(const FpropParams& p, int num_tiles, int* clusters) {
   int max_clusters = 0;
-  cudaError_t e = pair_max_clusters<BN, RESIDENT>(&max_clusters);
+  cudaError_t e = pair_max_clusters<BN, RESIDENT, NKY>(&max_clusters);
   if (e != cudaSuccess) return e;
   const int num_items = ((num_tiles + 1) / 2) * (p.N / BN);
   *clusters = num_items < max_clusters ? num_items : max_clusters;
   return cudaSuccess;
 }
 
-template <int BN, bool RESIDENT>
+template <int BN, bool RESIDENT, int NKY>
 cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const FpropParams& p,
                         int num_tiles, cudaStream_t stream) {
-  using L = PairCfg<BN>;
+  using L = PairCfg<BN, NKY>;
   int clusters = 0;
-  cudaError_t e = pair_clusters<BN, RESIDENT>(p, num_tiles, &clusters);
+  cudaError_t e = pair_clusters<BN, RESIDENT, NKY>(p, num_tiles, &clusters);
   if (e != cudaSuccess) return e;
   if (p.stats != nullptr && p.stat_groups > 0 && p.stat_rows != 4 * clusters) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
@@ -492,40 +502,53 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT>, mapA, mapB, mapO, p, num_tiles);
+  return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT, NKY>, mapA, mapB, mapO, p, num_tiles);
 }
 
 static bool pair_resident(const FpropParams& p, int bn) {
-  // weights resident in shared memory when one N block covers the layer and all 9 * kchunks half-tiles fit the B ring
-  const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
-                            : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
-  return p.N == bn && 9 * p.kchunks <= cap;
+  // weights resident in shared memory when one N block covers the layer and all its half-tiles fit the B ring
+  if (p.mode == 0) {
+    const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
+                              : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
+    return p.N == bn && 9 * p.kchunks <= cap;
+  }
+  const int cap = bn == 256 ? PairCfg<256, 1>::kSB : (bn == 128 ? PairCfg<128, 1>::kSB : PairCfg<64, 1>::kSB);
+  return p.N == bn && p.kchunks <= cap;
 }
+
+// (bn, resident, taps) -> instantiation
+#define B200CD_PAIR_DISPATCH(FN, ...)                                                              \
+  do {                                                                                              \
+    const bool res = pair_resident(p, bn);                                                          \
+    if (p.mode == 0) {                                                                              \
+      if (bn == 256) return res ? FN<256, true, 3>(__VA_ARGS__) : FN<256, false, 3>(__VA_ARGS__);   \
+      if (bn == 128) return res ? FN<128, true, 3>(__VA_ARGS__) : FN<128, false, 3>(__VA_ARGS__);   \
+      if (bn == 64) return res ? FN<64, true, 3>(__VA_ARGS__) : FN<64, false, 3>(__VA_ARGS__);      \
+    } else {                                                                                        \
+      if (bn == 256) return res ? FN<256, true, 1>(__VA_ARGS__) : FN<256, false, 1>(__VA_ARGS__);   \
+      if (bn == 128) return res ? FN<128, true, 1>(__VA_ARGS__) : FN<128, false, 1>(__VA_ARGS__);   \
+      if (bn == 64) return res ? FN<64, true, 1>(__VA_ARGS__) : FN<64, false, 1>(__VA_ARGS__);      \
+    }                                                                                               \
+  } while (0)
 
 }  // namespace
 
 cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
-  if (p.mode != 0 || p.out_mode != 0) return cudaErrorInvalidValue;
+  if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1)) return cudaErrorInvalidValue;
   if (p.stat_groups < 0 || p.stat_groups > 2) return cudaErrorInvalidValue;
-  const bool res = pair_resident(p, bn);
-  if (bn == 256) return res ? launch_pair<256, true>(mapA, mapB, mapO, p, num_tiles, stream)
-                            : launch_pair<256, false>(mapA, mapB, mapO, p, num_tiles, stream);
-  if (bn == 128) return res ? launch_pair<128, true>(mapA, mapB, mapO, p, num_tiles, stream)
-                            : launch_pair<128, false>(mapA, mapB, mapO, p, num_tiles, stream);
-  if (bn == 64) return res ? launch_pair<64, true>(mapA, mapB, mapO, p, num_tiles, stream)
-                           : launch_pair<64, false>(mapA, mapB, mapO, p, num_tiles, stream);
+  B200CD_PAIR_DISPATCH(launch_pair, mapA, mapB, mapO, p, num_tiles, stream);
+  return cudaErrorInvalidValue;
+}
+
+static cudaError_t pair_clusters_any(const FpropParams& p, int bn, int num_tiles, int* c) {
+  B200CD_PAIR_DISPATCH(pair_clusters, p, num_tiles, c);
   return cudaErrorInvalidValue;
 }
 
 int fprop_pair_ctas(const FpropParams& p, int bn, int num_tiles) {
-  const bool res = pair_resident(p, bn);
   int c = 0;
-  cudaError_t e = cudaErrorInvalidValue;
-  if (bn == 256) e = res ? pair_clusters<256, true>(p, num_tiles, &c) : pair_clusters<256, false>(p, num_tiles, &c);
-  else if (bn == 128) e = res ? pair_clusters<128, true>(p, num_tiles, &c) : pair_clusters<128, false>(p, num_tiles, &c);
-  else if (bn == 64) e = res ? pair_clusters<64, true>(p, num_tiles, &c) : pair_clusters<64, false>(p, num_tiles, &c);
-  return e == cudaSuccess ? 2 * c : -1;
+  return pair_clusters_any(p, bn, num_tiles, &c) == cudaSuccess ? 2 * c : -1;
 }
 
 }  // namespace b200cd

@@ -210,8 +210,9 @@ class StepEngine:
         tiles = ops.conv_gemm_tiles(H, W)
         # statistics rows per stat-group: one per 128-pixel tile, or (CTA-pair kernel) one per CTA and epilogue group
         st.stat_rows, st.stat_per_cta = (n_img // G) * tiles, False
-        if not first and self.device.type == "cuda":
-            st.stat_rows, st.stat_per_cta = ops.conv_stat_rows(n_img, H, W, conv.in_channels, C, G)
+        if self.device.type == "cuda":
+            ka = in_view.shape[3] if first else conv.in_channels
+            st.stat_rows, st.stat_per_cta = ops.conv_stat_rows(n_img, H, W, ka, C, G, mode=1 if first else 0)
         self._ws_need["stats"] = max(self._ws_need["stats"], G * st.stat_rows * C * 2)
         self._ws_need["stats2"] = max(self._ws_need["stats2"], 32 * G * C * 2)
         if self.train:

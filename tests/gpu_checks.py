@@ -232,7 +232,7 @@ def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> 
     return res
 
 
-def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3) -> dict:
+def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3, pair=None) -> dict:
     """ConvTranspose2d(c, c, 2, stride=2) forward, scattered into the second half of a 2c concat buffer."""
     g = _gen(seed)
     x = bf16r(torch.randn(n, c, h, w_, device=DEV, generator=g))
@@ -240,12 +240,44 @@ def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3) -> dict:
     b = torch.randn(c, device=DEV, generator=g)
     cat = torch.full((n, 2 * h, 2 * w_, 2 * c), 3.0, device=DEV, dtype=torch.bfloat16)
     Bw = ops.pack_weights(3, wt)  # [4c][c]
-    ops.conv_gemm(1, 1, nhwc(x).to(torch.bfloat16), Bw, cat[..., c:], bias=b)
+    ops.conv_gemm(1, 1, nhwc(x).to(torch.bfloat16), Bw, cat[..., c:], bias=b, pair=pair)
     ops.device_status()
     ref = F.conv_transpose2d(x, wt, b, stride=2)
     res = err(nchw(cat[..., c:].float()), ref, bf16_out=True)
     res["untouched"] = bool((cat[..., :c] == 3.0).all().item())
     res["ok"] = res["finite"] and res["rel_l2"] < tol and res["untouched"]
+    return res
+
+
+def check_first_conv(B=3, H=32, W=32, nc=4, cat_mode=0, seed=55, pair=None, G=2) -> dict:
+    """First-layer 3x3 conv (Cin = 2..8) as a single-tap GEMM over the im2col rows the input packer writes, with the
+    BatchNorm partial statistics (per tile, or per CTA with the CTA-pair kernel)."""
+    g = _gen(seed)
+    x1 = torch.rand(B, 6, H, W, device=DEV, generator=g)
+    x2 = torch.rand(B, 6, H, W, device=DEV, generator=g)
+    cin = 2 * nc if cat_mode else nc
+    kpad = 64 * ((9 * cin + 63) // 64)
+    w = bf16r(torch.randn(64, cin, 3, 3, device=DEV, generator=g) / (3.0 * cin ** 0.5))
+    b = torch.randn(64, device=DEV, generator=g)
+    cols = ops.pack_input(x1, x2, 2, nc, cat_mode, kpad)
+    n_img = cols.shape[0]
+    Bw = ops.pack_weights(2, w, kpad=kpad)
+    out = torch.empty(n_img, H, W, 64, device=DEV, dtype=torch.bfloat16)
+    Gs = G if (pair is not False and n_img % G == 0) else 0
+    if Gs:
+        rows, per_cta = ops.conv_stat_rows(n_img, H, W, kpad, 64, Gs, mode=1)
+    else:
+        rows, per_cta = n_img * ops.conv_gemm_tiles(H, W), False
+    stats = torch.zeros((Gs if per_cta else 1), rows if per_cta else n_img * ops.conv_gemm_tiles(H, W), 64, 2, device=DEV)
+    ops.conv_gemm(1, 0, cols, Bw, out, bias=b, stats=stats, pair=pair, stat_groups=Gs if per_cta else 0)
+    ops.device_status()
+    xin = torch.cat([x1[:, 2:2 + nc], x2[:, 2:2 + nc]], 1 if cat_mode else 0)
+    ref = F.conv2d(bf16r(xin), w, b, padding=1)
+    res = err(nchw(out.float()), ref, bf16_out=True)
+    o32 = out.float()
+    res["stats_sum_rel"] = ((stats[..., 0].sum((0, 1)) - o32.sum((0, 1, 2))).norm() / o32.sum((0, 1, 2)).norm()).item()
+    res["per_cta"] = per_cta
+    res["ok"] = res["finite"] and res["rel_l2"] < 6e-3 and res["stats_sum_rel"] < 1e-4
     return res
 
 
@@ -714,6 +746,14 @@ ALL_CHECKS = {
     "convt_fwd_tiny_8x8": lambda: check_convt_fwd(3, 8, 8, 128, seed=52),
     "convt_fwd_tiny_4x4": lambda: check_convt_fwd(3, 4, 4, 512, seed=53),
     "convt_fwd_odd_6x12": lambda: check_convt_fwd(2, 6, 12, 64, seed=54),
+    "convt_fwd_single_cta": lambda: check_convt_fwd(pair=False),
+    "convt_fwd_single_cta_odd_6x12": lambda: check_convt_fwd(2, 6, 12, 64, seed=54, pair=False),
+    "convt_fwd_many_256": lambda: check_convt_fwd(8, 32, 32, 256, seed=56),
+    "convt_fwd_many_64": lambda: check_convt_fwd(16, 64, 64, 64, seed=57),
+    "first_conv_siamese_pair": check_first_conv,
+    "first_conv_early_fusion_8ch_pair": lambda: check_first_conv(4, 32, 48, 4, cat_mode=1, seed=58, G=1),
+    "first_conv_single_cta": lambda: check_first_conv(pair=False),
+    "first_conv_many": lambda: check_first_conv(16, 64, 64, 2, cat_mode=1, seed=59, G=1),
     "convt_dgrad": check_convt_dgrad,
     "convt_dgrad_tiny_8x8": lambda: check_convt_dgrad(3, 8, 8, 128, seed=62),
     "convt_dgrad_tiny_4x4": lambda: check_convt_dgrad(3, 4, 4, 512, seed=63),
