@@ -104,7 +104,7 @@ int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int6
  *   flags: bit 0 (mode 0 only) = load the activation tile once per kx with a one-row halo and serve the three ky
  *          taps from it (less L2 -> SM traffic; same result bit for bit).
  *          bit 1 = use a 128 x 256 output tile when N (out_mode 1: cout) is a multiple of 256 and bit 0 is clear.
- *          bit 2 (mode 0 with out_mode 0, and mode 1 with either out_mode) = CTA-pair kernel: two SMs compute one 256-pixel tile with cta_group::2 MMAs,
+ *          bit 2 (every mode; out_mode 1 only with mode 1) = CTA-pair kernel: two SMs compute one 256-pixel tile with cta_group::2 MMAs,
  *          each loading half of the weight tile; persistent, weights resident in shared memory when they fit
  *          (same result bit for bit).
  *   requires ka % 64 == 0, N % 64 == 0, a_ld % 8 == 0, out_ld % 8 == 0.

@@ -231,7 +231,7 @@ struct ConvPlan {
 static ConvPlan plan_conv(int mode, int out_mode, int flags, int n_img, int H, int W, int N) {
   ConvPlan c;
   tile_shape(W, H, mode == 2 || out_mode == 1, &c.tw, &c.th);
-  c.pair = ((flags & 4) && ((mode == 0 && out_mode == 0) || mode == 1)) ? 1 : 0;
+  c.pair = ((flags & 4) && ((mode != 1 && out_mode == 0) || mode == 1)) ? 1 : 0;
   c.halo = (mode == 0 && ((flags & 1) || c.pair)) ? 1 : 0;
   c.num_tiles = n_img * ((W + c.tw - 1) / c.tw) * ((H + c.th - 1) / c.th);
   // N tile: 64 when the width is not a multiple of 128; 256 on request (flags bit 1) when it divides the width —
@@ -258,6 +258,7 @@ int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int
   memset(&p, 0, sizeof(p));
   p.mode = mode;
   p.out_mode = out_mode;
+  p.taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
   p.N = N;
   p.kchunks = ka / 64;
   const int ctas = b200cd::fprop_pair_ctas(p, c.bn, c.num_tiles);

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   const int num_pairs = (num_tiles + 1) >> 1;
   const int n_blocks = p.N / BN;
   const int num_items = num_pairs * n_blocks;  // item = n_block * num_pairs + pair (pairs fastest: all pairs share B)
-  const int steps = NKY * p.kchunks;           // A boxes per item (3x3: one per kx and 64-channel chunk)
+  // A boxes per item: 3x3: one per kx and 64-channel chunk; otherwise one per tap (1, or the 4 gathered taps of the
+  // transposed-conv input gradient) and chunk
+  const int steps = (NKY == 3 ? 3 : p.taps) * p.kchunks;
   constexpr bool resident = RESIDENT;  // host: n_blocks == 1 and all 3 * steps weight tiles fit in the B ring
 
   if (warp == 0 && lane == 0) {
@@ -141,7 +143,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         if (elect_one_sync()) {
           if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
           if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
-          else tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
+          else if (p.mode == 1) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
+          else  // mode 2: tap kx = (dy, dx) of the 2x2 / stride-2 gather from the full-resolution tensor
+            tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, kx & 1, x0, kx >> 1, img * p.H + y0);
         }
         __syncwarp();
         if (++sa == L::kSA) {
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
               if (elect_one_sync()) {
                 if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
                 tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb],
-                                 (NKY == 3 ? (ky * 3 + kx) * p.ka : 0) + kc * 64, nrow);
+                                 (NKY == 3 ? (ky * 3 + kx) : kx) * p.ka + kc * 64, nrow);
               }
               __syncwarp();
               if (++sb == L::kSB) {  // resident: the layer's tiles fill at most kSB slots, once, in order
@@ -513,7 +517,7 @@ static bool pair_resident(const FpropParams& p, int bn) {
     return p.N == bn && 9 * p.kchunks <= cap;
   }
   const int cap = bn == 256 ? PairCfg<256, 1>::kSB : (bn == 128 ? PairCfg<128, 1>::kSB : PairCfg<64, 1>::kSB);
-  return p.N == bn && p.kchunks <= cap;
+  return p.N == bn && p.taps * p.kchunks <= cap;
 }
 
 // (bn, resident, taps) -> instantiation
@@ -535,7 +539,7 @@ static bool pair_resident(const FpropParams& p, int bn) {
 
 cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
-  if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1)) return cudaErrorInvalidValue;
+  if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1 || (p.mode == 2 && p.out_mode == 0))) return cudaErrorInvalidValue;
   if (p.stat_groups < 0 || p.stat_groups > 2) return cudaErrorInvalidValue;
   B200CD_PAIR_DISPATCH(launch_pair, mapA, mapB, mapO, p, num_tiles, stream);
   return cudaErrorInvalidValue;

@@ -184,7 +184,7 @@ FPROP_PAIR = True           # 3x3 convs on CTA pairs (cta_group::2, persistent, 
 def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, stat_groups: int) -> int:
     """Tile policy (measured on B200, profiles/): 3x3 convs on CTA pairs; otherwise 128x256 tiles where N % 256 == 0,
     the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)."""
-    pair_ok = (mode == 0 and out_mode == 0) or mode == 1
+    pair_ok = out_mode == 0 or mode == 1
     if pair is None:
         pair = FPROP_PAIR and pair_ok and halo is None and wide is None
     pair = bool(pair) and pair_ok

@@ -281,7 +281,7 @@ def check_first_conv(B=3, H=32, W=32, nc=4, cat_mode=0, seed=55, pair=None, G=2)
     return res
 
 
-def check_convt_dgrad(n=2, h=16, w_=16, c=128, seed=6, tol=6e-3) -> dict:
+def check_convt_dgrad(n=2, h=16, w_=16, c=128, seed=6, tol=6e-3, pair=None) -> dict:
     g = _gen(seed)
     wt = bf16r(torch.randn(c, c, 2, 2, device=DEV, generator=g) / (2.0 * c ** 0.5))
     dcat = torch.zeros(n, 2 * h, 2 * w_, 2 * c, device=DEV, dtype=torch.bfloat16)
@@ -289,7 +289,7 @@ def check_convt_dgrad(n=2, h=16, w_=16, c=128, seed=6, tol=6e-3) -> dict:
     dcat[..., c:] = nhwc(dout).to(torch.bfloat16)
     Bd = ops.pack_weights(4, wt)  # [c][4c]
     out = torch.empty(n, h, w_, c, device=DEV, dtype=torch.bfloat16)
-    ops.conv_gemm(2, 0, dcat[..., c:], Bd, out)
+    ops.conv_gemm(2, 0, dcat[..., c:], Bd, out, pair=pair)
     ops.device_status()
     ref = F.conv2d(dout, wt, stride=2)  # input gradient of conv_transpose2d(x, wt, stride=2)
     res = err(nchw(out.float()), ref, bf16_out=True)
@@ -755,6 +755,10 @@ ALL_CHECKS = {
     "first_conv_single_cta": lambda: check_first_conv(pair=False),
     "first_conv_many": lambda: check_first_conv(16, 64, 64, 2, cat_mode=1, seed=59, G=1),
     "convt_dgrad": check_convt_dgrad,
+    "convt_dgrad_single_cta": lambda: check_convt_dgrad(pair=False),
+    "convt_dgrad_single_cta_tiny_4x4": lambda: check_convt_dgrad(3, 4, 4, 512, seed=63, pair=False),
+    "convt_dgrad_many_256": lambda: check_convt_dgrad(8, 32, 32, 256, seed=64),
+    "convt_dgrad_many_64": lambda: check_convt_dgrad(16, 64, 64, 64, seed=65),
     "convt_dgrad_tiny_8x8": lambda: check_convt_dgrad(3, 8, 8, 128, seed=62),
     "convt_dgrad_tiny_4x4": lambda: check_convt_dgrad(3, 4, 4, 512, seed=63),
     "convt_dgrad_64": lambda: check_convt_dgrad(2, 16, 32, 64, seed=61),
