@@ -112,6 +112,16 @@ int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int6
 int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
                      const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
                      void* stream);
+/* The input-gradient convolution (mode 0 with dgrad weights, or mode 2) of a layer whose INPUT was produced by
+ * BatchNorm+ReLU, with the reduce pass of that BatchNorm's backward fused into the epilogue: besides storing the gradient
+ * tile dy it accumulates, per CTA, S1 = sum dy*[y > 0] and S2 = sum dy*[y > 0]*r, where r is the pre-BN tensor of the
+ * producing layer (NHWC bf16 view [n_img][H][W][N], stride r_ld) and y = r*scale + shift (scale / shift fp32 [G][N], as
+ * written by b200cd_bn_stats). Requires the CTA-pair kernel with per-CTA statistics (flags bits 2 and 3, G in bits
+ * 8..15); sums is fp32 [G][rows][N][2] with rows = b200cd_conv_gemm_stat_rows(mode, 0, flags, ...). Feed the result to
+ * b200cd_bn_bwd_from_sums. */
+int b200cd_conv_gemm_bnbwd(int mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka, const void* Bw,
+                           int N, void* out_bf16, int64_t out_ld, const void* r, int64_t r_ld, const float* scale,
+                           const float* shift, float* sums, void* stream);
 /* tiles_per_image for (H, W): stats has n_img * tiles_per_image rows. */
 int b200cd_conv_gemm_tiles(int H, int W);
 /* flags bit 3 (with bit 2, the CTA-pair kernel) switches the statistics to per-CTA running sums: bits 8..15 of flags hold
@@ -191,6 +201,12 @@ typedef struct {
 int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
                   const float* shift, const b200cd_grad_src* srcs /* [3] */, int n_img, int H, int W, int C, int G,
                   float* ws, float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream);
+/* The same when the sums S1, S2 of the single gradient source were already accumulated by b200cd_conv_gemm_bnbwd
+ * (sums fp32 [G][sum_rows][C][2]): only the finalize and dx kernels run; srcs must describe that one direct source. */
+int b200cd_bn_bwd_from_sums(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                            const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G,
+                            const float* sums, int sum_rows, float* ws, float* dgamma, float* dbeta, void* dr_bf16,
+                            int64_t ld_dr, void* stream);
 size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G);
 
 /* OutConv (nn.Conv2d(c, 1, 1), utils/networks.py:454-461) forward over one or two C-channel inputs

@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200cd_pack_job_blocks": (_i, [_i, _i, _i, _i]),
     "b200cd_pack_weights_batched": (_i, [_vp, _i, _i64, _vp]),
     "b200cd_conv_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "b200cd_conv_gemm_bnbwd": (_i, [_i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200cd_conv_gemm_tiles": (_i, [_i, _i]),
     "b200cd_conv_gemm_stat_rows": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "b200cd_wgrad_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _i64, _i64, _i64, _vp]),
@@ -48,6 +49,8 @@ SIGNATURES = {
     "b200cd_bn_stats": (_i, [_vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200cd_bn_apply": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "b200cd_bn_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(GradSrc), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "b200cd_bn_bwd_from_sums": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(GradSrc), _i, _i, _i, _i, _i, _vp, _i, _vp, _vp,
+                                     _vp, _vp, _i64, _vp]),
     "b200cd_bn_bwd_ws_floats": (_sz, [_i, _i, _i, _i, _i]),
     "b200cd_head_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
     "b200cd_colsum": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp]),

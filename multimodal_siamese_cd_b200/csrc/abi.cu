@@ -265,9 +265,10 @@ int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int
   return ctas < 0 ? -1 : 2 * ctas;            // rows per stat-group: one per (CTA, epilogue group)
 }
 
-int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
-                     const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
-                     void* stream) {
+static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                          const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
+                          const void* bwd_r, int64_t bwd_ld, const float* bwd_scale, const float* bwd_shift,
+                          void* stream) {
   if (mode < 0 || mode > 2 || out_mode < 0 || out_mode > 1) return fail(B200CD_ERR_SHAPE, "conv_gemm: bad mode");
   if (ka < 64 || ka % 64 != 0 || N < 64 || N % 64 != 0)
     return fail(B200CD_ERR_SHAPE, "conv_gemm: ka=%d and N=%d must be multiples of 64", ka, N);
@@ -305,6 +306,16 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   p.err = err;
   p.n_img = n_img;
   p.stat_groups = cp.stat_groups;
+  if (bwd_r != nullptr) {
+    if (!pair || cp.stat_groups == 0 || stats == nullptr || out_mode != 0 || bwd_scale == nullptr || bwd_shift == nullptr)
+      return fail(B200CD_ERR_SHAPE, "conv_gemm_bnbwd: needs the CTA-pair kernel with per-CTA statistics (flags bits 2, 3)");
+    if (bwd_ld % 2 != 0 || bwd_ld < N || (reinterpret_cast<uintptr_t>(bwd_r) & 3u))
+      return fail(B200CD_ERR_ALIGN, "conv_gemm_bnbwd: pre-BN tensor stride / alignment");
+    p.bwd_r = bwd_r;
+    p.bwd_ld = bwd_ld;
+    p.bwd_scale = bwd_scale;
+    p.bwd_shift = bwd_shift;
+  }
   const int num_tiles = cp.num_tiles;
   if (cp.stat_groups > 0 && stats != nullptr) {
     const int ctas = b200cd::fprop_pair_ctas(p, bn, num_tiles);
@@ -332,6 +343,21 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
   else
     CUDA_TRY(b200cd::launch_fprop(mapA, mapB, mapO, p, bn, halo, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
+}
+
+int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                     const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
+                     void* stream) {
+  return conv_gemm_impl(mode, out_mode, flags, A, a_ld, n_img, H, W, ka, Bw, N, cout, out, out_ld, bias, stats, nullptr, 0,
+                        nullptr, nullptr, stream);
+}
+
+int b200cd_conv_gemm_bnbwd(int mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka, const void* Bw,
+                           int N, void* out, int64_t out_ld, const void* r, int64_t r_ld, const float* scale,
+                           const float* shift, float* sums, void* stream) {
+  if (r == nullptr) return fail(B200CD_ERR_SHAPE, "conv_gemm_bnbwd: r is NULL");
+  return conv_gemm_impl(mode, 0, flags, A, a_ld, n_img, H, W, ka, Bw, N, 0, out, out_ld, nullptr, sums, r, r_ld, scale, shift,
+                        stream);
 }
 
 int b200cd_wgrad_tiles(int n_img, int H, int W) { return n_img * ((W + 7) / 8) * ((H + 7) / 8); }
@@ -441,9 +467,29 @@ size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G) {
   return static_cast<size_t>(2) * G * C * (bn_bwd_nblk(n_img, H, W, C, G) + 1);
 }
 
+static int bn_bwd_impl(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                       const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
+                       float* dgamma, float* dbeta, void* dr, int64_t ld_dr, const float* sums, int sum_rows, void* stream);
+
 int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
                   const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
                   float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream) {
+  return bn_bwd_impl(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G, ws, dgamma, dbeta, dr, ld_dr, nullptr, 0,
+                     stream);
+}
+
+int b200cd_bn_bwd_from_sums(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                            const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G,
+                            const float* sums, int sum_rows, float* ws, float* dgamma, float* dbeta, void* dr,
+                            int64_t ld_dr, void* stream) {
+  if (sums == nullptr || sum_rows < 1) return fail(B200CD_ERR_SHAPE, "bn_bwd_from_sums: no partial sums");
+  return bn_bwd_impl(r, ld_r, mean, invstd, scale, shift, srcs, n_img, H, W, C, G, ws, dgamma, dbeta, dr, ld_dr, sums,
+                     sum_rows, stream);
+}
+
+static int bn_bwd_impl(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                       const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
+                       float* dgamma, float* dbeta, void* dr, int64_t ld_dr, const float* sums, int sum_rows, void* stream) {
   if (!chan_ok(C)) return fail(B200CD_ERR_SHAPE, "bn_bwd: C=%d must be a multiple of 64 with 256 %% (C/8) == 0", C);
   if (G <= 0 || n_img % G != 0) return fail(B200CD_ERR_SHAPE, "bn_bwd: n_img must be a multiple of G");
   if (ld_r % 8 || ld_dr % 8 || !aligned16(r) || !aligned16(dr)) return fail(B200CD_ERR_ALIGN, "bn_bwd: alignment");
@@ -470,8 +516,12 @@ int b200cd_bn_bwd(const void* r, int64_t ld_r, const float* mean, const float* i
   float* coefA = ws + static_cast<size_t>(2) * G * C * nblk;
   float* coefB = coefA + static_cast<size_t>(G) * C;
   const double count = static_cast<double>(n_img / G) * H * W;
-  CUDA_TRY(b200cd::launch_bn_bwd_reduce(r, ld_r, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
-  CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta, coefA, coefB, st));
+  if (sums != nullptr) {  // S1, S2 already reduced per CTA by the convolution that produced the gradient
+    CUDA_TRY(b200cd::launch_bn_bwd_finalize(sums, sum_rows, C, G, count, mean, invstd, scale, dgamma, dbeta, coefA, coefB, st));
+  } else {
+    CUDA_TRY(b200cd::launch_bn_bwd_reduce(r, ld_r, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
+    CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta, coefA, coefB, st));
+  }
   CUDA_TRY(b200cd::launch_bn_bwd_dx(r, ld_r, scale, shift, coefA, coefB, gs, n_img, H, W, C, G, nblk, dr, ld_dr, st));
   return 0;
 }

@@ -340,6 +340,24 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
 #pragma unroll
       for (int slab = 0; slab < BN / 64; ++slab, ++n_slab) {
         uint8_t* sbuf = stg + (n_slab % L::kStg) * kStageSlab;
+        // fused BatchNorm-backward sums: this thread's 8 rows x 8 channels of the pre-BN tensor, requested before the
+        // accumulator is read so that the global-load latency hides under the TMEM load / conversion / store issue
+        uint4 rv[8];
+        bool okr[8];
+        if (p.bwd_r != nullptr) {
+          const int oct = t & 7, rg = t >> 3;
+          const int tw_shift = p.tw == 16 ? 4 : 3;
+          const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.bwd_r) + n0 + slab * 64 + oct * 8;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = rg * 8 + u;
+            const int yy = y0 + (r >> tw_shift), xx = x0 + (r & (p.tw - 1));
+            okr[u] = real && r < p.tw * p.th && yy < p.H && xx < p.W;
+            rv[u] = okr[u] ? __ldg(reinterpret_cast<const uint4*>(
+                                 rbase + ((static_cast<long long>(img) * p.H + yy) * p.W + xx) * p.bwd_ld))
+                           : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         // the TMA store that last used this staging buffer has finished reading it
         if (t == 0 && n_slab >= L::kStg) {
           if (L::kStg == 2) tma_store_wait_read1();
@@ -389,25 +407,75 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           const int cp = t & 31;  // channel pair inside the slab
           const int rq = t >> 5;  // row quarter
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          for (int r = rq * 32; r < rq * 32 + 32; ++r) {
-            const uint32_t w =
-                *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
-            float lo = bf16_lo(w), hi = bf16_hi(w);
-            if (p.ragged) {
-              const bool ok = (r < p.tw * p.th) && (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
-              lo = ok ? lo : 0.f;
-              hi = ok ? hi : 0.f;
+          if (p.bwd_r != nullptr) {
+            // BatchNorm-backward sums of the gradient tile being stored: per channel (sum dy*m, sum dy*m*r) with the
+            // ReLU mask m recomputed from the pre-BN values exactly as the dx pass does. Thread = 8 rows x 8 channels;
+            // the four row groups of a warp are combined with shuffles, the four warps through `red`.
+            const int oct = t & 7, rg = t >> 3;
+            const int c0 = n0 + slab * 64 + oct * 8;
+            float sc[8], sh[8], ss[8], qq2[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              sc[jj] = __ldg(p.bwd_scale + sgrp * p.N + c0 + jj);
+              sh[jj] = __ldg(p.bwd_shift + sgrp * p.N + c0 + jj);
+              ss[jj] = qq2[jj] = 0.f;
             }
-            s0 += lo;
-            q0 += lo * lo;
-            s1 += hi;
-            q1 += hi * hi;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = rg * 8 + u;
+              const uint4 dv = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((oct ^ (r & 7)) << 4));
+              const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+              const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+              for (int h2 = 0; h2 < 4; ++h2) {
+                const float rlo = bf16_lo(rw[h2]), rhi = bf16_hi(rw[h2]);
+                const float dlo = (okr[u] && fmaf(rlo, sc[2 * h2], sh[2 * h2]) > 0.f) ? bf16_lo(dw[h2]) : 0.f;
+                const float dhi = (okr[u] && fmaf(rhi, sc[2 * h2 + 1], sh[2 * h2 + 1]) > 0.f) ? bf16_hi(dw[h2]) : 0.f;
+                ss[2 * h2] += dlo;
+                qq2[2 * h2] = fmaf(dlo, rlo, qq2[2 * h2]);
+                ss[2 * h2 + 1] += dhi;
+                qq2[2 * h2 + 1] = fmaf(dhi, rhi, qq2[2 * h2 + 1]);
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              ss[jj] += __shfl_xor_sync(0xffffffffu, ss[jj], 8);
+              ss[jj] += __shfl_xor_sync(0xffffffffu, ss[jj], 16);
+              qq2[jj] += __shfl_xor_sync(0xffffffffu, qq2[jj], 8);
+              qq2[jj] += __shfl_xor_sync(0xffffffffu, qq2[jj], 16);
+            }
+            if ((t & 31) < 8) {
+              float* dst = red + (((t >> 5) * 64) + oct * 8) * 2;   // [warp][channel][sum, sum*r]
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                dst[2 * jj] = ss[jj];
+                dst[2 * jj + 1] = qq2[jj];
+              }
+            }
+            s0 = s1 = q0 = q1 = 0.f;
+          } else {
+            for (int r = rq * 32; r < rq * 32 + 32; ++r) {
+              const uint32_t w =
+                  *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
+              float lo = bf16_lo(w), hi = bf16_hi(w);
+              if (p.ragged) {
+                const bool ok = (r < p.tw * p.th) && (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
+                lo = ok ? lo : 0.f;
+                hi = ok ? hi : 0.f;
+              }
+              s0 += lo;
+              q0 += lo * lo;
+              s1 += hi;
+              q1 += hi * hi;
+            }
           }
-          float* dst = red + ((rq * 64) + 2 * cp) * 2;
-          dst[0] = s0;
-          dst[1] = q0;
-          dst[2] = s1;
-          dst[3] = q1;
+          if (p.bwd_r == nullptr) {
+            float* dst = red + ((rq * 64) + 2 * cp) * 2;
+            dst[0] = s0;
+            dst[1] = q0;
+            dst[2] = s1;
+            dst[3] = q1;
+          }
           named_barrier_sync(bar2, 128);
           if (t < 64 && real) {
             float s = 0.f, qq = 0.f;

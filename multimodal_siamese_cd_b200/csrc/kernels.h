@@ -49,6 +49,14 @@ struct FpropParams {
   // CTA-pair kernel only: stat_groups > 0 switches the statistics to per-CTA running sums, stats[g][row][n] with
   // stat_rows rows per BatchNorm stat-group g = image / (n_img / stat_groups) (row = 2 * blockIdx.x + epilogue group)
   int stat_groups, stat_rows, n_img;
+  // CTA-pair kernel, per-CTA statistics only: when bwd_r != nullptr the tile being stored is the gradient dy w.r.t. a
+  // BatchNorm+ReLU output whose pre-BN tensor is bwd_r (same pixel grid, channel n of the tile = channel n of bwd_r):
+  // the statistics become the BatchNorm-backward sums S1 = sum dy*[y > 0], S2 = sum dy*[y > 0]*r with
+  // y = r*scale + shift (scale/shift: [stat_groups][N]) — the reduce pass of b200cd_bn_bwd, fused into the epilogue.
+  const void* bwd_r;
+  long long bwd_ld;
+  const float* bwd_scale;
+  const float* bwd_shift;
   int* err;
 };
 // CTAs the CTA-pair kernel launches for this problem (needs the current device: occupancy query on first use)

@@ -27,6 +27,10 @@ BF16 = torch.bfloat16
 # weight-gradient kernels split the pixel dimension until about this many CTAs are in flight (the per-split partial
 # results are summed by wgrad_reduce in a fixed order); measured on B200 in profiles/
 WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
+# BatchNorm backward of stages with a single direct gradient source: accumulate its reduce pass in the epilogue of the
+# input-gradient convolution that produces that gradient (ops.conv_gemm_bnbwd)
+FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != "0"
+FUSE_BN_BWD_MIN_PIXELS = int(__import__("os").environ.get("B200CD_FUSE_BN_BWD_MIN_PIXELS", 32768))
 # 64-wide weight-gradient tiles: one CTA may own two kx columns (gemm_wgrad.cu, NKX = 2). Measured slower than one kx
 # per CTA once tap pairs are issued as N = 128 MMAs (the kernel is bound by MN-major operand reads from shared memory,
 # not by the L2 -> SM stream): off by default, kept for the parity tests and for re-measurement.
@@ -64,6 +68,8 @@ class Stage:
     shift: torch.Tensor = None
     stat_rows: int = 0
     stat_per_cta: bool = False
+    bwd_sums: Optional[torch.Tensor] = None   # [G][rows][C][2]: BatchNorm-backward sums accumulated by the dgrad epilogue
+    bwd_sum_rows: int = 0
 
     @property
     def cin(self) -> int:
@@ -508,6 +514,27 @@ class StepEngine:
         splits = max(1, min(total, max(1, WGRAD_CTA_TARGET // ctas)))
         return (role, splits, self._ws_region(splits * 9 * cout * cin), 0)
 
+    def _fusable_producer(self, grad: torch.Tensor, mode: int = 0, ka: int = 64) -> Optional[Stage]:
+        """The stage whose BatchNorm backward has `grad` as its one and only (direct, unscaled) gradient source and the
+        same dense layout: its reduce pass can run in the epilogue of the kernel that writes `grad`. Allocates the
+        stage's partial-sum buffer on first use."""
+        if not FUSE_BN_BWD_REDUCE or self.device.type != "cuda" or not ops.FPROP_PAIR:
+            return None
+        for ps in self.stages:
+            if len(ps.srcs) == 1 and ps.srcs[0]["kind"] == 1 and ps.srcs[0]["t"] is grad and not ps.srcs[0].get("n_mod"):
+                if tuple(grad.shape) != tuple(ps.r.shape) or ps.cout % 64 != 0:
+                    return None
+                if ps.n_img * ps.H * ps.W < FUSE_BN_BWD_MIN_PIXELS:
+                    return None   # few work items per CTA pair: the longer epilogue is not hidden (measured)
+                if ps.bwd_sums is None:
+                    rows, per_cta = ops.conv_stat_rows(ps.n_img, ps.H, ps.W, ka, ps.cout, ps.G, mode=mode)
+                    if not per_cta:
+                        return None
+                    ps.bwd_sum_rows = rows
+                    ps.bwd_sums = self._new(ps.G, rows, ps.cout, 2, dtype=torch.float32)
+                return ps
+        return None
+
     def _emit_stage_bwd(self, st: Stage) -> None:
         eng = self
         g = self.grads
@@ -525,9 +552,13 @@ class StepEngine:
             size = splits * 9 * cout * cin
             eng._reduce_specs.append((op_index, off, gw, splits, 9 * cout * cin, 0, cout, cin, 9, splits2))
 
+        # the stage whose output feeds this conv: if this conv's input gradient is its ONLY gradient source, the reduce
+        # pass of its BatchNorm backward runs in this dgrad's epilogue (ops.conv_gemm_bnbwd)
+        prod = eng._fusable_producer(st.d_in, 0, st.cout) if st.d_in is not None else None
+
         def run():
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
-                       st.dr)
+                       st.dr, sums=st.bwd_sums, sum_rows=st.bwd_sum_rows)
             ws = eng.ws_wgrad.narrow(0, off, size)
             if role == "first":
                 ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
@@ -538,7 +569,10 @@ class StepEngine:
                 else:
                     ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
                 if st.d_in is not None:
-                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
+                    if prod is not None:
+                        ops.conv_gemm_bnbwd(0, st.dr, st.Wd, st.d_in, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
+                    else:
+                        ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
         eng.bwd_ops.append(run)
         eng.bwd_marks.append(g.end_of(conv.weight))
@@ -559,10 +593,15 @@ class StepEngine:
         self._ws_need["colsum"] = max(self._ws_need["colsum"], nblk * c)
         eng._reduce_specs.append((len(eng.bwd_ops), off, gw, splits, 4 * c * c, 0, c, c, 4, 0))
 
+        prod = eng._fusable_producer(uc.d_x, 2, c)
+
         def run():
             ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
             ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
-            ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
+            if prod is not None:
+                ops.conv_gemm_bnbwd(2, uc.d_out, uc.Wd, uc.d_x, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
+            else:
+                ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
 
         eng.bwd_ops.append(run)
         eng.bwd_marks.append(g.end_of(uc.up.weight))

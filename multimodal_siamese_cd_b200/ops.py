@@ -236,6 +236,28 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
                                                 out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
 
+def conv_gemm_bnbwd(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor, r: torch.Tensor, scale: torch.Tensor,
+                    shift: torch.Tensor, sums: torch.Tensor, stat_groups: int) -> None:
+    """Input-gradient convolution (mode 0 with dgrad weights / mode 2) whose epilogue also accumulates the
+    BatchNorm-backward sums of the gradient it stores (see include/b200cd.h: b200cd_conv_gemm_bnbwd)."""
+    _require_cuda(A, Bw, out, r, sums)
+    n, Ha, Wa, ka, a_ld = _nhwc(A)
+    H, W = (Ha // 2, Wa // 2) if mode == 2 else (Ha, Wa)
+    no, Ho, Wo, Co, o_ld = _nhwc(out)
+    nr, Hr, Wr, Cr, r_ld = _nhwc(r)
+    N = Bw.shape[0]
+    taps = 9 if mode == 0 else 4
+    assert mode in (0, 2) and Bw.shape[1] == taps * ka and (no, Ho, Wo, Co) == (n, H, W, N) == (nr, Hr, Wr, Cr)
+    assert sums.dtype == torch.float32 and scale.shape[-1] == N
+    flags = 4 | 8 | (stat_groups << 8)
+    _count(1)
+    fam = "fprop3x3" if mode == 0 else "convT_dgrad"
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw, r), f"{n}x{H}x{W} k{ka}->n{N} bnbwd"):
+        _lib.check(_lib.load().b200cd_conv_gemm_bnbwd(mode, flags, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N,
+                                                      out.data_ptr(), o_ld, r.data_ptr(), r_ld, scale.data_ptr(),
+                                                      shift.data_ptr(), sums.data_ptr(), _stream()))
+
+
 def wgrad_tiles(n: int, H: int, W: int) -> int:
     return _lib.load().b200cd_wgrad_tiles(n, H, W)
 
@@ -360,11 +382,21 @@ def bn_bwd_ws_floats(n: int, H: int, W: int, C_: int, G: int) -> int:
 
 
 def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-           srcs: C.Array, G: int, ws: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, dr: torch.Tensor) -> None:
+           srcs: C.Array, G: int, ws: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, dr: torch.Tensor,
+           sums: Optional[torch.Tensor] = None, sum_rows: int = 0) -> None:
     _require_cuda(r, dr, ws)
     n, H, W, Cc, ld_r = _nhwc(r)
-    _count(3)
     nsrc = sum(1.0 if s.kind == 1 else (0.25 if s.kind == 2 else 0.0) for s in srcs)
+    if sums is not None:
+        # the reduce pass ran in the epilogue of the convolution that produced the gradient: finalize + dx only
+        _count(2)
+        with _Prof("bn_bwd", 0.0, _nbytes(r) * (1.0 + nsrc + 1.0), f"{n}x{H}x{W}x{Cc} G{G} from_sums"):
+            _lib.check(_lib.load().b200cd_bn_bwd_from_sums(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(),
+                                                           scale.data_ptr(), shift.data_ptr(), srcs, n, H, W, Cc, G,
+                                                           sums.data_ptr(), sum_rows, ws.data_ptr(), dgamma.data_ptr(),
+                                                           dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4], _stream()))
+        return
+    _count(3)
     # two passes: each reads r and every gradient source; the second writes dr
     with _Prof("bn_bwd", 0.0, _nbytes(r) * (2.0 + 2.0 * nsrc + 1.0),
                f"{n}x{H}x{W}x{Cc} G{G} srcs{[s.kind for s in srcs]}"):

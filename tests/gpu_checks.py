@@ -232,6 +232,61 @@ def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> 
     return res
 
 
+def check_dgrad_bnbwd(n=4, H=32, W=32, cin=64, cout=128, G=2, seed=66, mode=0) -> dict:
+    """Input-gradient convolution with the BatchNorm-backward reduce pass fused into its epilogue: the gradient it
+    stores must equal the plain dgrad launch bit for bit, the per-CTA sums (S1, S2) must equal sum dy*m and sum dy*m*r
+    of the stored gradient, and bn_bwd_from_sums must reproduce bn_bwd."""
+    g = _gen(seed)
+    if mode == 0:
+        w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cout ** 0.5))
+        dout = bf16r(torch.randn(n, cout, H, W, device=DEV, generator=g))
+        Bd = ops.pack_weights(1, w)                                   # [cin][9*cout]
+        A = nhwc(dout).to(torch.bfloat16)
+    else:
+        w = bf16r(torch.randn(cin, cin, 2, 2, device=DEV, generator=g) / (2.0 * cin ** 0.5))
+        dout = bf16r(torch.randn(n, cin, 2 * H, 2 * W, device=DEV, generator=g))
+        Bd = ops.pack_weights(4, w)                                   # [cin][4*cin]
+        A = nhwc(dout).to(torch.bfloat16)
+    r = bf16r(torch.randn(n, H, W, cin, device=DEV, generator=g)).to(torch.bfloat16)   # pre-BN tensor of the producer
+    scale = torch.rand(G, cin, device=DEV, generator=g) + 0.5
+    scale[:, ::7] *= -1.0                                                               # negative gamma too
+    shift = torch.randn(G, cin, device=DEV, generator=g) * 0.3
+    mean = torch.randn(G, cin, device=DEV, generator=g) * 0.1
+    invstd = torch.rand(G, cin, device=DEV, generator=g) + 0.5
+    rows, per_cta = ops.conv_stat_rows(n, H, W, cout if mode == 0 else cin, cin, G, mode=mode)
+    sums = torch.full((G, rows, cin, 2), float("nan"), device=DEV)
+    d_fused = torch.empty(n, H, W, cin, device=DEV, dtype=torch.bfloat16)
+    d_plain = torch.empty_like(d_fused)
+    ops.conv_gemm_bnbwd(mode, A, Bd, d_fused, r, scale, shift, sums, G)
+    ops.conv_gemm(mode, 0, A, Bd, d_plain)
+    ops.device_status()
+    res = {"per_cta": per_cta, "same_gradient": bool(torch.equal(d_fused, d_plain)),
+           "finite": bool(torch.isfinite(sums).all().item())}
+    dy = d_fused.float().view(G, n // G, H, W, cin)
+    rr = r.float().view(G, n // G, H, W, cin)
+    m = (torch.addcmul(shift.view(G, 1, 1, 1, cin), rr, scale.view(G, 1, 1, 1, cin)) > 0).float()
+    s1 = (dy * m).sum((1, 2, 3))
+    s2 = (dy * m * rr).sum((1, 2, 3))
+    res["s1_rel"] = ((sums[..., 0].sum(1) - s1).norm() / s1.norm()).item()
+    res["s2_rel"] = ((sums[..., 1].sum(1) - s2).norm() / s2.norm()).item()
+    # bn_bwd from the fused sums vs the two-pass bn_bwd
+    srcs = ops.make_srcs([{"kind": 1, "t": d_fused}])
+    ws = torch.empty(ops.bn_bwd_ws_floats(n, H, W, cin, G), device=DEV)
+    out = {}
+    for tag, kw in (("two_pass", {}), ("from_sums", {"sums": sums, "sum_rows": rows})):
+        dg, db = torch.empty(cin, device=DEV), torch.empty(cin, device=DEV)
+        dr = torch.empty(n, H, W, cin, device=DEV, dtype=torch.bfloat16)
+        ops.bn_bwd(r, mean, invstd, scale, shift, srcs, G, ws, dg, db, dr, **kw)
+        out[tag] = (dg, db, dr.float())
+    torch.cuda.synchronize()
+    res["dgamma_rel"] = ((out["from_sums"][0] - out["two_pass"][0]).norm() / out["two_pass"][0].norm()).item()
+    res["dbeta_rel"] = ((out["from_sums"][1] - out["two_pass"][1]).norm() / out["two_pass"][1].norm()).item()
+    res["dr_rel"] = ((out["from_sums"][2] - out["two_pass"][2]).norm() / out["two_pass"][2].norm()).item()
+    res["ok"] = (res["per_cta"] and res["same_gradient"] and res["finite"] and res["s1_rel"] < 1e-5 and res["s2_rel"] < 1e-5
+                 and res["dgamma_rel"] < 1e-5 and res["dbeta_rel"] < 1e-5 and res["dr_rel"] < 2e-3)
+    return res
+
+
 def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3, pair=None) -> dict:
     """ConvTranspose2d(c, c, 2, stride=2) forward, scattered into the second half of a 2c concat buffer."""
     g = _gen(seed)
@@ -738,6 +793,13 @@ ALL_CHECKS = {
     "conv3x3_cta_stats_G1_many": lambda: check_conv3x3_cta_stats(16, 64, 64, 64, 64, G=1, seed=49),
     "conv3x3_cta_stats_G2_512": lambda: check_conv3x3_cta_stats(4, 16, 16, 256, 512, G=2, seed=50),
     "conv3x3_cta_stats_odd_tiles": lambda: check_conv3x3_cta_stats(6, 8, 8, 128, 64, G=2, seed=51),
+    "dgrad_bnbwd_G2": check_dgrad_bnbwd,
+    "dgrad_bnbwd_G1_many": lambda: check_dgrad_bnbwd(16, 64, 64, 64, 64, G=1, seed=67),
+    "dgrad_bnbwd_256_512": lambda: check_dgrad_bnbwd(4, 16, 16, 256, 512, G=1, seed=68),
+    "dgrad_bnbwd_odd_tiles_8x8": lambda: check_dgrad_bnbwd(6, 8, 8, 128, 64, G=2, seed=69),
+    "dgrad_bnbwd_ragged_24x40": lambda: check_dgrad_bnbwd(2, 24, 40, 64, 64, G=1, seed=70),
+    "convt_dgrad_bnbwd": lambda: check_dgrad_bnbwd(4, 16, 16, 128, 128, G=1, seed=71, mode=2),
+    "convt_dgrad_bnbwd_64_many": lambda: check_dgrad_bnbwd(8, 64, 64, 64, 64, G=1, seed=72, mode=2),
     "conv3x3_dgrad": check_conv3x3_dgrad,
     "conv3x3_dgrad_ragged_8x8": lambda: check_conv3x3_dgrad(3, 8, 8, 128, 128, seed=42),
     "conv3x3_dgrad_512_256": lambda: check_conv3x3_dgrad(2, 32, 32, 512, 256, seed=41),
