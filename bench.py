@@ -374,7 +374,7 @@ def main() -> None:
     fam = profile_step(ts)
     gpu_launches = fam.pop("_launches_per_step") * K   # our own kernels inside the timed region (graph-replayed)
     total_ms = sum(d["ms"] for d in fam.values())
-    tensor_fams = ("fprop3x3", "wgrad", "gemm1tap", "convT_dgrad")
+    tensor_fams = ("fprop3x3", "dgrad3x3_bnbwd", "wgrad", "gemm1tap", "convT_dgrad", "convT_dgrad_bnbwd")
     dom = max(fam, key=lambda k: fam[k]["ms"])
     d = fam[dom]
     if dom in tensor_fams:

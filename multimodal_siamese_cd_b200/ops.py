@@ -251,7 +251,8 @@ def conv_gemm_bnbwd(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Ten
     assert sums.dtype == torch.float32 and scale.shape[-1] == N
     flags = 4 | 8 | (stat_groups << 8)
     _count(1)
-    fam = "fprop3x3" if mode == 0 else "convT_dgrad"
+    # own profile families: these launches also do the BatchNorm-backward reduce pass of the gradient they store
+    fam = "dgrad3x3_bnbwd" if mode == 0 else "convT_dgrad_bnbwd"
     with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw, r), f"{n}x{H}x{W} k{ka}->n{N} bnbwd"):
         _lib.check(_lib.load().b200cd_conv_gemm_bnbwd(mode, flags, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N,
                                                       out.data_ptr(), o_ld, r.data_ptr(), r_ld, scale.data_ptr(),
