@@ -151,8 +151,8 @@ def run_reference_arm(args, out) -> None:
     if rank != 0:
         return
     mtype, cin, B, kind, alpha, gf, yaml = CONFIGS[args.config]
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    r = cpu_step_rate(args.config, sample_pairs=2, steps=steps, warmup=warm)
+    steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
+    r = cpu_step_rate(args.config, sample_pairs=8, steps=steps, warmup=warm)   # bounded sample: 8 pairs per step
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -399,7 +399,8 @@ def main() -> None:
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_step_rate(args.config, sample_pairs=2, steps=3, warmup=1)
+        # bounded sample of the same workload: 8 pairs per step, 1 warm-up + 4 timed steps (~10-15 s of host work)
+        r = cpu_step_rate(args.config, sample_pairs=8, steps=4, warmup=1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     value = B * world / ms * 1e3
