@@ -218,6 +218,11 @@ int b200cd_head_fwd(const void* a0, int64_t ld0, const void* a1, int64_t ld1, in
  * OutConv weight/bias gradients and the ConvTranspose2d bias gradient. ws: fp32 [nblk*C]. */
 int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
                   void* stream);
+/* out[j] = sum over rows of stats[row][c_off + j][0] for j < C, where stats is the fp32 [rows][ld][2] per-CTA
+ * statistics buffer of one stat-group written by b200cd_conv_gemm (flags bit 3): the nn.ConvTranspose2d bias gradient
+ * (utils/networks.py:433) is the pixel sum of the upper half of the concat-buffer gradient, which the input-gradient
+ * convolution of the following DoubleConv has just stored. */
+int b200cd_stat_rowsum(const float* stats, int rows, int ld, int c_off, int C, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * power_jaccard_loss, utils/loss_functions.py:141-150. sums = (sum p*t, sum p^2, sum t^2) in fp64 over the

@@ -546,6 +546,13 @@ int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t np
   return 0;
 }
 
+int b200cd_stat_rowsum(const float* stats, int rows, int ld, int c_off, int C, float* out, void* stream) {
+  if (stats == nullptr || rows < 1 || C < 1 || c_off < 0 || c_off + C > ld) return fail(B200CD_ERR_SHAPE, "stat_rowsum: bad arguments");
+  CUDA_TRY(b200cd::launch_stat_rowsum(reinterpret_cast<const float2*>(stats), rows, ld, c_off, C, out,
+                                      reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200cd_pj_fwd(const float* z, const float* t, int t_is_logit, const unsigned char* rowmask, int sel, int rows,
                   int64_t per_row, int nblk, double* ws, double* sums, void* stream) {
   if (rows < 1 || per_row < 4 || per_row % 4 != 0 || nblk < 1)

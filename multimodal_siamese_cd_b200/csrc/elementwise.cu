@@ -1341,6 +1341,30 @@ __global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __re
   }
 }
 
+// Column sums from the per-CTA statistics rows a convolution already produced: out[j] = sum_r stats[r][c_off + j].x
+// (the transposed-conv bias gradient is the pixel sum of the upper half of the concat-buffer gradient, which the
+// preceding input-gradient convolution wrote together with its per-channel sums). block = 8 channels x 32 lanes.
+__global__ void __launch_bounds__(256) stat_rowsum_kernel(const float2* __restrict__ stats, int rows, int ld, int c_off,
+                                                          int C, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;  // whole warp
+  double s = 0.0, s1 = 0.0;
+  const float2* base = stats + c_off + c;
+  int r = lane;
+  for (; r + 32 < rows; r += 64) {
+    s += __ldg(base + static_cast<long long>(r) * ld).x;
+    s1 += __ldg(base + static_cast<long long>(r + 32) * ld).x;
+  }
+  if (r < rows) s += __ldg(base + static_cast<long long>(r) * ld).x;
+  s += s1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[c] = static_cast<float>(s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Split reduction of the weight-gradient workspace into the reference parameter layouts.
 //   layout 0: ws[s][tap][d0][d1]          -> grad[d0][d1][tap]   (conv3x3: [co][ci][3][3]; convT: [ci][co][2][2])
@@ -1988,6 +2012,11 @@ cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, 
   size_t smem = 256 * sizeof(float);
   if (x != nullptr) smem = static_cast<size_t>(256 / (C / 8)) * C * sizeof(float);
   launch_k(colsum_kernel, dim3(nblk), dim3(256), smem, st, reinterpret_cast<const __nv_bfloat16*>(x), ld, C, wgt, npix, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stat_rowsum(const float2* stats, int rows, int ld, int c_off, int C, float* out, cudaStream_t st) {
+  launch_k(stat_rowsum_kernel, dim3((C + 7) / 8), dim3(256), 0, st, stats, rows, ld, c_off, C, out);
   return cudaGetLastError();
 }
 

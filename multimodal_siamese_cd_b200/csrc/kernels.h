@@ -140,6 +140,7 @@ cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long 
                             const float* b, long long npix, float* logits, cudaStream_t st);
 cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,
                           float* partial, cudaStream_t st);
+cudaError_t launch_stat_rowsum(const float2* stats, int rows, int ld, int c_off, int C, float* out, cudaStream_t st);
 cudaError_t launch_colsum_finalize(const float* partial, int nblk, int C, float* out, cudaStream_t st);
 cudaError_t launch_wgrad_reduce(const float* ws, int splits, long long split_stride, int layout, int d0, int d1,
                                 int taps, float* grad, cudaStream_t st);

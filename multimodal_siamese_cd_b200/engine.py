@@ -30,6 +30,8 @@ WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
 # BatchNorm backward of stages with a single direct gradient source: accumulate its reduce pass in the epilogue of the
 # input-gradient convolution that produces that gradient (ops.conv_gemm_bnbwd)
 FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != "0"
+# transposed-conv bias gradient from the per-CTA channel sums of the dgrad launch that writes the concat-buffer gradient
+UP_BIAS_FROM_STATS = __import__("os").environ.get("B200CD_UP_BIAS_FROM_STATS", "1") != "0"
 FUSE_BN_BWD_MIN_PIXELS = int(__import__("os").environ.get("B200CD_FUSE_BN_BWD_MIN_PIXELS", 32768))
 # 64-wide weight-gradient tiles: one CTA may own two kx columns (gemm_wgrad.cu, NKX = 2). Measured slower than one kx
 # per CTA once tap pairs are issued as N = 128 MMAs (the kernel is bound by MN-major operand reads from shared memory,
@@ -91,6 +93,7 @@ class UpConv:
     d_x: Optional[torch.Tensor] = None     # [nb, h, w, c]
     Wf: torch.Tensor = None
     Wd: Optional[torch.Tensor] = None
+    bias_rows: int = 0       # > 0: the dgrad that writes d_cat also wrote per-CTA channel sums (bias gradient for free)
 
 
 @dataclass
@@ -428,6 +431,7 @@ class StepEngine:
                 self._reduce_tables.append(ops.make_reduce_jobs(jobs, self.device))
             self.ws_bnbwd = self._new(max(n["bnbwd"], 4), dtype=torch.float32)
             self.ws_colsum = self._new(max(n["colsum"], 4), dtype=torch.float32)
+            self.ws_upstats = self._new(max(n.get("upstats", 0), 4), dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------------------
     # forward emission: stages were created in execution order, transposed convs are interleaved by name order
@@ -555,6 +559,13 @@ class StepEngine:
         # the stage whose output feeds this conv: if this conv's input gradient is its ONLY gradient source, the reduce
         # pass of its BatchNorm backward runs in this dgrad's epilogue (ops.conv_gemm_bnbwd)
         prod = eng._fusable_producer(st.d_in, 0, st.cout) if st.d_in is not None else None
+        up_rows = 0
+        uc_of = {id(s1): uc for (uc, s1, s2) in eng._up_plan}.get(id(st))
+        if uc_of is not None and prod is None and eng.device.type == "cuda" and ops.FPROP_PAIR and UP_BIAS_FROM_STATS:
+            rows, per_cta = ops.conv_stat_rows(st.n_img, st.H, st.W, st.cout, st.cin, 1)
+            if per_cta:
+                up_rows = uc_of.bias_rows = rows
+                eng._ws_need["upstats"] = max(eng._ws_need.get("upstats", 0), rows * st.cin * 2)
 
         def run():
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
@@ -571,6 +582,10 @@ class StepEngine:
                 if st.d_in is not None:
                     if prod is not None:
                         ops.conv_gemm_bnbwd(0, st.dr, st.Wd, st.d_in, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
+                    elif up_rows:
+                        # d_in is the concat-buffer gradient of an Up: its per-channel pixel sums (upper half = the
+                        # transposed-conv bias gradient) come out of this launch's per-CTA statistics
+                        ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats, stat_groups=1)
                     else:
                         ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
@@ -597,7 +612,10 @@ class StepEngine:
 
         def run():
             ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
-            ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
+            if uc.bias_rows:
+                ops.stat_rowsum(eng.ws_upstats, uc.bias_rows, 2 * c, c, c, gb)
+            else:
+                ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
             if prod is not None:
                 ops.conv_gemm_bnbwd(2, uc.d_out, uc.Wd, uc.d_x, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
             else:

@@ -430,6 +430,15 @@ def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nb
                                              _stream()))
 
 
+def stat_rowsum(stats: torch.Tensor, rows: int, ld: int, c_off: int, Cc: int, out: torch.Tensor) -> None:
+    """out[j] = sum over the per-CTA statistics rows of channel c_off + j (transposed-conv bias gradient)."""
+    _require_cuda(stats, out)
+    assert stats.dtype == torch.float32 and out.dtype == torch.float32 and out.numel() == Cc
+    _count(1)
+    with _Prof("colsum", 0.0, 8.0 * rows * Cc):
+        _lib.check(_lib.load().b200cd_stat_rowsum(stats.data_ptr(), rows, ld, c_off, Cc, out.data_ptr(), _stream()))
+
+
 def pj_fwd(z: torch.Tensor, t: torch.Tensor, t_is_logit: bool, rowmask: Optional[torch.Tensor], sel: int, nblk: int,
            ws: torch.Tensor, sums: torch.Tensor) -> None:
     _require_cuda(z, t, ws, sums)
