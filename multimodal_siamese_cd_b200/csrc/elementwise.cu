@@ -98,6 +98,69 @@ __global__ void __launch_bounds__(128) pack_input_kernel(const float* __restrict
   }
 }
 
+// The same with the channel count known at compile time: a thread builds the im2col row of its pixel in registers
+// (k = tap * CIN + ci is a compile-time index), writes it to shared memory as 16-byte chunks (row pitch kpad*2 + 16
+// bytes: conflict-free) and the block copies the 128 rows out with coalesced 16-byte stores.
+template <int CIN>
+__global__ void __launch_bounds__(128) pack_input_t_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                           int csrc, int c_lo, int nc, int cat_mode, int B, int H, int W,
+                                                           __nv_bfloat16* __restrict__ out, long long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int KPAD = 64 * ((9 * CIN + 63) / 64);
+  constexpr int CH = KPAD / 8;        // 16-byte chunks per row
+  constexpr int PITCH = CH + 1;       // in 16-byte units
+  extern __shared__ uint4 smv[];
+  const int t = threadIdx.x;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * 128;
+  const long long pix = pix0 + t;
+  float v[KPAD];
+#pragma unroll
+  for (int k = 0; k < KPAD; ++k) v[k] = 0.f;
+  if (pix < npix) {
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* src;
+      int b, c;
+      if (cat_mode == 0) {
+        src = n < B ? src0 : src1;
+        b = n < B ? n : n - B;
+        c = c_lo + ci;
+      } else {
+        src = ci < nc ? src0 : src1;
+        b = n;
+        c = c_lo + (ci < nc ? ci : ci - nc);
+      }
+      const float* plane = src + (static_cast<long long>(b) * csrc + c) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = x + kx - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[(ky * 3 + kx) * CIN + ci] = __ldg(plane + static_cast<long long>(yy) * W + xx);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = v[ch * 8 + j];
+    smv[t * PITCH + ch] = pack8(f);
+  }
+  __syncthreads();
+  uint4* o = reinterpret_cast<uint4*>(out) + pix0 * CH;
+  const long long nvalid = (npix - pix0 < 128 ? npix - pix0 : 128) * CH;
+  for (int i = t; i < 128 * CH; i += 128) {
+    if (i < nvalid) o[i] = smv[(i / CH) * PITCH + (i % CH)];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight packing fp32 (reference layouts) -> bf16 GEMM operands.
 //   mode 0: conv3x3 forward   w[d0=co][d1=ci][3][3] -> out[co][tap][ci]
@@ -1824,9 +1887,28 @@ cudaError_t launch_pack_input(const float* src0, const float* src1, int csrc, in
   const int n_img = cat_mode ? B : 2 * B;
   const long long npix = static_cast<long long>(n_img) * H * W;
   const int grid = static_cast<int>((npix + 127) / 128);
+  const int cin = cat_mode ? 2 * nc : nc;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (kpad == 64 * ((9 * cin + 63) / 64)) {
+    const size_t sm = 128 * static_cast<size_t>(kpad / 8 + 1) * 16;
+#define B200CD_PACK(CIN)                                                                                              \
+  case CIN:                                                                                                          \
+    launch_k(pack_input_t_kernel<CIN>, dim3(grid), dim3(128), sm, st, src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, o, \
+             npix);                                                                                                  \
+    return cudaGetLastError();
+    switch (cin) {
+      B200CD_PACK(2)
+      B200CD_PACK(3)
+      B200CD_PACK(4)
+      B200CD_PACK(6)
+      B200CD_PACK(8)
+      B200CD_PACK(12)
+      default: break;
+    }
+#undef B200CD_PACK
+  }
   const size_t smem = 128 * (kpad / 2 + 1) * 4;
-  launch_k(pack_input_kernel, dim3(grid), dim3(128), smem, st, src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad,
-           reinterpret_cast<__nv_bfloat16*>(out), npix);
+  launch_k(pack_input_kernel, dim3(grid), dim3(128), smem, st, src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad, o, npix);
   return cudaGetLastError();
 }
 
