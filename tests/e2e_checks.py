@@ -165,3 +165,49 @@ def run_eval_case(mtype: str, cin: int, topo, B: int, H: int, W: int, warm_steps
         torch.allclose(sd_after[k], v, atol=2e-3) for k, v in sd.items() if k.endswith(("running_mean", "running_var")))
     net.module.release_engines()
     return res
+
+
+def run_training_loop(mtype: str = "siameseunet", cin: int = 4, topo=(64, 128), B: int = 4, H: int = 32, W: int = 32,
+                      steps: int = 6, lr: float = 1e-3, optimizer: str = "torch", kind: str = "supervised") -> dict:
+    """The body of the reference's training loop (train_supervised.py:63-79) for several optimizer steps: drop-in
+    modules + AdamW on the GPU against the oracle + torch.optim.AdamW on the CPU, different batch every step. Loss
+    trajectories must track each other: parameters, BatchNorm running statistics and optimizer state all evolve."""
+    dev = torch.device("cuda", 0)
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg)
+    sd = O.clone_state(net.state_dict())
+    net.to(dev).train()
+    if optimizer == "fused":
+        from multimodal_siamese_cd_b200.optim import FusedAdamW
+        opt = FusedAdamW(net.parameters(), lr=lr, weight_decay=0.01)
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=lr, weight_decay=0.01)
+    ref_params = [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
+    ref_names = [k for k, v in sd.items() if v.is_floating_point() and v.requires_grad]
+    ref_opt = torch.optim.AdamW(ref_params, lr=lr, weight_decay=0.01)
+    crit = loss_functions.get_criterion("PowerJaccardLoss")
+    xc = 6 if mtype in TWO_STREAM else cin
+    got, ref = [], []
+    for it in range(steps):
+        batch = O.synthetic_batch(B, xc, H, W, seed=100 + it)
+        opt.zero_grad()
+        loss = crit(net(batch["x_t1"].to(dev), batch["x_t2"].to(dev)), batch["y_change"].to(dev))
+        loss.backward()
+        opt.step()
+        got.append(loss.item())
+        r = O.train_step(mtype, sd, batch, kind=kind, q=True)
+        for n, p in zip(ref_names, ref_params):
+            p.grad = r["grads"][n]
+        ref_opt.step()
+        ref_opt.zero_grad()
+        ref.append(r["loss"].item())
+    torch.cuda.synchronize()
+    sd_after = {k[len("module."):]: v.detach().cpu() for k, v in net.state_dict().items()}
+    # weights only: Adam turns every gradient into a step of ~lr regardless of its magnitude, so parameters that start
+    # at zero (BatchNorm / conv biases) follow the sign of noise-level gradients and are not comparable element-wise
+    prm = max(((sd_after[n] - p.detach()).norm() / p.detach().norm().clamp_min(1e-12)).item()
+              for n, p in zip(ref_names, ref_params) if p.dim() >= 2)
+    net.module.release_engines()
+    return {"loss_cuda": got, "loss_ref": ref, "max_loss_diff": max(abs(a - b) for a, b in zip(got, ref)),
+            "loss_moved": abs(ref[0] - ref[-1]), "max_param_rel": prm}
