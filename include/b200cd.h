@@ -262,6 +262,16 @@ int64_t b200cd_reduce_job_blocks(int splits, int d0, int d1, int taps);
 int b200cd_wgrad_reduce_batched(const b200cd_reduce_job* jobs_dev, int njobs, int64_t total_blocks, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Thresholded confusion counts — MultiThresholdMetric.add_sample, utils/metrics.py:23-31, as used by
+ * utils/evaluation.py:23 — in one pass over the prediction and the label: for each of nthr (<= 8) thresholds
+ * pred = round(p - thr + 0.5) != 0, where p = pred[i] (from_logits = 0) or sigmoid(pred[i]) (from_logits = 1), and
+ * counts[t][0..3] += (TP, TN, FP, FN) in the REFERENCE's naming (its FP counts y_true & ~pred, its FN ~y_true & pred).
+ * counts is uint64 [nthr][4] on the device and is ACCUMULATED into (zero it before the first sample).
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_confusion_counts(const float* pred, const float* truth, int64_t n, int from_logits, const float* thresholds,
+                            int nthr, uint64_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * AdamW step over every parameter tensor in ONE launch — optim.AdamW(net.parameters(), lr=cfg.TRAINER.LR,
  * weight_decay=0.01) train_supervised.py:32 (decoupled weight decay, betas (0.9, 0.999), eps 1e-8, no amsgrad).
  * `jobs_dev` is a DEVICE array; job j owns thread blocks [start_j, start_j + ceil(n_j / 1024)). Parameters without a

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200cd_reduce_job_parts": (_i, [_i, _i, _i]),
     "b200cd_reduce_job_blocks": (_i64, [_i, _i, _i, _i]),
     "b200cd_wgrad_reduce_batched": (_i, [_vp, _i, _i64, _vp]),
+    "b200cd_confusion_counts": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "b200cd_adamw_step": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _vp]),
     "b200cd_pj_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp, _vp, _f, _i, _vp, _vp, _vp]),
 }

@@ -579,6 +579,15 @@ int b200cd_pj_bwd(const float* z, const float* t, int t_is_logit, const unsigned
   return 0;
 }
 
+int b200cd_confusion_counts(const float* pred, const float* truth, int64_t n, int from_logits, const float* thresholds,
+                            int nthr, uint64_t* counts, void* stream) {
+  if (pred == nullptr || truth == nullptr || thresholds == nullptr || counts == nullptr || n < 1 || nthr < 1 || nthr > 8)
+    return fail(B200CD_ERR_SHAPE, "confusion_counts: 1..8 thresholds and a non-empty input are required");
+  CUDA_TRY(b200cd::launch_confusion(pred, truth, n, from_logits, thresholds, nthr,
+                                    reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200cd_reduce_job_parts(int splits, int d1, int taps) {
   return (splits < 1 || d1 < 4 || taps < 1) ? -1 : b200cd::reduce_job_parts(splits, d1, taps);
 }

@@ -1873,6 +1873,58 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamWJob* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Thresholded confusion counts of utils/metrics.py:23-31 (MultiThresholdMetric.add_sample) in one pass:
+// pred = round(p - thr + 0.5) != 0 with p the probability (or sigmoid(logit) when from_logits), counted against
+// y_true != 0 for up to 8 thresholds. counts[t] = (TP, TN, FP, FN) with the REFERENCE's naming: its "FP" is
+// y_true & ~pred and its "FN" is ~y_true & pred (utils/metrics.py:29-30).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict__ pred, const float* __restrict__ truth,
+                                                        long long n, int from_logits, const float* __restrict__ thr,
+                                                        int nthr, unsigned long long* __restrict__ counts) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ unsigned int sh[8][4];
+  if (threadIdx.x < 32) sh[threadIdx.x >> 2][threadIdx.x & 3] = 0u;
+  __syncthreads();
+  float th[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) th[t] = t < nthr ? __ldg(thr + t) : 0.f;
+  unsigned int c[8][4];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) c[t][0] = c[t][1] = c[t][2] = c[t][3] = 0u;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float pv = __ldg(pred + i);
+    if (from_logits) pv = 1.f / (1.f + expf(-pv));
+    const bool yt = __ldg(truth + i) != 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < nthr) {
+        const bool pd = rintf(pv - th[t] + 0.5f) != 0.f;
+        c[t][0] += (yt && pd);
+        c[t][1] += (!yt && !pd);
+        c[t][2] += (yt && !pd);
+        c[t][3] += (!yt && pd);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (t < nthr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned int v = c[t][k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sh[t][k], v);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * nthr) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x >> 2][threadIdx.x & 3]));
+}
+
 inline int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -2168,6 +2220,12 @@ long long reduce_job_blocks(int splits, int d0, int d1, int taps) {
 
 cudaError_t launch_wgrad_reduce_batched(const ReduceJob* jobs, int njobs, long long total_blocks, cudaStream_t st) {
   launch_k(wgrad_reduce_batched_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, st, jobs, njobs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_confusion(const float* pred, const float* truth, long long n, int from_logits, const float* thr, int nthr,
+                             unsigned long long* counts, cudaStream_t st) {
+  launch_k(confusion_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, pred, truth, n, from_logits, thr, nthr, counts);
   return cudaGetLastError();
 }
 

@@ -152,6 +152,9 @@ cudaError_t launch_pj_bwd(const float* z, const float* t, int t_is_logit, const 
                           int rows, long long per_row, const double* sums, const float* gptr, float gmul,
                           int accumulate, float* dz, float* dt, cudaStream_t st);
 
+cudaError_t launch_confusion(const float* pred, const float* truth, long long n, int from_logits, const float* thr, int nthr,
+                             unsigned long long* counts, cudaStream_t st);
+
 struct ReduceJob {      // layout == b200cd_reduce_job (include/b200cd.h)
   const float* ws;
   float* grad;

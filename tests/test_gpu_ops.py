@@ -84,3 +84,55 @@ def test_fused_adamw_matches_torch():
     cpu_p.grad = torch.ones(3)
     with pytest.raises(Exception, match="CUDA parameters only"):
         FusedAdamW([cpu_p], lr=1e-3).step()
+
+
+def _metric_ref(y_true, y_pred, thr):
+    """utils/metrics.py:23-31 restated with plain torch ops (reference naming of FP / FN included)."""
+    yt = y_true.bool()[None, ...]
+    off = (y_pred[None, ...] - thr[:, None, None, None, None] + 0.5).round().bool()
+    dims = (-1, -2, -3, -4)
+    return torch.stack([(yt & off).sum(dims), (~yt & ~off).sum(dims), (yt & ~off).sum(dims), (~yt & off).sum(dims)], 1)
+
+
+def test_confusion_counts_match_reference_metric():
+    """metrics.MultiThresholdMetric (one kernel) against the restated reference metric on random data with several
+    thresholds and exact ties, and against the TP / F1 the UNMODIFIED reference produced for the golden fixtures."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pathlib import Path
+
+    from multimodal_siamese_cd_b200.metrics import MultiThresholdMetric
+    from oracle import unet_oracle as O
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    thr = torch.tensor([0.5, 0.25, 0.75, 0.9], device=dev)
+    m = MultiThresholdMetric(thr)
+    want = torch.zeros(4, 4, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        p = torch.rand(3, 1, 64, 48, device=dev, generator=g)
+        p.view(-1)[::7] = 0.5                      # exact ties: round-half-to-even makes them negative at thr 0.5
+        p.view(-1)[::11] = 0.75
+        y = (torch.rand(3, 1, 64, 48, device=dev, generator=g) > 0.7).float()
+        m.add_sample(y, p)
+        want += _metric_ref(y, p, thr)
+    assert torch.equal(m._counts, want)
+    assert torch.equal(torch.stack([m.TP, m.TN, m.FP, m.FN], 1), want.float())
+    # logits path == sigmoid + probability path
+    z = torch.randn(2, 1, 32, 32, device=dev, generator=g) * 3
+    y = (torch.rand(2, 1, 32, 32, device=dev, generator=g) > 0.5).float()
+    a, b = MultiThresholdMetric(thr[:1]), MultiThresholdMetric(thr[:1])
+    a.add_logits(y, z)
+    b.add_sample(y, torch.sigmoid(z))
+    assert torch.equal(a._counts, b._counts)
+    # golden fixtures: TP and F1 computed by the reference's own utils/metrics.py on the reference's logits
+    for f in sorted((Path(__file__).parent / "golden").glob("*.pt")):
+        fix = torch.load(f, map_location="cpu", weights_only=False)   # our own fixtures (tuples, dicts, tensors)
+        name, mtype, cin, topo, B, kind, H, W, alpha = fix["case"]
+        xc = 6 if mtype in ("dualstreamunet", "whatevernet", "whatevernet2") else cin
+        batch = O.synthetic_batch(B, xc, H, W, seed=7)
+        mm = MultiThresholdMetric(torch.tensor([0.5], device=dev))
+        mm.add_logits(batch["y_change"].to(dev), fix["outs"][0].to(dev))
+        assert float(mm.TP.item()) == fix["mask_f1"]["tp"], name
+        assert abs(float(mm.compute_f1().item()) - fix["mask_f1"]["f1"]) < 1e-6, name
+    with pytest.raises(RuntimeError):
+        MultiThresholdMetric(torch.tensor([0.5]))
