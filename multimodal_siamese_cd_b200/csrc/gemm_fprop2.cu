@@ -25,7 +25,8 @@ namespace b200cd {
 
 namespace {
 
-constexpr int kThreads = 320;  // producer warp, MMA warp, two epilogue warpgroups
+constexpr int kThreads = 352;  // A producer warp, MMA warp, two epilogue warpgroups, B producer warp
+constexpr int kBProducerWarp = 10;
 constexpr int kABox = 160 * 128;  // tw x (th + 2) <= 160 pixels x 64 bf16 (16 x 10 or 8 x 18 boxes)
 constexpr int kStageSlab = 128 * 128;  // one 64-channel slab of the output tile
 
@@ -56,6 +57,14 @@ struct PairCfg {
   static constexpr int kTmemCols = 2 * BN;
   static_assert(kTotal + 16 <= 232448, "shared memory budget");
 };
+
+static int pair_threads() {
+  static const int t = [] {
+    const char* e = getenv("B200CD_PAIR_SPLIT");
+    return (e && e[0] == '0') ? 320 : kThreads;
+  }();
+  return t;
+}
 
 template <int BN, bool RESIDENT, int NKY>
 __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -125,8 +134,11 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above is independent of the predecessor kernel's output
 
-  if (warp == 0) {
-    // ---------------- TMA producer (one warp per CTA, one elected lane issues; full barriers live in the leader) ------
+  if (warp == 0 || warp == kBProducerWarp) {
+    // ---------------- TMA producers (warp 0: pixel boxes, warp 10: weight tiles; the two rings are independent, and
+    // two issuing threads keep more loads in flight than one; full barriers live in the leader) ------
+    const bool split = blockDim.x > 320;  // B200CD_PAIR_SPLIT=0 launches without warp 10: warp 0 feeds both rings
+    const bool do_a = warp == 0, do_b = split ? !do_a : do_a;
     uint32_t sa = 0, pa = 1, sb = 0, pb = 1;  // ring slot and the parity to wait for on its empty barrier
     bool first = true;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -139,20 +151,22 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const int nrow = nb * BN + static_cast<int>(rank) * (BN / 2);
       int kx = 0, kc = 0;  // same K order as fprop_kernel<., ., HALO>: kx outer, 64-channel chunk inner
       for (int st = 0; st < steps; ++st) {
-        mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
-        if (elect_one_sync()) {
-          if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
-          if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
-          else if (p.mode == 1) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
-          else  // mode 2: tap kx = (dy, dx) of the 2x2 / stride-2 gather from the full-resolution tensor
-            tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, kx & 1, x0, kx >> 1, img * p.H + y0);
+        if (do_a) {
+          mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
+          if (elect_one_sync()) {
+            if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
+            if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
+            else if (p.mode == 1) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
+            else  // mode 2: tap kx = (dy, dx) of the 2x2 / stride-2 gather from the full-resolution tensor
+              tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, kx & 1, x0, kx >> 1, img * p.H + y0);
+          }
+          __syncwarp();
+          if (++sa == L::kSA) {
+            sa = 0;
+            pa ^= 1;
+          }
         }
-        __syncwarp();
-        if (++sa == L::kSA) {
-          sa = 0;
-          pa ^= 1;
-        }
-        if (!resident || first) {
+        if (do_b && (!resident || first)) {
           if (L::kG == 3) {
             if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
             if (elect_one_sync()) {
@@ -523,7 +537,7 @@ cudaError_t pair_max_clusters(int* out) {
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(sms & ~1);
-    qc.blockDim = dim3(kThreads);
+    qc.blockDim = dim3(pair_threads());
     qc.dynamicSmemBytes = L::kDynamic;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
@@ -562,7 +576,7 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   if (p.stats != nullptr && p.stat_groups > 0 && p.stat_rows != 4 * clusters) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(pair_threads());
   cfg.dynamicSmemBytes = L::kDynamic;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
