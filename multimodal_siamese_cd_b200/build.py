@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-cudart", "static",
+    *os.environ.get("B200CD_NVCC_EXTRA", "").split(),  # e.g. -DB200CD_TRACE for tools/trace_pair.py
 ]
 
 

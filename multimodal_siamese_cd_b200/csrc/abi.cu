@@ -333,7 +333,16 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
     const uint64_t dims[2] = {ktot, (uint64_t)N};
     const uint64_t strides[1] = {ktot * 2};
     const uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};  // pair: each CTA loads half of the weight tile
-    if ((rc = make_map(&mapB, Bw, 2, dims, strides, box))) return rc;
+    if (pair && b200cd::fprop_pair_stacked_weights(mode, bn)) {
+      // K index = (ky * 3 + kx) * ka + k: the three ky tiles of one kx as a single box, stacked tile after tile
+      const uint64_t dims4[4] = {(uint64_t)ka, (uint64_t)N, 3, 3};
+      const uint64_t strides4[3] = {ktot * 2, 3 * (uint64_t)ka * 2, (uint64_t)ka * 2};
+      const uint32_t box4[4] = {64, (uint32_t)(bn / 2), 3, 1};
+      rc = make_map(&mapB, Bw, 4, dims4, strides4, box4);
+    } else {
+      rc = make_map(&mapB, Bw, 2, dims, strides, box);
+    }
+    if (rc) return rc;
   }
   if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout, W, H, n_img, tw, th);
   else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);

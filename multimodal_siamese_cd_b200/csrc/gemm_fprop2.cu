@@ -35,13 +35,15 @@ constexpr int kStageSlab = 128 * 128;  // one 64-channel slab of the output tile
 template <int BN, int NKY = 3>
 struct PairCfg {
   static constexpr int kBTile = (BN / 2) * 128;  // this CTA's half of a weight tile: BN/2 rows x 64 bf16
-  // weight tiles per B-ring slot (= per barrier): with 64-wide tiles an MMA lasts 32 cycles, so the three ky tiles of a
-  // step travel together and the issuer handles one barrier per 12 MMAs
-  static constexpr int kG = (BN == 64 && NKY == 3) ? 3 : 1;
+  // weight tiles per B-ring slot (= per barrier and per TMA instruction): up to 128-wide tiles the three ky tiles of a
+  // step travel together as ONE rank-4 box [ky][n][64 k] (a thread can start a bulk-tensor load only every ~230 cycles
+  // — tools/ubench/tma_rate.cu — and three 8 KB loads per step left the weight ring starved), and the issuer handles
+  // one barrier per 12 MMAs
+  static constexpr int kG = (BN <= 128 && NKY == 3) ? 3 : 1;
   static constexpr int kBSlot = kG * kBTile;
   static constexpr int kStg = BN == 64 ? 1 : 2;                   // staging slabs per epilogue group
   static constexpr int kSA = BN == 64 ? 5 : 3;
-  static constexpr int kSB = BN == 256 ? 6 : (BN == 128 ? 12 : 6);
+  static constexpr int kSB = BN == 256 ? 6 : (BN == 128 ? (kG == 3 ? 4 : 12) : 6);  // slots of kG tiles
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kSA * kABox;
   static constexpr int kStgOff = kBOff + kSB * kBSlot;           // two staging slabs (ping-pong) per epilogue group
@@ -57,6 +59,22 @@ struct PairCfg {
   static constexpr int kTmemCols = 2 * BN;
   static_assert(kTotal + 16 <= 232448, "shared memory budget");
 };
+
+#ifdef B200CD_TRACE
+// debug build only (B200CD_NVCC_EXTRA=-DB200CD_TRACE): clock64 stamps of CTA 0's warps, read by tools/trace_pair.py
+__device__ long long g_trace[6][4096];
+#define TRACE_DECL(role)                                            \
+  int tr_i = 0;                                                     \
+  const bool tr_on = blockIdx.x == 0 && (threadIdx.x & 31) == 0;    \
+  const int tr_role = (role);
+#define TR()                                                                    \
+  do {                                                                          \
+    if (tr_on && tr_i < 4096) g_trace[tr_role][tr_i++] = clock64();             \
+  } while (0)
+#else
+#define TRACE_DECL(role)
+#define TR()
+#endif
 
 static int pair_threads() {
   static const int t = [] {
@@ -141,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
     const bool do_a = warp == 0, do_b = split ? !do_a : do_a;
     uint32_t sa = 0, pa = 1, sb = 0, pb = 1;  // ring slot and the parity to wait for on its empty barrier
     bool first = true;
+    TRACE_DECL(do_a ? 1 : 2)
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int nb = item / num_pairs;
       const int tile = 2 * (item - nb * num_pairs) + static_cast<int>(rank);
@@ -152,7 +171,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       int kx = 0, kc = 0;  // same K order as fprop_kernel<., ., HALO>: kx outer, 64-channel chunk inner
       for (int st = 0; st < steps; ++st) {
         if (do_a) {
+          TR();
           mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
+          TR();
           if (elect_one_sync()) {
             if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
             if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
@@ -168,13 +189,13 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         }
         if (do_b && (!resident || first)) {
           if (L::kG == 3) {
+            TR();
             if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
+            TR();
             if (elect_one_sync()) {
               if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky)
-                tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot + ky * L::kBTile, &mapB, &b_full[sb],
-                                 (ky * 3 + kx) * p.ka + kc * 64, nrow);
+              // mapB is the rank-4 view [kx][ky][n][k within tap]: one box = the three ky tiles, stacked
+              tma_load_4d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb], kc * 64, nrow, 0, kx);
             }
             __syncwarp();
             if (++sb == L::kSB) {
@@ -184,7 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           } else {
 #pragma unroll 1
             for (int ky = 0; ky < NKY; ++ky) {
+              TR();
               if (!resident) mbar_wait(&b_empty[sb], pb, p.err, DEV_ERR_EMPTY_TIMEOUT);
+              TR();
               if (elect_one_sync()) {
                 if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * L::kBSlot);
                 tma_load_2d_2cta(smem + L::kBOff + sb * L::kBSlot, &mapB, &b_full[sb],
@@ -217,15 +240,20 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const uint32_t ky_step = static_cast<uint32_t>(p.tw * 128) >> 4;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot and the parity to wait for on its full barrier
       uint32_t n_item = 0;
+      TRACE_DECL(0)
       for (int item = cluster_id; item < num_items; item += num_clusters, ++n_item) {
         const uint32_t buf = n_item & 1;
+        TR();
         mbar_wait(&acc_empty[buf], ((n_item >> 1) & 1) ^ 1, p.err, DEV_ERR_ACC_TIMEOUT);
+        TR();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         if (resident) sb = 0;
 #pragma unroll 1
         for (int st = 0; st < steps; ++st) {
+          TR();
           mbar_wait(&a_full[sa], pa, p.err, DEV_ERR_FULL_TIMEOUT);
+          TR();
           const uint32_t a_lo = a_lo0 + sa * (kABox >> 4);
           if (L::kG == 3 || resident) {
             // the three weight tiles of this step sit behind one barrier (kG == 3) or are resident: 12 MMAs and the
@@ -280,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
             sa = 0;
             pa ^= 1;
           }
+          TR();
         }
         if (elect_one_sync()) umma_commit_2cta(&acc_full[buf], 3);
         __syncwarp();
@@ -297,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
     red += grp * 4 * 64 * 2;
     uint32_t n_item = grp, n_slab = 0;
     int bias_nb = -1;
+    TRACE_DECL(q == 2 ? 3 + grp : 5)  // warps 2 and 6 (q == 2) stamp for their group
     // per-CTA BatchNorm statistics (p.stat_groups > 0): thread t < 64 keeps the running (sum, sum of squares) of
     // channel t of every slab of the current N block, per stat-group, and writes them once per N block
     const bool cta_stats = p.stats != nullptr && p.stat_groups > 0;
@@ -349,7 +379,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         bias_nb = nb;
       }
       const uint32_t buf = grp;
+      TR();
       mbar_wait(&acc_full[buf], (n_item >> 1) & 1, p.err, DEV_ERR_ACC_TIMEOUT);
+      TR();
       tc_fence_after();
 #pragma unroll
       for (int slab = 0; slab < BN / 64; ++slab, ++n_slab) {
@@ -403,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+          TR();
         }
         fence_proxy_async_smem();
         named_barrier_sync(bar1, 128);
@@ -510,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           // `red` is rewritten only after the next slab's first named barrier, which every reader passes first
         }
       }
+      TR();
     }
     if (cta_stats && acc_nb >= 0) flush_stats(acc_nb);
     if (t == 0) tma_store_wait_read0();
@@ -619,6 +653,8 @@ static bool pair_resident(const FpropParams& p, int bn) {
 
 }  // namespace
 
+bool fprop_pair_stacked_weights(int mode, int bn) { return mode == 0 && bn <= 128; }
+
 cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
   if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1 || (p.mode == 2 && p.out_mode == 0))) return cudaErrorInvalidValue;
@@ -638,3 +674,9 @@ int fprop_pair_ctas(const FpropParams& p, int bn, int num_tiles) {
 }
 
 }  // namespace b200cd
+
+#ifdef B200CD_TRACE
+extern "C" int b200cd_debug_trace(long long* host) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host, b200cd::g_trace, sizeof(long long) * 6 * 4096));
+}
+#endif

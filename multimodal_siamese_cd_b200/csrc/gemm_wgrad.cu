@@ -22,7 +22,7 @@ namespace b200cd {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;  // U producer, MMA issuer, 4 epilogue warps, V producer (B200CD_WGRAD_SPLIT=0: 192, warp 0 loads both)
 constexpr int kUBytes = 2 * 64 * 128;  // 64 pixels x 128 channels (two 64-channel slabs)
 
 // NKX (3x3 mode with HALO only): kx columns per CTA. With 64-wide N tiles an MMA lasts 32 cycles and a (U, V box) pair
@@ -48,6 +48,29 @@ struct WgradCfg {
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(kCols <= 512, "accumulators exceed TMEM");
 };
+
+#ifdef B200CD_TRACE
+__device__ long long g_trace_w[4][4096];
+#define WTRACE_DECL(role)                                           \
+  int tr_i = 0;                                                     \
+  const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0; \
+  const int tr_role = (role);
+#define WTR()                                                                   \
+  do {                                                                          \
+    if (tr_on && tr_i < 4096) g_trace_w[tr_role][tr_i++] = clock64();           \
+  } while (0)
+#else
+#define WTRACE_DECL(role)
+#define WTR()
+#endif
+
+static int wgrad_threads() {
+  static const int t = [] {
+    const char* e = getenv("B200CD_WGRAD_SPLIT");
+    return (e && e[0] == '0') ? 192 : kThreads;
+  }();
+  return t;
+}
 
 template <int BN, int MODE, bool HALO, int NKX>
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__ CUtensorMap mapU,
@@ -105,24 +128,36 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above is independent of the predecessor kernel's output
 
-  if (warp == 0) {
-    // ---------------- TMA producer (whole warp runs the loop, one elected lane issues) ----------------
+  if (warp == 0 || warp == 6) {
+    // ---------------- TMA producers (whole warp runs the loop, one elected lane issues): warp 0 arms the stage's
+    // barrier and loads U, warp 6 loads V — a thread can start a bulk-tensor load only every ~230 cycles
+    // (tools/ubench/tma_rate.cu), so the four loads of a stage are spread over two issuing warps ----------------
+    const bool split_prod = blockDim.x > 192;
+    const bool do_u = warp == 0, do_v = split_prod ? warp == 6 : warp == 0;
+    WTRACE_DECL(do_u ? 1 : 2)
     uint32_t s = 0, ph = 1;
     int tile = t_begin;
     int tx = tile % p.tiles_x;
     int ty = (tile / p.tiles_x) % p.tiles_y;
     int img = tile / (p.tiles_x * p.tiles_y);
     for (int it = 0; it < iters; ++it) {
+      WTR();
       mbar_wait(&empty[s], ph, p.err, DEV_ERR_EMPTY_TIMEOUT);
+      WTR();
       const int x0 = tx * 8, y0 = ty * 8;
       uint8_t* u_dst = smem + s * C::kStageBytes;
       uint8_t* v_dst = u_dst + kUBytes;
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&full[s], NKX == 1 ? C::kStageBytes : kUBytes + nkx * (BN / 64) * C::kVSlab);
+        if (do_u) {
+          // the byte count may be armed after warp 6's loads have begun to land: the phase cannot complete before this
+          // arrival, and the transaction count is signed
+          mbar_arrive_expect_tx(&full[s], NKX == 1 ? C::kStageBytes : kUBytes + nkx * (BN / 64) * C::kVSlab);
 #pragma unroll
-        for (int slab = 0; slab < 2; ++slab)
-          tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
-        if (MODE == 0) {
+          for (int slab = 0; slab < 2; ++slab)
+            tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
+        }
+        if (!do_v) {
+        } else if (MODE == 0) {
           if (HALO) {
 #pragma unroll
             for (int b = 0; b < NKX; ++b) {
@@ -176,8 +211,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     const uint32_t u_lo0 = smem_desc_lo(smem_u32(smem), 8192);
     const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem) + kUBytes, C::kVSlab);
     uint32_t s = 0, ph = 0;
+    WTRACE_DECL(0)
     for (int it = 0; it < iters; ++it) {
+      WTR();
       mbar_wait(&full[s], ph, p.err, DEV_ERR_FULL_TIMEOUT);
+      WTR();
       tc_fence_after();
       const uint32_t u_lo = u_lo0 + s * (C::kStageBytes >> 4);
       const uint32_t v_lo = v_lo0 + s * (C::kStageBytes >> 4);
@@ -228,13 +266,17 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         ph ^= 1;
       }
     }
+    WTR();
     if (elect_one_sync()) umma_commit(accbar);
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> fp32 workspace ----------------
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
+    WTRACE_DECL(3)
+    WTR();
     mbar_wait(accbar, 0, p.err, DEV_ERR_ACC_TIMEOUT);
+    WTR();
     tc_fence_after();
     float* base = p.ws + static_cast<long long>(split) * p.split_stride;
 #pragma unroll 1
@@ -262,6 +304,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         }
       }
     }
+    WTR();
   }
 
   tc_fence_before();
@@ -284,7 +327,7 @@ cudaError_t launch_one(const CUtensorMap& mapU, const CUtensorMap& mapV, const W
   }
   const int z = NKX == 2 ? p.splits + p.splits2 : (MODE == 0 ? 3 : 1) * p.splits;
   dim3 grid((p.cu + 127) / 128, p.cv / BN, z);
-  launch_k(wgrad_kernel<BN, MODE, HALO, NKX>, dim3(grid), dim3(kThreads), C::kDynamic, stream, mapU, mapV, p);
+  launch_k(wgrad_kernel<BN, MODE, HALO, NKX>, dim3(grid), dim3(wgrad_threads()), C::kDynamic, stream, mapU, mapV, p);
   return cudaGetLastError();
 }
 
@@ -307,3 +350,9 @@ cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const
 }
 
 }  // namespace b200cd
+
+#ifdef B200CD_TRACE
+extern "C" int b200cd_debug_trace_wgrad(long long* host) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host, b200cd::g_trace_w, sizeof(long long) * 4 * 4096));
+}
+#endif

@@ -64,6 +64,10 @@ int fprop_pair_ctas(const FpropParams& p, int bn, int num_tiles);
 cudaError_t launch_fprop(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                          const FpropParams& p, int bn, int halo, int num_tiles, cudaStream_t stream);
 
+// true when the CTA-pair kernel for (mode, bn) wants mapB as the rank-4 view {k within tap, n, ky, kx} with box
+// {64, bn / 2, 3, 1} (one load per step) instead of the rank-2 [N][taps * ka] view with box {64, bn / 2}
+bool fprop_pair_stacked_weights(int mode, int bn);
+
 // G1p (gemm_fprop2.cu): mode 0 / out_mode 0 on CTA pairs (cta_group::2), persistent, halo A boxes (p.rows = tw*(th+2)).
 cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO,
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream);

@@ -320,6 +320,13 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                                  int c3, int c4) {
   asm volatile(
