@@ -151,6 +151,11 @@ int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld,
 /* number of 8x8 pixel tiles (upper bound for `splits`) */
 int b200cd_wgrad_tiles(int n_img, int H, int W);
 
+/* CTAs one pixel-range split of b200cd_wgrad_gemm launches (the caller sizes `splits` so that splits * this fills the
+ * 148 SMs): (cu / 128 rounded up) * (cv / N tile) * 3 filter columns for the 3x3 modes — except with halo, 64-wide N
+ * tiles and cu <= 64, where one CTA owns all nine taps. -1 on bad arguments. */
+int b200cd_wgrad_ctas_per_split(int mode, int halo, int cu, int cv);
+
 /* Fixed-order sum over splits into the reference parameter layout.
  *   layout 0: ws[s][tap][d0][d1] -> grad[d0][d1][tap]  (Conv2d.weight [co][ci][3][3]; ConvTranspose2d.weight [ci][co][2][2])
  *   layout 1: ws[s][d0][ld1], k = tap*d1 + i -> grad[d0][d1][tap], split_stride = d0*ld1 (first layer) */

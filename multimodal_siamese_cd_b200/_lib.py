@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200cd_conv_gemm_stat_rows": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "b200cd_wgrad_gemm": (_i, [_i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "b200cd_wgrad_tiles": (_i, [_i, _i, _i]),
+    "b200cd_wgrad_ctas_per_split": (_i, [_i, _i, _i, _i]),
     "b200cd_wgrad_reduce": (_i, [_vp, _i, _i64, _i, _i, _i, _i, _vp, _vp]),
     "b200cd_bn_stats": (_i, [_vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200cd_bn_apply": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),

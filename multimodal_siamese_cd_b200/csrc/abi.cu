@@ -371,6 +371,14 @@ int b200cd_conv_gemm_bnbwd(int mode, int flags, const void* A, int64_t a_ld, int
 
 int b200cd_wgrad_tiles(int n_img, int H, int W) { return n_img * ((W + 7) / 8) * ((H + 7) / 8); }
 
+int b200cd_wgrad_ctas_per_split(int mode, int halo, int cu, int cv) {
+  if (mode < 0 || mode > 2 || cu < 64 || cu % 64 != 0 || cv < 64 || cv % 64 != 0) return -1;
+  const int bn = (cv % 128 == 0) ? 128 : 64;
+  const int xy = ((cu + 127) / 128) * (cv / bn);
+  if (mode != 0) return xy;
+  return (bn == 64 && halo && b200cd::wgrad_mstack(cu)) ? xy : 3 * xy;
+}
+
 int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
                       int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
                       int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {

@@ -31,15 +31,19 @@ constexpr int kUBytes = 2 * 64 * 128;  // 64 pixels x 128 channels (two 64-chann
 // z >= splits own kx 2 over 1/splits2 of them (splits2 = splits / 2 balances the work).
 template <int BN, int MODE, bool HALO, int NKX = 1>
 struct WgradCfg {
+  // NKX = 3 (64-wide N tiles, U <= 64 channels): ONE CTA owns all nine taps. The kx shift moves to the U side — three
+  // 64-channel U tiles at x - sign, x, x + sign — and two of them stack along M (the M = 128 tile would otherwise be
+  // half empty); the three ky taps stack along N out of one unshifted V halo box (N = 192).
   static constexpr int kTaps = MODE == 0 ? 3 * NKX : (MODE == 1 ? 1 : 4);
   static constexpr int kVRows = HALO ? 80 : 64;
   static constexpr int kVSlab = kVRows * 128;
-  static constexpr int kVTiles = HALO ? NKX : kTaps;  // separately loaded tap tiles / boxes
+  static constexpr int kVTiles = NKX == 3 ? 1 : (HALO ? NKX : kTaps);  // separately loaded tap tiles / boxes
   static constexpr int kVBytes = kVTiles * (BN / 64) * kVSlab;
-  static constexpr int kStageBytes = kUBytes + kVBytes;
+  static constexpr int kUBytesC = NKX == 3 ? 3 * 64 * 128 : kUBytes;
+  static constexpr int kStageBytes = kUBytesC + kVBytes;
   static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kCols = kTaps * BN;
+  static constexpr int kCols = NKX == 3 ? 384 : kTaps * BN;
   static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kTmemSlotOff = kBarOff + 8 * (2 * kStages + 1);
@@ -64,6 +68,20 @@ __device__ long long g_trace_w[4][4096];
 #define WTR()
 #endif
 
+}  // namespace
+
+// 3x3 / halo / 64-wide N tiles with at most 64 U channels: one CTA per pixel range owns all nine taps (grid z = splits,
+// not 3 * splits) — see WgradCfg. B200CD_WGRAD_MSTACK=0 keeps the one-kx-per-CTA kernel.
+bool wgrad_mstack(int cu) {
+  static const bool on = [] {
+    const char* e = getenv("B200CD_WGRAD_MSTACK");
+    return !(e && e[0] == '0');
+  }();
+  return on && cu <= 64;
+}
+
+namespace {
+
 static int wgrad_threads() {
   static const int t = [] {
     const char* e = getenv("B200CD_WGRAD_SPLIT");
@@ -78,6 +96,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
                                                          const WgradParams p) {
   using C = WgradCfg<BN, MODE, HALO, NKX>;
   static_assert(NKX == 1 || (MODE == 0 && HALO), "NKX > 1 needs the 3x3 halo variant");
+  static_assert(NKX != 3 || BN == 64, "the M-stacked variant is for 64-wide N tiles");
   constexpr int STAGES = C::kStages;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -92,7 +111,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * BN;
   int split, kx, nkx, nsplit;  // this CTA: kx columns [kx, kx + nkx) over pixel-tile range split / nsplit
-  if (NKX == 2) {
+  if (NKX == 3) {
+    split = blockIdx.z;
+    kx = 0;
+    nkx = 3;
+    nsplit = p.splits;
+  } else if (NKX == 2) {
     const bool first = static_cast<int>(blockIdx.z) < p.splits;
     split = first ? blockIdx.z : blockIdx.z - p.splits;
     nsplit = first ? p.splits : p.splits2;
@@ -146,17 +170,25 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       WTR();
       const int x0 = tx * 8, y0 = ty * 8;
       uint8_t* u_dst = smem + s * C::kStageBytes;
-      uint8_t* v_dst = u_dst + kUBytes;
+      uint8_t* v_dst = u_dst + C::kUBytesC;
       if (elect_one_sync()) {
         if (do_u) {
           // the byte count may be armed after warp 6's loads have begun to land: the phase cannot complete before this
           // arrival, and the transaction count is signed
-          mbar_arrive_expect_tx(&full[s], NKX == 1 ? C::kStageBytes : kUBytes + nkx * (BN / 64) * C::kVSlab);
+          mbar_arrive_expect_tx(&full[s], NKX != 2 ? C::kStageBytes : kUBytes + nkx * (BN / 64) * C::kVSlab);
+          if (NKX == 3) {
 #pragma unroll
-          for (int slab = 0; slab < 2; ++slab)
-            tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
+            for (int a = 0; a < 3; ++a)  // U tile a pairs with the unshifted V box as filter column kx = a
+              tma_load_5d(u_dst + a * 8192, &mapU, &full[s], m0, x0 - p.sign * (a - 1), y0, img, 0);
+          } else {
+#pragma unroll
+            for (int slab = 0; slab < 2; ++slab)
+              tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
+          }
         }
         if (!do_v) {
+        } else if (NKX == 3) {
+          tma_load_5d(v_dst, &mapV, &full[s], n0, x0, y0 - 1, img, 0);
         } else if (MODE == 0) {
           if (HALO) {
 #pragma unroll
@@ -209,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
     const uint32_t desc_hi = smem_desc_hi(1024);
     const uint32_t u_lo0 = smem_desc_lo(smem_u32(smem), 8192);
-    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem) + kUBytes, C::kVSlab);
+    const uint32_t v_lo0 = smem_desc_lo(smem_u32(smem) + C::kUBytesC, C::kVSlab);
     uint32_t s = 0, ph = 0;
     WTRACE_DECL(0)
     for (int it = 0; it < iters; ++it) {
@@ -219,7 +251,21 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t u_lo = u_lo0 + s * (C::kStageBytes >> 4);
       const uint32_t v_lo = v_lo0 + s * (C::kStageBytes >> 4);
-      if (BN == 64 && HALO && MODE == 0) {
+      if (NKX == 3) {
+        // rows 0..63 / 64..127 of the first accumulator: kx 0 / kx 1; rows 0..63 of the second: kx 2 (its upper half
+        // multiplies whatever follows the third U tile — the V box, finite — and is never read); columns [ky][64]
+        constexpr uint32_t idesc3 = make_idesc_bf16(128, 192, 1, 1);
+        const uint32_t vp = (v_lo & 0xFFFFu) + ((1024u >> 4) << 16);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lo(tmem_base + h * 192, u_lo + h * (16384 >> 4) + k * (2048 >> 4), vp + k * (2048 >> 4), desc_hi,
+                           idesc3, it > 0 || k > 0);
+          umma_commit(&empty[s]);
+        }
+      } else if (BN == 64 && HALO && MODE == 0) {
         // 64-wide N tiles: an N = 64 MMA costs as much tensor-pipe time as an N = 128 one (measured: ~70 cycles either
         // way), so two taps are issued as ONE N = 128 MMA — the B descriptor's leading byte offset is the distance
         // between the two taps' 64-channel blocks (next ky: 1024 bytes; last ky of a box -> first ky of the next box:
@@ -244,6 +290,23 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16_lo(tmem_base + j * BN, u_lo + k * (2048 >> 4), vj + k * (2048 >> 4), desc_hi, idesc, it > 0 || k > 0);
+          }
+          umma_commit(&empty[s]);
+        }
+      } else if (BN == 128 && HALO && MODE == 0 && NKX == 1) {
+        // 128-wide N tiles: the three ky taps of one 64-channel slab of the V box are 1024 bytes apart, so they form
+        // ONE N = 192 operand (leading byte offset 1024) and U is read from shared memory twice per K step instead of
+        // three times — this kernel is bound by the SM's 128 B/clk of shared-memory bandwidth (operand reads + TMA
+        // writes), not by the tensor pipe. Accumulator columns: [slab][tap][64 channels].
+        constexpr uint32_t idesc3 = make_idesc_bf16(128, 192, 1, 1);
+        const uint32_t v_base = (v_lo & 0xFFFFu);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const uint32_t vp = v_base + sl * (C::kVSlab >> 4) + ((1024u >> 4) << 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lo(tmem_base + sl * 192, u_lo + k * (2048 >> 4), vp + k * (2048 >> 4), desc_hi, idesc3, it > 0 || k > 0);
           }
           umma_commit(&empty[s]);
         }
@@ -279,6 +342,38 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     WTR();
     tc_fence_after();
     float* base = p.ws + static_cast<long long>(split) * p.split_stride;
+    if (NKX == 3) {
+      const int ch = (q & 1) * 32 + lane;  // U channel of this accumulator row
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && q >= 2) break;       // upper half of the second accumulator is padding
+        const int kxx = h == 0 ? (q >> 1) : 2;
+#pragma unroll 1
+        for (int j = 0; j < 3; ++j) {
+          const int tap = (p.sign > 0 ? j : 2 - j) * 3 + kxx;
+          float* tbase = base + tap * p.tap_stride + static_cast<long long>(ch) * p.m_stride;
+#pragma unroll 1
+          for (int c32 = 0; c32 < 2; ++c32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 192 + j * 64 + c32 * 32, v);
+            tmem_ld_wait();
+            if (ch < p.cu) {
+              if (p.n_stride == 1) {
+                float4* dst = reinterpret_cast<float4*>(tbase + n0 + c32 * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  tbase[static_cast<long long>(n0 + c32 * 32 + i) * p.n_stride] = __uint_as_float(v[i]);
+              }
+            }
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int j = 0; j < C::kTaps; ++j) {
       if (NKX == 2 && j >= 3 * nkx) break;
@@ -288,7 +383,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
 #pragma unroll 1
       for (int c32 = 0; c32 < BN / 32; ++c32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN + c32 * 32, v);
+        const int col = (BN == 128 && HALO && MODE == 0 && NKX == 1) ? (c32 >> 1) * 192 + j * 64 + (c32 & 1) * 32
+                                                                     : j * BN + c32 * 32;
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col, v);
         tmem_ld_wait();
         if (m < p.cu) {
           if (p.n_stride == 1) {
@@ -325,7 +422,7 @@ cudaError_t launch_one(const CUtensorMap& mapU, const CUtensorMap& mapV, const W
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int z = NKX == 2 ? p.splits + p.splits2 : (MODE == 0 ? 3 : 1) * p.splits;
+  const int z = NKX == 3 ? p.splits : NKX == 2 ? p.splits + p.splits2 : (MODE == 0 ? 3 : 1) * p.splits;
   dim3 grid((p.cu + 127) / 128, p.cv / BN, z);
   launch_k(wgrad_kernel<BN, MODE, HALO, NKX>, dim3(grid), dim3(wgrad_threads()), C::kDynamic, stream, mapU, mapV, p);
   return cudaGetLastError();
@@ -338,6 +435,7 @@ cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const
   if (p.mode == 0) {
     if (bn == 128) return halo ? launch_one<128, 0, true>(mapU, mapV, p, stream) : launch_one<128, 0, false>(mapU, mapV, p, stream);
     if (bn == 64 && halo && p.splits2 > 0) return launch_one<64, 0, true, 2>(mapU, mapV, p, stream);
+    if (bn == 64 && halo && wgrad_mstack(p.cu)) return launch_one<64, 0, true, 3>(mapU, mapV, p, stream);
     if (bn == 64) return halo ? launch_one<64, 0, true>(mapU, mapV, p, stream) : launch_one<64, 0, false>(mapU, mapV, p, stream);
   } else if (p.mode == 1) {
     if (bn == 128) return launch_one<128, 1, false>(mapU, mapV, p, stream);

@@ -79,6 +79,9 @@ cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, 
 //   mode 1: single tap
 //   mode 2: transposed conv (4 taps, V gathered with stride 2 from the full-resolution gradient)
 // ----------------------------------------------------------------------------------------------
+// true when launch_wgrad runs the M-stacked all-taps-per-CTA variant for (mode 0, halo, 64-wide N tiles, cu)
+bool wgrad_mstack(int cu);
+
 struct WgradParams {
   int mode, sign;
   int H, W, tiles_x, tiles_y, total_tiles, splits;

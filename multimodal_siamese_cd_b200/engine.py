@@ -504,14 +504,14 @@ class StepEngine:
             return ("first", splits, self._ws_region(splits * cout * kp), 0)
         if cout >= 128 or cin < 128:
             role = "pos"   # M <-> cout (U = dr), N <-> cin
-            ctas = ((cout + 127) // 128) * (cin // 128 if cin % 128 == 0 else cin // 64) * 3
+            ctas = ops.wgrad_ctas_per_split(0, 1, cout, cin)
         else:
             role = "neg"   # M <-> cin (U = input), N <-> cout
-            ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
+            ctas = ops.wgrad_ctas_per_split(0, 1, cin, cout)
         nwide = cin if role == "pos" else cout      # width of the N side of the GEMM
         if WGRAD_TWO_KX and nwide % 128 != 0:
             # 64-wide N tiles: CTAs own two kx columns (splits of them) or the third one (splits2 = splits / 2)
-            per_xy = ctas // 3
+            per_xy = max(1, ctas // 3)
             splits2 = max(1, min(total, WGRAD_CTA_TARGET // (3 * per_xy)))
             splits = min(total, 2 * splits2)
             return (role, splits, self._ws_region(splits * 9 * cout * cin), splits2)

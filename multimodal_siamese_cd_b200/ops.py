@@ -263,6 +263,14 @@ def wgrad_tiles(n: int, H: int, W: int) -> int:
     return _lib.load().b200cd_wgrad_tiles(n, H, W)
 
 
+def wgrad_ctas_per_split(mode: int, halo: int, cu: int, cv: int) -> int:
+    """CTAs one pixel-range split of wgrad_gemm launches (b200cd_wgrad_ctas_per_split)."""
+    c = _lib.load().b200cd_wgrad_ctas_per_split(mode, halo, cu, cv)
+    if c <= 0:
+        raise ValueError(f"wgrad_ctas_per_split({mode}, {halo}, {cu}, {cv})")
+    return c
+
+
 def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor, ws: torch.Tensor, splits: int,
                split_stride: int, tap_stride: int, m_stride: int, n_stride: int, splits2: int = 0) -> None:
     """G2. U: NHWC view at the GEMM resolution; V: NHWC view (mode 2: at 2x)."""

@@ -830,6 +830,9 @@ ALL_CHECKS = {
     "wgrad3x3_neg_halo": lambda: check_wgrad3x3(2, 32, 32, 128, 64, sign=-1, halo=1, seed=71),
     "wgrad3x3_64_64_halo": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, seed=72),
     "wgrad3x3_64_64_many_splits": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, splits=27, seed=76),
+    "wgrad3x3_64_64_mstack_neg": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=-1, halo=1, splits=9, seed=83),
+    "wgrad3x3_64_64_mstack_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 64, sign=1, halo=1, splits=7, seed=84),
+    "wgrad3x3_64_64_mstack_1px_edge": lambda: check_wgrad3x3(1, 9, 9, 64, 64, sign=1, halo=1, splits=4, seed=85),
     "wgrad3x3_64_64_two_kx": lambda: check_wgrad3x3(2, 32, 32, 64, 64, sign=1, halo=1, splits=10, splits2=5, seed=77),
     "wgrad3x3_64_128_two_kx": lambda: check_wgrad3x3(2, 32, 32, 64, 128, sign=1, halo=1, splits=24, splits2=12, seed=78),
     "wgrad3x3_256_64_two_kx_neg": lambda: check_wgrad3x3(2, 32, 32, 256, 64, sign=-1, halo=1, splits=6, splits2=3, seed=79),

@@ -11,10 +11,7 @@ dev = "cuda"
 x = torch.randn(n, H, H, cin, device=dev).to(torch.bfloat16)
 dr = torch.randn(n, H, H, cout, device=dev).to(torch.bfloat16)
 total = ops.wgrad_tiles(n, H, H)
-if cout >= 128 or cin < 128:
-    ctas = ((cout + 127) // 128) * (cin // 128 if cin % 128 == 0 else cin // 64) * 3
-else:
-    ctas = (cin // 128) * (cout // 128 if cout % 128 == 0 else cout // 64) * 3
+ctas = ops.wgrad_ctas_per_split(0, 1, cout, cin) if (cout >= 128 or cin < 128) else ops.wgrad_ctas_per_split(0, 1, cin, cout)
 splits = max(1, min(total, 148 // ctas))
 ws = torch.empty(splits, 9, cout, cin, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
