@@ -30,6 +30,11 @@ WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
 # BatchNorm backward of stages with a single direct gradient source: accumulate its reduce pass in the epilogue of the
 # input-gradient convolution that produces that gradient (ops.conv_gemm_bnbwd)
 FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != "0"
+# B200CD_WGRAD_SIDE_STREAM=1: weight-gradient GEMMs on a second stream (forked after the layer's input-gradient GEMM,
+# joined before each batched reduce) so that the HBM-bound BatchNorm-backward kernels of the next layers could run
+# under them. Measured neutral on B200 (9.71-9.76 ms either way): a 198 KB-shared-memory GEMM CTA and the elementwise
+# CTAs do not share an SM, so the kernels still alternate. Off by default.
+WGRAD_SIDE_STREAM = __import__("os").environ.get("B200CD_WGRAD_SIDE_STREAM", "0") == "1"
 # transposed-conv bias gradient from the per-CTA channel sums of the dgrad launch that writes the concat-buffer gradient
 UP_BIAS_FROM_STATS = __import__("os").environ.get("B200CD_UP_BIAS_FROM_STATS", "1") != "0"
 FUSE_BN_BWD_MIN_PIXELS = int(__import__("os").environ.get("B200CD_FUSE_BN_BWD_MIN_PIXELS", 32768))
@@ -157,6 +162,8 @@ class StepEngine:
         self.heads: list[Head] = []
         self.fwd_ops: list[Callable[[], None]] = []
         self.bwd_ops: list[Callable[[], None]] = []
+        self._side_stream = None
+        self._side_dirty = False
         self.pack_fwd: list[Callable[[], None]] = []
         self.pack_bwd: list[Callable[[], None]] = []
         self.bwd_marks: list[int] = []  # per backward op: length of the flat-gradient prefix complete after it
@@ -486,6 +493,36 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------------
     # backward emission: reverse order of the forward stages
     # ------------------------------------------------------------------------------------------------
+    def _side(self):
+        """Context manager: the enclosed launches go to the side stream, ordered after everything already on the
+        current stream (fork). No-op on CPU or with B200CD_WGRAD_SIDE_STREAM=0."""
+        eng = self
+
+        class _Fork:
+            def __enter__(self_inner):
+                self_inner.ctx = None
+                if eng.device.type != "cuda" or not WGRAD_SIDE_STREAM:
+                    return
+                if eng._side_stream is None:
+                    eng._side_stream = torch.cuda.Stream(device=eng.device)
+                eng._side_stream.wait_stream(torch.cuda.current_stream())
+                self_inner.ctx = torch.cuda.stream(eng._side_stream)
+                self_inner.ctx.__enter__()
+                eng._side_dirty = True
+
+            def __exit__(self_inner, *exc):
+                if self_inner.ctx is not None:
+                    self_inner.ctx.__exit__(*exc)
+                return False
+
+        return _Fork()
+
+    def _join_side(self) -> None:
+        """The current stream waits for everything launched on the side stream so far."""
+        if self._side_stream is not None and self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._side_dirty = False
+
     def _ws_region(self, floats: int) -> int:
         """Every layer owns a region of the split workspace: the per-split partial weight gradients of a whole
         backward segment are summed by ONE batched launch (ops.wgrad_reduce_batched)."""
@@ -571,23 +608,25 @@ class StepEngine:
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
                        st.dr, sums=st.bwd_sums, sum_rows=st.bwd_sum_rows)
             ws = eng.ws_wgrad.narrow(0, off, size)
-            if role == "first":
-                ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
-                ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
-            else:
-                if role == "pos":
+            # input gradient first (the next layer's BatchNorm backward waits for it), then the weight gradient on the
+            # side stream: it starts when the dgrad kernel leaves the SMs and runs under the next HBM-bound kernels
+            if role != "first" and st.d_in is not None:
+                if prod is not None:
+                    ops.conv_gemm_bnbwd(0, st.dr, st.Wd, st.d_in, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
+                elif up_rows:
+                    # d_in is the concat-buffer gradient of an Up: its per-channel pixel sums (upper half = the
+                    # transposed-conv bias gradient) come out of this launch's per-CTA statistics
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats, stat_groups=1)
+                else:
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
+            with eng._side():
+                if role == "first":
+                    ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
+                    ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
+                elif role == "pos":
                     ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1, splits2)
                 else:
                     ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
-                if st.d_in is not None:
-                    if prod is not None:
-                        ops.conv_gemm_bnbwd(0, st.dr, st.Wd, st.d_in, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
-                    elif up_rows:
-                        # d_in is the concat-buffer gradient of an Up: its per-channel pixel sums (upper half = the
-                        # transposed-conv bias gradient) come out of this launch's per-CTA statistics
-                        ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats, stat_groups=1)
-                    else:
-                        ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
 
         eng.bwd_ops.append(run)
         eng.bwd_marks.append(g.end_of(conv.weight))
@@ -611,7 +650,6 @@ class StepEngine:
         prod = eng._fusable_producer(uc.d_x, 2, c)
 
         def run():
-            ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
             if uc.bias_rows:
                 ops.stat_rowsum(eng.ws_upstats, uc.bias_rows, 2 * c, c, c, gb)
             else:
@@ -620,6 +658,8 @@ class StepEngine:
                 ops.conv_gemm_bnbwd(2, uc.d_out, uc.Wd, uc.d_x, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
             else:
                 ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
+            with eng._side():
+                ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
 
         eng.bwd_ops.append(run)
         eng.bwd_marks.append(g.end_of(uc.up.weight))
@@ -686,6 +726,7 @@ class StepEngine:
 
             def run(orig=orig, fi=fi):
                 orig()
+                self._join_side()
                 tab, nj, blocks, nbytes = self._reduce_tables[fi]
                 ops.wgrad_reduce_batched(tab, nj, blocks, nbytes)
 
@@ -714,6 +755,7 @@ class StepEngine:
             f()
         for f in self.bwd_ops:
             f()
+        self._join_side()
 
     def forward(self, x_t1: torch.Tensor, x_t2: torch.Tensor) -> None:
         """Copies the inputs into the static buffers and runs the forward plan; logits land in head.logits."""

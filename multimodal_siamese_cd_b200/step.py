@@ -170,6 +170,7 @@ class TrainStep:
             def seg(o0=o0, o1=o1):
                 for f in eng.bwd_ops[o0:o1]:
                     f()
+                eng._join_side()   # weight-gradient GEMMs forked inside the segment (engine.WGRAD_SIDE_STREAM)
             if eng.use_graphs and self._steps >= 2:
                 if self._bwd_graphs[bi] is None:
                     torch.cuda.synchronize()
