@@ -219,6 +219,13 @@ size_t b200cd_bn_bwd_ws_floats(int n_img, int H, int W, int C, int G);
 int b200cd_head_fwd(const void* a0, int64_t ld0, const void* a1, int64_t ld1, int C, const float* w, const float* b,
                     int64_t npix, float* logits, void* stream);
 
+/* Centre pad of Up (utils/networks.py:440-443, F.pad of the transposed-conv output to the skip tensor's size):
+ * dst[n][top + y][left + x][0..C) = src[n][y][x][0..C) for the h x w source, zero elsewhere in the H x W window.
+ * Both tensors NHWC bf16 with pixel strides ld (dst is typically the upper half of a concat buffer). Used by
+ * inference on tiles whose levels have odd sizes; training tiles (multiples of 16) never need it. */
+int b200cd_pad_copy(const void* src, int64_t ld_src, int n_img, int h, int w, int C, void* dst, int64_t ld_dst, int H,
+                    int W, int top, int left, void* stream);
+
 /* out[c] = sum_pixels wgt[pixel] * x[pixel][c]  (x == NULL: C = 1, out = sum wgt; wgt == NULL: plain column sum).
  * OutConv weight/bias gradients and the ConvTranspose2d bias gradient. ws: fp32 [nblk*C]. */
 int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,

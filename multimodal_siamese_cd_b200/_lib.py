@@ -54,6 +54,7 @@ SIGNATURES = {
                                      _vp, _vp, _i64, _vp]),
     "b200cd_bn_bwd_ws_floats": (_sz, [_i, _i, _i, _i, _i]),
     "b200cd_head_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "b200cd_pad_copy": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _i, _vp]),
     "b200cd_colsum": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "b200cd_stat_rowsum": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "b200cd_pj_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),

@@ -551,6 +551,17 @@ int b200cd_head_fwd(const void* a0, int64_t ld0, const void* a1, int64_t ld1, in
   return 0;
 }
 
+int b200cd_pad_copy(const void* src, int64_t ld_src, int n_img, int h, int w, int C, void* dst, int64_t ld_dst, int H,
+                    int W, int top, int left, void* stream) {
+  if (n_img <= 0 || h <= 0 || w <= 0 || C <= 0 || C % 8 != 0 || top < 0 || left < 0 || top + h > H || left + w > W)
+    return fail(B200CD_ERR_SHAPE, "pad_copy: %dx%d at (%d, %d) does not fit %dx%d (C=%d)", h, w, top, left, H, W, C);
+  if (ld_src % 8 != 0 || ld_dst % 8 != 0 || ld_src < C || ld_dst < C || !aligned16(src) || !aligned16(dst))
+    return fail(B200CD_ERR_ALIGN, "pad_copy: strides must be multiples of 8 elements and pointers 16-byte aligned");
+  CUDA_TRY(b200cd::launch_pad_copy(src, ld_src, n_img, h, w, C, dst, ld_dst, H, W, top, left,
+                                   reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200cd_colsum(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
                   void* stream) {
   if (x != nullptr && !chan_ok(C)) return fail(B200CD_ERR_SHAPE, "colsum: unsupported C=%d", C);

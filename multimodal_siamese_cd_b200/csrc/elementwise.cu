@@ -1271,6 +1271,33 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_dx_kernel(const BwdArgs p, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Centre pad of Up (utils/networks.py:440-443): the transposed-conv output [n][h][w][C] placed at (top, left) of a
+// [n][H][W] window with row pitch W and pixel stride ld_d (the upper half of a concat buffer); the border is zero.
+// Only inference on tiles whose size is not a multiple of 16 needs it (odd levels: MaxPool floors, Up pads).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_copy_kernel(const __nv_bfloat16* __restrict__ src, long long ld_s, int n_img,
+                                                       int h, int w, int C, __nv_bfloat16* __restrict__ dst,
+                                                       long long ld_d, int H, int W, int top, int left) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cvecs = C >> 3;
+  const long long total = static_cast<long long>(n_img) * H * W * cvecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvecs);
+    long long px = i / cvecs;
+    const int x = static_cast<int>(px % W);
+    const int y = static_cast<int>((px / W) % H);
+    const int n = static_cast<int>(px / (static_cast<long long>(W) * H));
+    const int ys = y - top, xs = x - left;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ys >= 0 && ys < h && xs >= 0 && xs < w)
+      v = ldg16(src + ((static_cast<long long>(n) * h + ys) * w + xs) * ld_s + cv * 8);
+    *reinterpret_cast<uint4*>(dst + px * ld_d + cv * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 1x1 head (OutConv, C -> 1) over one or two 64..128-channel inputs; 8 lanes per pixel.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ a0, long long ld0,
@@ -2138,6 +2165,14 @@ cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long 
   launch_k(head_fwd_kernel, dim3(static_cast<int>((threads + 255) / 256)), dim3(256), 0, st, 
       reinterpret_cast<const __nv_bfloat16*>(a0), ld0, reinterpret_cast<const __nv_bfloat16*>(a1), ld1, C, w, b, npix,
       logits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pad_copy(const void* src, long long ld_s, int n_img, int h, int w, int C, void* dst, long long ld_d,
+                            int H, int W, int top, int left, cudaStream_t st) {
+  const long long total = static_cast<long long>(n_img) * H * W * (C / 8);
+  launch_k(pad_copy_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), ld_s,
+           n_img, h, w, C, reinterpret_cast<__nv_bfloat16*>(dst), ld_d, H, W, top, left);
   return cudaGetLastError();
 }
 

@@ -145,6 +145,8 @@ cudaError_t launch_bn_bwd_dx(const void* r, long long ld_r, const float* scale, 
                              void* dr, long long ld_dr, cudaStream_t st);
 cudaError_t launch_head_fwd(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
                             const float* b, long long npix, float* logits, cudaStream_t st);
+cudaError_t launch_pad_copy(const void* src, long long ld_s, int n_img, int h, int w, int C, void* dst, long long ld_d,
+                            int H, int W, int top, int left, cudaStream_t st);
 cudaError_t launch_colsum(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,
                           float* partial, cudaStream_t st);
 cudaError_t launch_stat_rowsum(const float2* stats, int rows, int ld, int c_off, int C, float* out, cudaStream_t st);

@@ -99,6 +99,9 @@ class UpConv:
     Wf: torch.Tensor = None
     Wd: Optional[torch.Tensor] = None
     bias_rows: int = 0       # > 0: the dgrad that writes d_cat also wrote per-CTA channel sums (bias gradient for free)
+    # inference on odd-sized levels: the 2h x 2w output goes to `dense`, then ops.pad_copy centres it in `out`
+    dense: Optional[torch.Tensor] = None
+    pad: tuple = (0, 0)
 
 
 @dataclass
@@ -153,8 +156,10 @@ class StepEngine:
 
     def __init__(self, net: nn.Module, B: int, H: int, W: int, train: bool, device: torch.device,
                  use_graphs: bool = True):
-        if H % 16 != 0 or W % 16 != 0:
-            raise ValueError(f"b200cd engine: H and W must be multiples of 16 (got {H}x{W})")
+        if train and (H % 16 != 0 or W % 16 != 0):
+            raise ValueError(f"b200cd engine: training tiles must be multiples of 16 (got {H}x{W})")
+        if H < 16 or W < 16:
+            raise ValueError(f"b200cd engine: tiles smaller than 16x16 vanish in the four MaxPool levels (got {H}x{W})")
         self.net, self.B, self.H, self.W, self.train, self.device = net, B, H, W, train, device
         self.use_graphs = use_graphs
         self.stages: list[Stage] = []
@@ -321,6 +326,13 @@ class StepEngine:
                 assert "a" not in skip_stage.outs, "plain skip is written straight into the concat buffer"
                 skip_stage.outs["a"] = cat[..., :c]
             uc = UpConv(f"{tag}.{uname}.up", up.up, x, cat[..., c:])
+            hx, wx = x.shape[1], x.shape[2]
+            if (2 * hx, 2 * wx) != (Hs, Ws):
+                # MaxPool floored an odd level: the reference pads the up-sampled tensor to the skip's size with
+                # diff // 2 on the top / left (utils/networks.py:440-443)
+                assert not self.train and 0 <= Hs - 2 * hx <= 1 and 0 <= Ws - 2 * wx <= 1
+                uc.dense = self._new(nb, 2 * hx, 2 * wx, c)
+                uc.pad = ((Hs - 2 * hx) // 2, (Ws - 2 * wx) // 2)
             uc.Wf = self._new(4 * c, c)
             self.upconvs.append(uc)
             d_cat = None
@@ -482,7 +494,13 @@ class StepEngine:
                     self._pack_specs.append((3, uc.up.weight, uc.Wf, 0, 4, uc.Wd))
                 else:
                     self._pack_specs.append((3, uc.up.weight, uc.Wf, 0))
-                self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
+                if uc.dense is None:
+                    self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
+                else:
+                    def run_up(uc=uc):
+                        ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.dense, bias=uc.up.bias)
+                        ops.pad_copy(uc.dense, uc.out, uc.pad[0], uc.pad[1])
+                    self.fwd_ops.append(run_up)
             self._emit_stage_fwd(st)
         for hd in self.heads:
             def run(hd=hd):

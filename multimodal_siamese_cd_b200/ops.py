@@ -425,6 +425,19 @@ def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: t
                                                n * H * W, logits.data_ptr(), _stream()))
 
 
+def pad_copy(src: torch.Tensor, dst: torch.Tensor, top: int, left: int) -> None:
+    """dst (NHWC view, e.g. the upper half of a concat buffer) = src placed at (top, left), zero border:
+    Up's centre pad, utils/networks.py:440-443."""
+    _require_cuda(src, dst)
+    n, h, w, Cc, ld_s = _nhwc(src)
+    n2, H, W, C2, ld_d = _nhwc(dst)
+    assert n == n2 and Cc == C2
+    _count(1)
+    with _Prof("pad_copy", 0.0, 2.0 * n * (h * w + H * W) * Cc):
+        _lib.check(_lib.load().b200cd_pad_copy(src.data_ptr(), ld_s, n, h, w, Cc, dst.data_ptr(), ld_d, H, W, top, left,
+                                               _stream()))
+
+
 def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nblk: int, ws: torch.Tensor,
            out: torch.Tensor) -> None:
     _require_cuda(ws, out)

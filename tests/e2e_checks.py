@@ -129,7 +129,7 @@ def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alph
     return res
 
 
-def run_eval_case(mtype: str, cin: int, topo, B: int, H: int, W: int, warm_steps: int = 1) -> dict:
+def run_eval_case(mtype: str, cin: int, topo, B: int, H: int, W: int, warm_steps: int = 1, warm_hw=None) -> dict:
     """Inference path of utils/evaluation.py:7-23: net.eval(), no_grad, sigmoid(logits) > 0.5, F1 — after `warm_steps`
     training steps so that the BatchNorm running statistics are not the initial (0, 1)."""
     dev = torch.device("cuda", 0)
@@ -143,10 +143,13 @@ def run_eval_case(mtype: str, cin: int, topo, B: int, H: int, W: int, warm_steps
     gb = {k: v.to(dev) for k, v in batch.items() if k != "is_labeled"}
     sd = O.clone_state(sd0, requires_grad=False)
     net.train()
+    # training tiles are multiples of 16 (the reference trains on 256 x 256 crops): odd-sized inference cases warm the
+    # running statistics on a separate even-sized batch
+    wb = batch if warm_hw is None else O.synthetic_batch(B, xc, warm_hw[0], warm_hw[1], seed=11)
     for _ in range(warm_steps):                      # forward only: updates the running statistics on both sides
         with torch.no_grad():
-            net(gb["x_t1"], gb["x_t2"])
-            O.forward(mtype, sd, batch["x_t1"], batch["x_t2"], train=True, q=True)
+            net(wb["x_t1"].to(dev), wb["x_t2"].to(dev))
+            O.forward(mtype, sd, wb["x_t1"], wb["x_t2"], train=True, q=True)
     net.eval()
     with torch.no_grad():
         out = net(gb["x_t1"], gb["x_t2"])

@@ -287,6 +287,18 @@ def check_dgrad_bnbwd(n=4, H=32, W=32, cin=64, cout=128, G=2, seed=66, mode=0) -
     return res
 
 
+def check_pad_copy(n=2, h=8, w_=10, c=64, H=9, W=11, top=0, left=0, seed=90) -> dict:
+    """Up's centre pad (utils/networks.py:440-443): dense tensor placed in the upper half of a concat buffer."""
+    g = _gen(seed)
+    src = torch.randn(n, h, w_, c, device=DEV, generator=g).to(torch.bfloat16)
+    cat = torch.full((n, H, W, 2 * c), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.pad_copy(src, cat[..., c:], top, left)
+    ops.device_status()
+    ref = torch.nn.functional.pad(src.permute(0, 3, 1, 2), (left, W - w_ - left, top, H - h - top)).permute(0, 2, 3, 1)
+    ok = bool(torch.equal(cat[..., c:], ref)) and bool((cat[..., :c] == 3.0).all())
+    return {"ok": ok}
+
+
 def check_convt_fwd(n=2, h=16, w_=16, c=128, seed=5, tol=6e-3, pair=None) -> dict:
     """ConvTranspose2d(c, c, 2, stride=2) forward, scattered into the second half of a 2c concat buffer."""
     g = _gen(seed)
@@ -842,6 +854,8 @@ ALL_CHECKS = {
     "wgrad3x3_512_512_halo": lambda: check_wgrad3x3(4, 16, 16, 512, 512, sign=1, halo=1, splits=8, seed=73),
     "wgrad3x3_tiny_4x4": lambda: check_wgrad3x3(3, 4, 4, 512, 512, sign=1, halo=1, splits=2, seed=74),
     "wgrad3x3_ragged_24x40": lambda: check_wgrad3x3(2, 24, 40, 64, 128, sign=1, halo=1, splits=7, seed=75),
+    "pad_copy_bottom_right": check_pad_copy,
+    "pad_copy_centre_2px": lambda: check_pad_copy(3, 6, 6, 128, 8, 9, top=1, left=1, seed=91),
     "wgrad_convt": check_wgrad_convt,
     "wgrad_convt_tiny_4x4": lambda: check_wgrad_convt(3, 4, 4, 512, splits=2, seed=82),
     "wgrad_convt_64": lambda: check_wgrad_convt(2, 16, 32, 64, seed=81),

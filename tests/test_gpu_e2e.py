@@ -54,6 +54,11 @@ EVAL_CASES = {
     "siamese_eval": dict(mtype="siameseunet", cin=4, topo=SMALL, B=2, H=64, W=48),
     "dualstream_eval_full": dict(mtype="dualstreamunet", cin=6, topo=FULL, B=1, H=128, W=128),
     "whatevernet_eval_fusion_only": dict(mtype="whatevernet", cin=6, topo=SMALL, B=2, H=32, W=32),
+    # full tiles of arbitrary size (utils/evaluation.py:15-17): MaxPool floors odd levels (67 -> 33 -> 16 -> 8 -> 4,
+    # 45 -> 22 -> 11 -> 5 -> 2) and Up pads the up-sampled tensor back to the skip's size (utils/networks.py:440-443)
+    "siamese_eval_odd_67x45": dict(mtype="siameseunet", cin=4, topo=FULL, B=1, H=67, W=45, warm_hw=(64, 48)),
+    "dualstream_eval_odd_35x50": dict(mtype="dualstreamunet", cin=6, topo=SMALL, B=2, H=35, W=50, warm_hw=(32, 48)),
+    "unet_eval_odd_41x41": dict(mtype="unet", cin=6, topo=SMALL, B=1, H=41, W=41, warm_hw=(32, 32)),
 }
 
 
