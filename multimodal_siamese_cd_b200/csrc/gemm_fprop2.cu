@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         }
         fence_proxy_async_smem();
         named_barrier_sync(bar1, 128);
+        TR();
         if (t == 0) {
           if (p.out_mode == 0) {
             tma_store_5d(&mapO, sbuf, n0 + slab * 64, x0, y0, img, 0);  // clipped at the tensor bounds
@@ -451,9 +452,6 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
         }
         if (p.stats != nullptr) {
           // per-channel partial sums over the 128 staged (bf16-rounded) rows; conflict-free swizzled reads
-          const int cp = t & 31;  // channel pair inside the slab
-          const int rq = t >> 5;  // row quarter
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           if (p.bwd_r != nullptr) {
             // BatchNorm-backward sums of the gradient tile being stored: per channel (sum dy*m, sum dy*m*r) with the
             // ReLU mask m recomputed from the pre-BN values exactly as the dx pass does. Thread = 8 rows x 8 channels;
@@ -499,31 +497,48 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
                 dst[2 * jj + 1] = qq2[jj];
               }
             }
-            s0 = s1 = q0 = q1 = 0.f;
           } else {
-            for (int r = rq * 32; r < rq * 32 + 32; ++r) {
-              const uint32_t w =
-                  *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + ((cp & 3) << 2));
-              float lo = bf16_lo(w), hi = bf16_hi(w);
-              if (p.ragged) {
-                const bool ok = (r < p.tw * p.th) && (x0 + r % p.tw < p.W) && (y0 + r / p.tw < p.H);
-                lo = ok ? lo : 0.f;
-                hi = ok ? hi : 0.f;
+            // thread = 8 rows x 8 channels (one 16-byte read per row); the four row groups of a warp are combined with
+            // shuffles, the four warps through `red` — 8 shared-memory reads per thread instead of 32
+            const int oct = t & 7, rg = t >> 3;
+            const int tw_shift = p.tw == 16 ? 4 : 3;
+            float ss[8], qq2[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) ss[jj] = qq2[jj] = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = rg * 8 + u;
+              const uint4 dv = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((oct ^ (r & 7)) << 4));
+              const bool ok = !p.ragged || ((r < p.tw * p.th) && (x0 + (r & (p.tw - 1)) < p.W) && (y0 + (r >> tw_shift) < p.H));
+              const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+              for (int h2 = 0; h2 < 4; ++h2) {
+                const float lo = ok ? bf16_lo(dw[h2]) : 0.f, hi = ok ? bf16_hi(dw[h2]) : 0.f;
+                ss[2 * h2] += lo;
+                qq2[2 * h2] = fmaf(lo, lo, qq2[2 * h2]);
+                ss[2 * h2 + 1] += hi;
+                qq2[2 * h2 + 1] = fmaf(hi, hi, qq2[2 * h2 + 1]);
               }
-              s0 += lo;
-              q0 += lo * lo;
-              s1 += hi;
-              q1 += hi * hi;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              ss[jj] += __shfl_xor_sync(0xffffffffu, ss[jj], 8);
+              ss[jj] += __shfl_xor_sync(0xffffffffu, ss[jj], 16);
+              qq2[jj] += __shfl_xor_sync(0xffffffffu, qq2[jj], 8);
+              qq2[jj] += __shfl_xor_sync(0xffffffffu, qq2[jj], 16);
+            }
+            if ((t & 31) < 8) {
+              float* dst = red + (((t >> 5) * 64) + oct * 8) * 2;   // [warp][channel][sum, sum of squares]
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                dst[2 * jj] = ss[jj];
+                dst[2 * jj + 1] = qq2[jj];
+              }
             }
           }
-          if (p.bwd_r == nullptr) {
-            float* dst = red + ((rq * 64) + 2 * cp) * 2;
-            dst[0] = s0;
-            dst[1] = q0;
-            dst[2] = s1;
-            dst[3] = q1;
-          }
+          TR();
           named_barrier_sync(bar2, 128);
+          TR();
           if (t < 64 && real) {
             float s = 0.f, qq = 0.f;
 #pragma unroll

@@ -156,7 +156,9 @@ def check_conv3x3(n=2, H=32, W=32, cin=64, cout=64, bias=True, slice_in=False, s
         stats1 = torch.zeros_like(stats)
         ops.conv_gemm(0, 0, A, Bw, out1, bias=b, stats=stats1, halo=True, wide=False, pair=False)
         ops.device_status()
-        res["same_as_single"] = bool(torch.equal(out1, out.contiguous()) and torch.equal(stats1, stats))
+        # outputs bit-identical; the per-tile statistics are summed in a different (fixed) order by the two kernels
+        res["same_as_single"] = bool(torch.equal(out1, out.contiguous()) and
+                                     torch.allclose(stats1, stats, rtol=2e-5, atol=1e-4))
     got_sum = stats[..., 0].sum(0)
     got_sq = stats[..., 1].sum(0)
     o32 = out.float()
