@@ -121,6 +121,11 @@ int bn_bwd_nblk(int n_img, int H, int W, int C, int G) {
   const int lanes = 256 / (C / 8);
   long long nblk = units / (static_cast<long long>(lanes) * 32);
   const long long cap = (148 * 2 * 4) / G;
+  // small layers (16 x 16, 32 x 32 levels): down to 8 pixels per lane so that the launch still spreads over ~4 CTAs per
+  // SM — a 4 MB layer on 64 CTAs is a chain of dependent DRAM round trips, not a bandwidth problem
+  const long long want = (148 * 4) / G, fine = units / (static_cast<long long>(lanes) * 8);
+  static const bool fine_on = [] { const char* e = getenv("B200CD_BN_FINE"); return !(e && e[0] == '0'); }();
+  if (fine_on && nblk < want) nblk = fine < want ? fine : want;
   if (nblk > cap) nblk = cap;
   if (nblk < 1) nblk = 1;
   return static_cast<int>(nblk);

@@ -2060,6 +2060,9 @@ cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, c
     const long long npx = static_cast<long long>(n_img / G) * H * W;
     long long nblk = npx / ((256 / (C / 8)) * 16);
     const long long cap = (148 * 4 * 4) / G;
+    const long long want = (148 * 4) / G, fine = npx / ((256 / (C / 8)) * 4);  // small layers: >= 4 pixels per lane
+    static const bool fine_on = [] { const char* e = getenv("B200CD_BN_FINE_APPLY"); return !(e && e[0] == '0'); }();
+    if (fine_on && nblk < want) nblk = fine < want ? fine : want;
     nblk = nblk > cap ? cap : (nblk < 1 ? 1 : nblk);
     launch_k(bn_apply_px_kernel, dim3(dim3(static_cast<unsigned>(nblk), G)), dim3(256), 0, st, p);
     return cudaGetLastError();

@@ -19,10 +19,21 @@ Bw = ops.pack_weights(0, w)
 o = torch.empty(n, H, H, cout, device=dev, dtype=torch.bfloat16)
 stats = torch.empty(n * ops.conv_gemm_tiles(H, H), cout, 2, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+fused = "--bnbwd" in sys.argv   # input-gradient launch with the fused BatchNorm-backward sums
+if fused:
+    G = 1
+    r = torch.randn(n, H, H, cout, device=dev).to(torch.bfloat16)
+    scale = torch.rand(G, cout, device=dev) + 0.5
+    shift = torch.randn(G, cout, device=dev) * 0.3
+    rows, per_cta = ops.conv_stat_rows(n, H, H, cin, cout, G, mode=0)
+    sums = torch.empty(G, rows, cout, 2, device=dev)
 for i in range(3):
     if i == 2:
         e0.record()
-    ops.conv_gemm(0, 0, A, Bw, o, stats=stats, pair=True)
+    if fused:
+        ops.conv_gemm_bnbwd(0, A, Bw, o, r, scale, shift, sums, G)
+    else:
+        ops.conv_gemm(0, 0, A, Bw, o, stats=stats, pair=True)
 e1.record()
 torch.cuda.synchronize()
 ops.device_status()
