@@ -23,6 +23,9 @@ from . import ops
 from .engine import StepEngine
 
 
+_DEBUG_SKIP_ALLREDUCE = __import__("os").environ.get("B200CD_DEBUG_SKIP_ALLREDUCE", "0") == "1"
+
+
 @dataclass
 class _Term:
     z: torch.Tensor                 # logits [rows, 1, H, W] fp32 (static engine buffer)
@@ -101,7 +104,7 @@ class TrainStep:
                 self.dp = dist.group.WORLD
         elif dp_group is not None:
             self.dp = dp_group
-        self.grad_buckets = max(1, grad_buckets)
+        self.grad_buckets = max(1, int(__import__("os").environ.get("B200CD_GRAD_BUCKETS", grad_buckets)))
         self._comm_stream = torch.cuda.Stream(device=dev) if self.dp is not None else None
         self._bucket_plan = None
         self._bwd_graphs = None
@@ -184,6 +187,8 @@ class TrainStep:
             ev = torch.cuda.Event()
             ev.record(main)
             self._comm_stream.wait_event(ev)
+            if _DEBUG_SKIP_ALLREDUCE:   # measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1): wrong gradients
+                continue
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(eng.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=self.dp)
         main.wait_stream(self._comm_stream)
