@@ -329,6 +329,8 @@ def main() -> None:
 
         keys = {"supervised": ["y_change"], "dualtask": ["y_change", "y_sem_t1", "y_sem_t2"], "mmcr": ["y_change"]}[kind]
         host_batch = {"x_t1": host["x_t1"], "x_t2": host["x_t2"], "is_labeled": is_labeled, **{k: host[k] for k in keys}}
+        if os.environ.get("B200CD_DEBUG_E2E_RESIDENT") == "1":   # measurement aid: what the PCIe staging costs (invalid e2e)
+            host_batch = {k: (v.to(dev) if torch.is_tensor(v) and k != "is_labeled" else v) for k, v in host_batch.items()}
 
         def host_batches(n):           # the pinned host batch, staged host -> device again for every step
             for _ in range(n):

@@ -146,6 +146,22 @@ class GradArena:
     def view_of(self, p: nn.Parameter) -> torch.Tensor:
         return self.views[self._names[id(p)]]
 
+    def detached_copy_views(self) -> list:
+        """Per-parameter views (in `self.params` order, None for skipped parameters) of ONE fresh copy of the flat
+        buffer. autograd's AccumulateGrad deep-copies a returned gradient unless it holds the only reference to it —
+        for views kept in `self.views` that is one small copy kernel per parameter (~160 launches per DualStream step);
+        fresh views of a fresh copy are adopted as `p.grad` without further kernels, and `p.grad` never aliases the
+        buffer the next backward overwrites (gradient accumulation over several backward calls stays correct)."""
+        flat = self.flat.clone()
+        out = []
+        for n, p in self.params:
+            if n in self.skip:
+                out.append(None)
+            else:
+                o = self.offsets[n]
+                out.append(flat[o:o + p.numel()].view(p.shape))
+        return out
+
     def end_of(self, p: nn.Parameter) -> int:
         n = self._names[id(p)]
         return self.offsets[n] + (p.numel() + 3) // 4 * 4

@@ -121,10 +121,7 @@ class _StepFunction(torch.autograd.Function):
             touched.add(id(hd))
         eng.backward_static()
         parallel.allreduce_gradients(eng.grads.flat)   # SUM over replicas when data parallelism is enabled
-        grads = []
-        for name, p in eng.grads.params:
-            grads.append(None if name in eng.grads.skip else eng.grads.views[name])
-        return (None, None, None, *grads)
+        return (None, None, None, *eng.grads.detached_copy_views())
 
 
 class B200Net(nn.Module):

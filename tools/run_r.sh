@@ -1,3 +1,4 @@
-for cfg in "0 0" "1 0" "0 1" "0 0" "1 0" "0 1"; do set -- $cfg
-B200CD_BN_FINE=$1 B200CD_BN_FINE_APPLY=$2 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e 2>gpurun_out/bench_r.err | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); kb=d['kernel_breakdown']; print('FINE bwd=$1 apply=$2 VALUE', round(d['value'],1), round(d['ms_per_step'],3), 'bn_bwd', kb['bn_bwd']['ms'], 'bn_apply', kb['bn_apply']['ms'], 'bn_stats', kb['bn_stats']['ms'])"; done
+python -m pytest tests -m gpu -q -x -k "e2e or step or train or eval or dropin or adamw" > gpurun_out/pytest_r.log 2>&1; tail -3 gpurun_out/pytest_r.log
+for r in 0 1; do python bench.py --steps 60 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(\"value\", round(d[\"value\"],1), round(d[\"ms_per_step\"],3), \"e2e\", round(d[\"e2e\"][\"value\"],1), round(d[\"e2e\"][\"ms_per_step\"],3))"; done
+python tools/host_probe.py dualstream 2>&1 | head -2
