@@ -84,3 +84,14 @@ def test_training_loop_tracks_oracle(optimizer):
     # weights after six Adam steps: every element has moved by ~6 * lr whatever the size of its gradient, so elements
     # whose gradient is at the bf16 noise level may have moved the other way; measured 0.085 on the worst tensor
     assert r["max_param_rel"] <= 0.15, r
+
+
+def test_baseline_size_properties():
+    """BASELINE config #2 at full size (DualStreamUNet, 16 pairs of 256 x 256): determinism across eager / graph replay,
+    fused loss = the formula on the step's own logits, every parameter gets a finite non-zero gradient."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = E.run_baseline_size_properties()
+    assert r["deterministic"], r
+    assert r["loss_vs_formula"] <= 1e-5, r
+    assert r["all_finite"] and not r["zero_grad_tensors"] and r["prebn_bias_grad_max"] == 0.0, r
