@@ -34,6 +34,16 @@ FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != 
 # joined before each batched reduce) so that the HBM-bound BatchNorm-backward kernels of the next layers could run
 # under them. Measured neutral on B200 (9.71-9.76 ms either way): a 198 KB-shared-memory GEMM CTA and the elementwise
 # CTAs do not share an SM, so the kernels still alternate. Off by default.
+# The two U-Net trunks of DualStreamUNet / WhateverNet / WhateverNet2 are independent until the fusion head: with
+# B200CD_BRANCH_STREAMS=1 (default) the second trunk's launches go to a second stream (forked after the weight packing /
+# the head gradients, joined before the head / every batched split reduce), so the ramp-up, tail and launch gaps of one
+# trunk's kernels are filled by the other's. Each trunk has its own statistics / reduction workspaces.
+# Measured (same box): DualStream B=16 9.95 -> 9.62 ms (+3.5 %, value and e2e), WhateverNet B=16 +3.7 %, WhateverNet
+# B=64 -0.9 % (long launches have no tails worth filling, and two concurrent working sets share the L2) — so "1" enables
+# it only below BRANCH_MAX_PIXELS full-resolution pixels per trunk launch; "2" always, "0" never.
+_BRANCH_MODE = __import__("os").environ.get("B200CD_BRANCH_STREAMS", "1")
+BRANCH_STREAMS = _BRANCH_MODE != "0"
+BRANCH_MAX_PIXELS = 4 << 20
 WGRAD_SIDE_STREAM = __import__("os").environ.get("B200CD_WGRAD_SIDE_STREAM", "0") == "1"
 # transposed-conv bias gradient from the per-CTA channel sums of the dgrad launch that writes the concat-buffer gradient
 UP_BIAS_FROM_STATS = __import__("os").environ.get("B200CD_UP_BIAS_FROM_STATS", "1") != "0"
@@ -77,6 +87,7 @@ class Stage:
     stat_per_cta: bool = False
     bwd_sums: Optional[torch.Tensor] = None   # [G][rows][C][2]: BatchNorm-backward sums accumulated by the dgrad epilogue
     bwd_sum_rows: int = 0
+    branch: int = 0          # trunk (stream) the stage belongs to
 
     @property
     def cin(self) -> int:
@@ -102,6 +113,7 @@ class UpConv:
     # inference on odd-sized levels: the 2h x 2w output goes to `dense`, then ops.pad_copy centres it in `out`
     dense: Optional[torch.Tensor] = None
     pad: tuple = (0, 0)
+    branch: int = 0
 
 
 @dataclass
@@ -185,6 +197,13 @@ class StepEngine:
         self.bwd_ops: list[Callable[[], None]] = []
         self._side_stream = None
         self._side_dirty = False
+        self._cur_branch = 0                      # trunk being built (0, or 1 for the second stream's trunk)
+        self.fwd_branch: list[int] = []           # per forward op: 0 / 1 = trunk, -1 = needs both trunks (heads)
+        self.bwd_branch: list[int] = []
+        self._branch_stream = None
+        self._branch_main = None
+        self._branch_active = False
+        self.branch_streams = BRANCH_STREAMS      # bench.profile_step turns it off to time launches one by one
         self.pack_fwd: list[Callable[[], None]] = []
         self.pack_bwd: list[Callable[[], None]] = []
         self.bwd_marks: list[int] = []  # per backward op: length of the flat-gradient prefix complete after it
@@ -230,6 +249,7 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------------
     def _stage(self, name, conv, bn, in_view, n_img, H, W, G, order_rev=False, first=False) -> Stage:
         st = Stage(name, conv, bn, n_img, H, W, G, order_rev, first, in_view)
+        st.branch = self._cur_branch
         C = conv.out_channels
         if C % 64 != 0 or (not first and conv.in_channels % 64 != 0):
             raise ValueError(f"b200cd engine: channel counts must be multiples of 64 ({name}: {conv.in_channels}->{C})")
@@ -279,6 +299,7 @@ class StepEngine:
         kpad = _kpad(cin)
         cols = self._new(n_img, H, W, kpad)
         self.fwd_ops.append(lambda: ops.pack_input(self.x_t1, self.x_t2, c_lo, nc, 0 if siamese else 1, kpad, out=cols))
+        self.fwd_branch.append(self._cur_branch)
         levels = []
         s1, s2 = self._double_conv(f"{tag}.inc", inc.conv, cols, n_img, H, W, G, first=True)
         levels.append(s2)
@@ -342,6 +363,7 @@ class StepEngine:
                 assert "a" not in skip_stage.outs, "plain skip is written straight into the concat buffer"
                 skip_stage.outs["a"] = cat[..., :c]
             uc = UpConv(f"{tag}.{uname}.up", up.up, x, cat[..., c:])
+            uc.branch = self._cur_branch
             hx, wx = x.shape[1], x.shape[2]
             if (2 * hx, 2 * wx) != (Hs, Ws):
                 # MaxPool floored an odd level: the reference pads the up-sampled tensor to the skip's size with
@@ -421,8 +443,10 @@ class StepEngine:
         elif t in ("dualstreamunet", "whatevernet2"):
             lv1 = self._encoder("s1", net.inc_stream1, net.encoder_stream1, 0, ns1, siamese=False)
             d1 = self._decoder("s1.dec", net.decoder_stream1, lv1, "plain")
+            self._cur_branch = 1
             lv2 = self._encoder("s2", net.inc_stream2, net.encoder_stream2, ns1, ns2, siamese=False)
             d2 = self._decoder("s2.dec", net.decoder_stream2, lv2, "plain")
+            self._cur_branch = 0
             if t == "dualstreamunet":
                 self.outputs = [(self._head("outc", net.outc.conv, [d1, d2]), None)]
             else:
@@ -433,8 +457,10 @@ class StepEngine:
         elif t == "whatevernet":
             lv1 = self._encoder("s1", net.inc_stream1, net.encoder_stream1, 0, ns1, siamese=True)
             d1 = self._decoder("s1.dec", net.decoder_stream1, lv1, "diff")
+            self._cur_branch = 1
             lv2 = self._encoder("s2", net.inc_stream2, net.encoder_stream2, ns1, ns2, siamese=True)
             d2 = self._decoder("s2.dec", net.decoder_stream2, lv2, "diff")
+            self._cur_branch = 0
             hf = self._head("outc_fusion", net.outc_fusion.conv, [d1, d2])
             h1 = self._head("outc_stream1", net.outc_stream1.conv, [d1])
             h2 = self._head("outc_stream2", net.outc_stream2.conv, [d2])
@@ -456,17 +482,18 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------------
     def _alloc_ws(self) -> None:
         n = self._ws_need
-        self.ws_stats = self._new(max(n["stats"], 2), dtype=torch.float32)
-        self.ws_stats2 = self._new(max(n["stats2"], 2), dtype=torch.float64)
+        nbr = 2 if any(st.branch == 1 for st in self.stages) else 1   # one set of scratch buffers per trunk
+        self.ws_stats = [self._new(max(n["stats"], 2), dtype=torch.float32) for _ in range(nbr)]
+        self.ws_stats2 = [self._new(max(n["stats2"], 2), dtype=torch.float64) for _ in range(nbr)]
         if self.train:
             self.ws_wgrad = self._new(max(n["wgrad"], 4), dtype=torch.float32)
             for group in getattr(self, "_flush_groups", []):
                 jobs = [(self.ws_wgrad.narrow(0, off, splits * stride), gw, splits, stride, layout, d0, d1, taps, s2)
                         for (_, off, gw, splits, stride, layout, d0, d1, taps, s2) in group]
                 self._reduce_tables.append(ops.make_reduce_jobs(jobs, self.device))
-            self.ws_bnbwd = self._new(max(n["bnbwd"], 4), dtype=torch.float32)
-            self.ws_colsum = self._new(max(n["colsum"], 4), dtype=torch.float32)
-            self.ws_upstats = self._new(max(n.get("upstats", 0), 4), dtype=torch.float32)
+            self.ws_bnbwd = [self._new(max(n["bnbwd"], 4), dtype=torch.float32) for _ in range(nbr)]
+            self.ws_colsum = [self._new(max(n["colsum"], 4), dtype=torch.float32) for _ in range(nbr)]
+            self.ws_upstats = [self._new(max(n.get("upstats", 0), 4), dtype=torch.float32) for _ in range(nbr)]
 
     # ------------------------------------------------------------------------------------------------
     # forward emission: stages were created in execution order, transposed convs are interleaved by name order
@@ -491,15 +518,16 @@ class StepEngine:
         outs = st.outs
 
         def run():
-            stats = eng.ws_stats if train else None
+            stats = eng.ws_stats[st.branch] if train else None
             ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats, stat_groups=sg)
-            ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2, bn.weight, bn.bias, bn.running_mean,
+            ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2[st.branch], bn.weight, bn.bias, bn.running_mean,
                          bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
                          st.order_rev, st.mean, st.invstd, st.scale, st.shift)
             ops.bn_apply(st.r, st.scale, st.shift, st.G, bool(outs.get("diff", False)), a=outs.get("a"),
                          a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"), pool_idx=outs.get("pool_idx"))
 
         eng.fwd_ops.append(run)
+        eng.fwd_branch.append(st.branch)
 
     def _emit_forward(self) -> None:
         up_by_first_stage = {id(s1): uc for (uc, s1, s2) in self._up_plan}
@@ -512,17 +540,20 @@ class StepEngine:
                     self._pack_specs.append((3, uc.up.weight, uc.Wf, 0))
                 if uc.dense is None:
                     self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
+                    self.fwd_branch.append(uc.branch)
                 else:
                     def run_up(uc=uc):
                         ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.dense, bias=uc.up.bias)
                         ops.pad_copy(uc.dense, uc.out, uc.pad[0], uc.pad[1])
                     self.fwd_ops.append(run_up)
+                    self.fwd_branch.append(uc.branch)
             self._emit_stage_fwd(st)
         for hd in self.heads:
             def run(hd=hd):
                 a1 = hd.inputs[1] if len(hd.inputs) > 1 else None
                 ops.head_fwd(hd.inputs[0], a1, hd.conv.weight.view(-1), hd.conv.bias, hd.logits)
             self.fwd_ops.append(run)
+            self.fwd_branch.append(-1)
 
     # ------------------------------------------------------------------------------------------------
     # backward emission: reverse order of the forward stages
@@ -639,7 +670,7 @@ class StepEngine:
                 eng._ws_need["upstats"] = max(eng._ws_need.get("upstats", 0), rows * st.cin * 2)
 
         def run():
-            ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd, ggam, gbet,
+            ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd[st.branch], ggam, gbet,
                        st.dr, sums=st.bwd_sums, sum_rows=st.bwd_sum_rows)
             ws = eng.ws_wgrad.narrow(0, off, size)
             # input gradient first (the next layer's BatchNorm backward waits for it), then the weight gradient on the
@@ -650,7 +681,7 @@ class StepEngine:
                 elif up_rows:
                     # d_in is the concat-buffer gradient of an Up: its per-channel pixel sums (upper half = the
                     # transposed-conv bias gradient) come out of this launch's per-CTA statistics
-                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats, stat_groups=1)
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats[st.branch], stat_groups=1)
                 else:
                     ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
             with eng._side():
@@ -663,6 +694,7 @@ class StepEngine:
                     ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
 
         eng.bwd_ops.append(run)
+        eng.bwd_branch.append(st.branch)
         eng.bwd_marks.append(g.end_of(conv.weight))
 
     def _emit_up_bwd(self, uc: UpConv) -> None:
@@ -685,9 +717,9 @@ class StepEngine:
 
         def run():
             if uc.bias_rows:
-                ops.stat_rowsum(eng.ws_upstats, uc.bias_rows, 2 * c, c, c, gb)
+                ops.stat_rowsum(eng.ws_upstats[uc.branch], uc.bias_rows, 2 * c, c, c, gb)
             else:
-                ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum, gb)
+                ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum[uc.branch], gb)
             if prod is not None:
                 ops.conv_gemm_bnbwd(2, uc.d_out, uc.Wd, uc.d_x, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
             else:
@@ -696,6 +728,7 @@ class StepEngine:
                 ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
 
         eng.bwd_ops.append(run)
+        eng.bwd_branch.append(uc.branch)
         eng.bwd_marks.append(g.end_of(uc.up.weight))
 
     def _emit_backward(self) -> None:
@@ -720,9 +753,10 @@ class StepEngine:
             def run(hd=hd, C=C, npix=npix, nblk=nblk, gw=gw, gb=gb):
                 dz = hd.dz.view(-1)
                 for i, a in enumerate(hd.inputs):
-                    ops.colsum(a, dz, npix, nblk, self.ws_colsum, gw[i * C:(i + 1) * C])
-                ops.colsum(None, dz, npix, nblk, self.ws_colsum, gb)
+                    ops.colsum(a, dz, npix, nblk, self.ws_colsum[0], gw[i * C:(i + 1) * C])
+                ops.colsum(None, dz, npix, nblk, self.ws_colsum[0], gb)
             self.bwd_ops.append(run)
+            self.bwd_branch.append(-1)
             self.bwd_marks.append(g.end_of(hd.conv.bias))
         up_by_first_stage = {id(s1): uc for (uc, s1, s2) in self._up_plan}
         for st in reversed(self.stages):
@@ -761,6 +795,7 @@ class StepEngine:
             def run(orig=orig, fi=fi):
                 orig()
                 self._join_side()
+                self._join_branches()     # the group may hold layers of both trunks
                 tab, nj, blocks, nbytes = self._reduce_tables[fi]
                 ops.wgrad_reduce_batched(tab, nj, blocks, nbytes)
 
@@ -778,18 +813,62 @@ class StepEngine:
     # ------------------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------------------
+    def _two_streams(self, branches: list) -> bool:
+        if not (self.branch_streams and self.device.type == "cuda" and any(b == 1 for b in branches)):
+            return False
+        px = max(st.n_img * st.H * st.W for st in self.stages)
+        return _BRANCH_MODE == "2" or px <= BRANCH_MAX_PIXELS
+
+    def _join_branches(self) -> None:
+        """The current stream waits for everything queued so far on the other trunk's stream (no-op when the plan runs
+        on one stream)."""
+        if self._branch_active:
+            cur = torch.cuda.current_stream()
+            other = self._branch_stream if cur != self._branch_stream else self._branch_main
+            cur.wait_stream(other)
+
+    def _run_ops(self, ops_list: list, branches: list) -> None:
+        """Run plan ops; trunk-1 ops go to the branch stream, ops that need both trunks (-1) run on the main stream
+        after a join. Forks after the first op(s) that precede any trunk work, joins at the end."""
+        if not self._two_streams(branches):
+            for f in ops_list:
+                f()
+            return
+        if self._branch_stream is None:
+            self._branch_stream = torch.cuda.Stream(device=self.device)
+        main, side = torch.cuda.current_stream(), self._branch_stream
+        self._branch_main = main
+        side.wait_stream(main)                       # fork: everything queued so far is visible to both trunks
+        self._branch_active = True
+        try:
+            for b, f in zip(branches, ops_list):
+                if b == 1:
+                    with torch.cuda.stream(side):
+                        f()
+                elif b == 0:
+                    f()
+                else:                                # needs both trunks, and later trunk ops need it
+                    main.wait_stream(side)
+                    f()
+                    side.wait_stream(main)
+        finally:
+            self._branch_active = False
+        main.wait_stream(side)                       # join
+
+    def run_bwd_range(self, o0: int, o1: int) -> None:
+        """Backward ops [o0, o1) (a data-parallel caller runs the plan in segments, step.py)."""
+        self._run_ops(self.bwd_ops[o0:o1], self.bwd_branch[o0:o1])
+        self._join_side()
+
     def _run_fwd_eager(self) -> None:
         for f in self.pack_fwd:
             f()
-        for f in self.fwd_ops:
-            f()
+        self._run_ops(self.fwd_ops, self.fwd_branch)
 
     def _run_bwd_eager(self) -> None:
         for f in self.pack_bwd:
             f()
-        for f in self.bwd_ops:
-            f()
-        self._join_side()
+        self.run_bwd_range(0, len(self.bwd_ops))
 
     def forward(self, x_t1: torch.Tensor, x_t2: torch.Tensor) -> None:
         """Copies the inputs into the static buffers and runs the forward plan; logits land in head.logits."""

@@ -171,9 +171,7 @@ class TrainStep:
             f()
         for bi, (o0, o1, g0, g1) in enumerate(self._bucket_plan):
             def seg(o0=o0, o1=o1):
-                for f in eng.bwd_ops[o0:o1]:
-                    f()
-                eng._join_side()   # weight-gradient GEMMs forked inside the segment (engine.WGRAD_SIDE_STREAM)
+                eng.run_bwd_range(o0, o1)   # forks / joins the second trunk's stream inside the segment
             if eng.use_graphs and self._steps >= 2:
                 if self._bwd_graphs[bi] is None:
                     torch.cuda.synchronize()
