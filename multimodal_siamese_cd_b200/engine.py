@@ -88,6 +88,7 @@ class Stage:
     bwd_sums: Optional[torch.Tensor] = None   # [G][rows][C][2]: BatchNorm-backward sums accumulated by the dgrad epilogue
     bwd_sum_rows: int = 0
     branch: int = 0          # trunk (stream) the stage belongs to
+    join_before_bwd: bool = False   # its backward needs the gradients of both branches (first encoder op after two decoders)
 
     @property
     def cin(self) -> int:
@@ -114,6 +115,7 @@ class UpConv:
     dense: Optional[torch.Tensor] = None
     pad: tuple = (0, 0)
     branch: int = 0
+    fork_before_fwd: bool = False   # first op of a branch that consumes what the main stream produced so far
 
 
 @dataclass
@@ -434,8 +436,16 @@ class StepEngine:
             self.outputs = [(self._head("outc", net.outc.conv, [d]), None)]
         elif t == "dtsiameseunet":
             lv = self._encoder("s", net.inc, net.encoder, 0, cfg.MODEL.IN_CHANNELS, siamese=True)
-            dc = self._decoder("s.dec_change", net.decoder_change, lv, "diff")
+            # the two decoders are independent between the shared encoder and the heads: decoder_sem is branch 1, forked
+            # right after the encoder (its ops precede decoder_change's in the plan so that the fork does not wait for
+            # them) and joined before the heads (forward) / before the encoder's backward
+            n_up = len(self.upconvs)
+            self._cur_branch = 1
             ds = self._decoder("s.dec_sem", net.decoder_sem, lv, "copy", order_rev=True)
+            self._cur_branch = 0
+            self.upconvs[n_up].fork_before_fwd = True
+            lv[-1].join_before_bwd = True
+            dc = self._decoder("s.dec_change", net.decoder_change, lv, "diff")
             hc = self._head("outc_change", net.outc_change.conv, [dc])
             hs = self._head("outc_sem", net.outc_sem.conv, [ds])
             B = self.B
@@ -540,13 +550,13 @@ class StepEngine:
                     self._pack_specs.append((3, uc.up.weight, uc.Wf, 0))
                 if uc.dense is None:
                     self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
-                    self.fwd_branch.append(uc.branch)
+                    self.fwd_branch.append(10 if uc.fork_before_fwd else uc.branch)
                 else:
                     def run_up(uc=uc):
                         ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.dense, bias=uc.up.bias)
                         ops.pad_copy(uc.dense, uc.out, uc.pad[0], uc.pad[1])
                     self.fwd_ops.append(run_up)
-                    self.fwd_branch.append(uc.branch)
+                    self.fwd_branch.append(10 if uc.fork_before_fwd else uc.branch)
             self._emit_stage_fwd(st)
         for hd in self.heads:
             def run(hd=hd):
@@ -694,7 +704,7 @@ class StepEngine:
                     ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
 
         eng.bwd_ops.append(run)
-        eng.bwd_branch.append(st.branch)
+        eng.bwd_branch.append(-10 if st.join_before_bwd else st.branch)
         eng.bwd_marks.append(g.end_of(conv.weight))
 
     def _emit_up_bwd(self, uc: UpConv) -> None:
@@ -814,7 +824,7 @@ class StepEngine:
     # execution
     # ------------------------------------------------------------------------------------------------
     def _two_streams(self, branches: list) -> bool:
-        if not (self.branch_streams and self.device.type == "cuda" and any(b == 1 for b in branches)):
+        if not (self.branch_streams and self.device.type == "cuda" and any(b in (1, 10) for b in branches)):
             return False
         px = max(st.n_img * st.H * st.W for st in self.stages)
         return _BRANCH_MODE == "2" or px <= BRANCH_MAX_PIXELS
@@ -828,8 +838,9 @@ class StepEngine:
             cur.wait_stream(other)
 
     def _run_ops(self, ops_list: list, branches: list) -> None:
-        """Run plan ops; trunk-1 ops go to the branch stream, ops that need both trunks (-1) run on the main stream
-        after a join. Forks after the first op(s) that precede any trunk work, joins at the end."""
+        """Run plan ops. Branch codes: 0 main stream; 1 branch stream; 10 branch stream after waiting for the main
+        stream (first op of a branch that consumes main-stream results); -10 main stream after waiting for the branch
+        stream; -1 needs both (join, run on main, fork again: heads). Forks at the start, joins at the end."""
         if not self._two_streams(branches):
             for f in ops_list:
                 f()
@@ -842,10 +853,15 @@ class StepEngine:
         self._branch_active = True
         try:
             for b, f in zip(branches, ops_list):
-                if b == 1:
+                if b == 1 or b == 10:
+                    if b == 10:                      # consumes what the main stream has produced so far
+                        side.wait_stream(main)
                     with torch.cuda.stream(side):
                         f()
                 elif b == 0:
+                    f()
+                elif b == -10:                       # main-stream op that consumes the branch stream's results
+                    main.wait_stream(side)
                     f()
                 else:                                # needs both trunks, and later trunk ops need it
                     main.wait_stream(side)
