@@ -83,6 +83,39 @@ def test_parameter_counts_and_plan(mtype, cin, n_params):
         assert 1 <= len(st.srcs) <= 3, st.name
 
 
+@pytest.mark.parametrize("mtype,two", [("unet", False), ("siameseunet", False), ("dualstreamunet", True),
+                                       ("dtsiameseunet", True), ("whatevernet", True), ("whatevernet2", True)])
+def test_branch_plan_respects_dependencies(mtype, two):
+    """Two-stream plans (engine._run_ops): one branch code per op; a branch-1 op may only consume main-stream results
+    that were queued before its branch was forked, and main-stream ops that consume branch-1 results sit behind a join."""
+    net = networks.create_network(synthetic_cfg(mtype, in_channels=6 if mtype != "siameseunet" else 4))
+    eng = StepEngine(net.module, 2, 64, 64, True, torch.device("meta"))
+    assert len(eng.fwd_branch) == len(eng.fwd_ops) and len(eng.bwd_branch) == len(eng.bwd_ops)
+    assert set(eng.fwd_branch) <= {0, 1, 10, -1} and set(eng.bwd_branch) <= {0, 1, -10, -1}
+    assert any(b in (1, 10) for b in eng.fwd_branch) == two
+    assert eng.fwd_branch[-1] == -1 and eng.bwd_branch[0] == -1            # heads: last forward, first backward
+    if not two:
+        return
+    if mtype == "dtsiameseunet":
+        # forward: encoder (0) ... fork (10) ... decoder_sem (1) ... decoder_change (0) ... heads (-1)
+        i10 = eng.fwd_branch.index(10)
+        assert all(b == 0 for b in eng.fwd_branch[:i10]), "everything before the fork is the shared encoder"
+        assert eng.fwd_branch.count(10) == 1
+        after = [b for b in eng.fwd_branch[i10 + 1:] if b != -1]
+        first0 = after.index(0)
+        assert all(b == 1 for b in after[:first0]) and all(b == 0 for b in after[first0:]), \
+            "decoder_sem's ops directly follow the fork, decoder_change's come after them"
+        # backward: heads, the two decoders, then ONE join in front of the first encoder op, encoder on the main stream
+        j = eng.bwd_branch.index(-10)
+        assert eng.bwd_branch.count(-10) == 1 and all(b == 0 for b in eng.bwd_branch[j + 1:])
+        n_enc = sum(1 for st in eng.stages if st.name.startswith("s.inc") or st.name.startswith("s.down"))
+        assert len(eng.bwd_branch) - j == n_enc
+    else:
+        # two trunks: no cross-trunk dependency before the heads, so no fork/join codes at all
+        assert 10 not in eng.fwd_branch and -10 not in eng.bwd_branch
+        assert sum(b == 1 for b in eng.fwd_branch) == sum(b == 0 for b in eng.fwd_branch)
+
+
 def test_bucket_plan_covers_gradient_buffer_once():
     from multimodal_siamese_cd_b200.step import TrainStep
     net = networks.create_network(synthetic_cfg("dtsiameseunet", in_channels=6)).module
