@@ -220,29 +220,57 @@ __global__ void pack_weights_kernel(int mode, const float* __restrict__ w, __nv_
 constexpr int kPackTile = 32;
 constexpr int kPackGenericPerBlock = 2048;
 
-__device__ __forceinline__ void pack_tile_store(int mode, const float* tile, int pitch, int taps, __nv_bfloat16* out,
-                                                int d0, int d1, int r0, int c0) {
-  // tile[r][cl * taps + tap] = w[r0 + r][c0 + cl][tap]
-  const int n = kPackTile * kPackTile * taps;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int fast = i & 31;
-    const int rest = i >> 5;
-    const int tap = rest % taps;
-    const int slow = rest / taps;
+template <int TAPS>
+__device__ __forceinline__ void pack_tile_store(int mode, const float* tile, __nv_bfloat16* out, int d0, int d1, int r0,
+                                                int c0) {
+  // tile[r][cl * TAPS + tap] = w[r0 + r][c0 + cl][tap]; TAPS is a compile-time constant so that the index arithmetic
+  // below is multiply-shift, not integer division (the kernel was instruction bound, not bandwidth bound)
+  constexpr int pitch = kPackTile * TAPS + 1;
+  constexpr int n2 = kPackTile * kPackTile * TAPS / 2;   // two consecutive outputs (one 4-byte store) per iteration
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n2; i += 256) {
+    const int fast = (i & 15) * 2;
+    const int rest = i >> 4;
+    const int tap = rest % TAPS;
+    const int slow = rest / TAPS;
+    float v0, v1;
+    long long o;
     if (mode == 0) {         // out[co = d0][tap][ci = d1]
-      out[(static_cast<long long>(r0 + slow) * taps + tap) * d1 + c0 + fast] =
-          __float2bfloat16_rn(tile[slow * pitch + fast * taps + tap]);
+      o = (static_cast<long long>(r0 + slow) * TAPS + tap) * d1 + c0 + fast;
+      v0 = tile[slow * pitch + fast * TAPS + tap];
+      v1 = tile[slow * pitch + (fast + 1) * TAPS + tap];
     } else if (mode == 1) {  // out[ci = d1][tap'][co = d0] = w[co][ci][8 - tap']
-      out[(static_cast<long long>(c0 + slow) * taps + tap) * d0 + r0 + fast] =
-          __float2bfloat16_rn(tile[fast * pitch + slow * taps + (taps - 1 - tap)]);
+      o = (static_cast<long long>(c0 + slow) * TAPS + tap) * d0 + r0 + fast;
+      v0 = tile[fast * pitch + slow * TAPS + (TAPS - 1 - tap)];
+      v1 = tile[(fast + 1) * pitch + slow * TAPS + (TAPS - 1 - tap)];
     } else if (mode == 3) {  // out[tap * d1 + co][ci = d0]
-      out[(static_cast<long long>(tap) * d1 + c0 + slow) * d0 + r0 + fast] =
-          __float2bfloat16_rn(tile[fast * pitch + slow * taps + tap]);
+      o = (static_cast<long long>(tap) * d1 + c0 + slow) * d0 + r0 + fast;
+      v0 = tile[fast * pitch + slow * TAPS + tap];
+      v1 = tile[(fast + 1) * pitch + slow * TAPS + tap];
     } else {                 // mode 4: out[ci = d0][tap * d1 + co]
-      out[static_cast<long long>(r0 + slow) * (taps * d1) + static_cast<long long>(tap) * d1 + c0 + fast] =
-          __float2bfloat16_rn(tile[slow * pitch + fast * taps + tap]);
+      o = static_cast<long long>(r0 + slow) * (TAPS * d1) + static_cast<long long>(tap) * d1 + c0 + fast;
+      v0 = tile[slow * pitch + fast * TAPS + tap];
+      v1 = tile[slow * pitch + (fast + 1) * TAPS + tap];
     }
+    *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(v0, v1);   // o is even, out 4-byte aligned
   }
+}
+
+template <int TAPS>
+__device__ __forceinline__ void pack_tile(const PackJob& j, int lb, float* tile) {
+  constexpr int pitch = kPackTile * TAPS + 1;
+  constexpr int run = kPackTile * TAPS;
+  const int tiles1 = j.d1 / kPackTile;
+  const int r0 = (lb / tiles1) * kPackTile, c0 = (lb % tiles1) * kPackTile;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kPackTile * run; i += 256) {
+    const int r = i / run, k = i - r * run;
+    tile[r * pitch + k] = __ldg(j.w + (static_cast<long long>(r0 + r) * j.d1 + c0) * TAPS + k);
+  }
+  __syncthreads();
+  pack_tile_store<TAPS>(j.mode, tile, reinterpret_cast<__nv_bfloat16*>(j.out), j.d0, j.d1, r0, c0);
+  if (j.out2 != nullptr)
+    pack_tile_store<TAPS>(j.mode2, tile, reinterpret_cast<__nv_bfloat16*>(j.out2), j.d0, j.d1, r0, c0);
 }
 
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
@@ -274,19 +302,8 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     }
     return;
   }
-  const int taps = (j.mode == 0 || j.mode == 1) ? 9 : 4;
-  const int pitch = kPackTile * taps + 1;
-  const int tiles1 = j.d1 / kPackTile;
-  const int r0 = (lb / tiles1) * kPackTile, c0 = (lb % tiles1) * kPackTile;
-  const int run = kPackTile * taps;
-  for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
-    const int r = i / run, k = i - r * run;
-    tile[r * pitch + k] = __ldg(j.w + (static_cast<long long>(r0 + r) * j.d1 + c0) * taps + k);
-  }
-  __syncthreads();
-  pack_tile_store(j.mode, tile, pitch, taps, reinterpret_cast<__nv_bfloat16*>(j.out), j.d0, j.d1, r0, c0);
-  if (j.out2 != nullptr)
-    pack_tile_store(j.mode2, tile, pitch, taps, reinterpret_cast<__nv_bfloat16*>(j.out2), j.d0, j.d1, r0, c0);
+  if (j.mode == 0 || j.mode == 1) pack_tile<9>(j, lb, tile);
+  else pack_tile<4>(j, lb, tile);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -155,6 +155,7 @@ def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, i
         mode2, out2 = (spec[4], spec[5]) if len(spec) > 4 else (0, None)
         assert w.dtype == torch.float32 and w.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
         assert out2 is None or (out2.dtype == torch.bfloat16 and out2.is_contiguous() and out2.numel() == out.numel())
+        assert out.data_ptr() % 4 == 0 and (out2 is None or out2.data_ptr() % 4 == 0), "packed operands are written 4 bytes at a time"
         arr[i] = (w.data_ptr(), out.data_ptr(), 0 if out2 is None else out2.data_ptr(), mode, mode2, w.shape[0],
                   w.shape[1], kpad, 0, blocks)
         nb = lib.b200cd_pack_job_blocks(mode, w.shape[0], w.shape[1], kpad)
