@@ -255,3 +255,82 @@ def run_baseline_size_properties(mtype: str = "dualstreamunet", cin: int = 6, B:
     res["prebn_bias_grad_max"] = max(float(g.views[n].abs().max()) for n, _ in g.params if is_prebn_bias(n))
     net.module.release_engines()
     return res
+
+
+def run_golden_train_case(fixture_path) -> dict:
+    """The drop-in step on the GPU against a fixture written by the UNMODIFIED reference (oracle/make_golden.py): same
+    seed-7 default init, same synthetic batch; logits and loss compared directly with the reference's fp32 values."""
+    fix = torch.load(fixture_path, weights_only=False)
+    name, mtype, cin, topo, B, kind, H, W, alpha = fix["case"]
+    dev = torch.device("cuda", 0)
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg).to(dev).train()
+    batch = O.synthetic_batch(B, 6 if mtype in TWO_STREAM else cin, H, W, seed=7)
+    gb = {k: v.to(dev) for k, v in batch.items() if k != "is_labeled"}
+    crit = loss_functions.get_criterion("PowerJaccardLoss")
+    outs = net(gb["x_t1"], gb["x_t2"])
+    if kind == "supervised":
+        loss, out_list = crit(outs, gb["y_change"]), [outs]
+    elif kind == "dualtask":
+        c, s1, s2 = outs
+        loss = (crit(c, gb["y_change"]) + (crit(s1, gb["y_sem_t1"]) + crit(s2, gb["y_sem_t2"])) / 2) / 2
+        out_list = [c, s1, s2]
+    else:
+        f, s1, s2 = outs
+        lab, y = batch["is_labeled"], gb["y_change"]
+        unl = torch.logical_not(lab)
+        loss = alpha * (crit(f[lab,], y[lab,]) + crit(s1[lab,], y[lab,]) + crit(s2[lab,], y[lab,])) / 3 + \
+            (1 - alpha) * crit(s1[unl,], torch.sigmoid(s2)[unl,])
+        out_list = [f, s1, s2]
+    loss.backward()
+    torch.cuda.synchronize()
+    res = {"loss_diff": abs(loss.item() - fix["loss"].item()),
+           "logits_rel": max(rel(o, g) for o, g in zip(out_list, fix["outs"]))}
+    g_rel = []
+    for k, p in net.named_parameters():
+        ref = fix["grads"][k]
+        if ref is None:
+            assert p.grad is None, k
+            continue
+        if is_prebn_bias(k[len("module."):] if k.startswith("module.") else k):
+            continue                                   # analytically zero; the reference carries ~1e-9 noise
+        got = p.grad.detach().double().flatten().cpu()
+        g_rel.append((abs(got.norm().item() - ref[0].item()), ref[0].item()))
+    # fingerprints hold the L2 norm of every gradient: relative error of the norms, norm-weighted
+    res["grad_norm_rel"] = sum(d for d, _ in g_rel) / max(sum(n for _, n in g_rel), 1e-30)
+    gm = (out_list[0].detach() > 0)
+    res["popcount_diff"] = abs(int(gm.sum()) - fix["mask_f1"]["popcount"])
+    res["n_pixels"] = gm.numel()
+    net.module.release_engines()
+    return res
+
+
+def run_golden_eval_case(fixture_path) -> dict:
+    """Odd-sized inference on the GPU against a fixture written by the UNMODIFIED reference
+    (oracle/make_eval_golden.py)."""
+    fix = torch.load(fixture_path, weights_only=False)
+    name, mtype, cin, topo, B, H, W, Hw, Ww = fix["case"]
+    dev = torch.device("cuda", 0)
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg).to(dev)
+    xc = 6 if mtype in TWO_STREAM else cin
+    warm = O.synthetic_batch(B, xc, Hw, Ww, seed=11)
+    batch = O.synthetic_batch(B, xc, H, W, seed=7)
+    net.train()
+    with torch.no_grad():
+        net(warm["x_t1"].to(dev), warm["x_t2"].to(dev))
+    net.eval()
+    with torch.no_grad():
+        out = net(batch["x_t1"].to(dev), batch["x_t2"].to(dev))
+    torch.cuda.synchronize()
+    ref = fix["logits"]
+    res = {"logits_rel": rel(out, ref)}
+    flips = ((out.cpu() > 0) != (ref > 0)) & (ref.abs() >= 0.05)
+    res["margin_flips"] = int(flips.sum())
+    _, f1 = O.change_mask_f1(out.cpu(), batch["y_change"])
+    res["f1_diff"] = abs(float(f1) - fix["f1"])
+    net.module.release_engines()
+    return res
+

@@ -95,3 +95,31 @@ def test_baseline_size_properties():
     assert r["deterministic"], r
     assert r["loss_vs_formula"] <= 1e-5, r
     assert r["all_finite"] and not r["zero_grad_tensors"] and r["prebn_bias_grad_max"] == 0.0, r
+
+
+from pathlib import Path  # noqa: E402
+
+_GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("name", sorted(p.stem for p in _GOLD.glob("*.pt")))
+def test_step_against_reference_fixture(name):
+    """The CUDA path against values the UNMODIFIED reference produced (tests/golden/*.pt), not only against the oracle:
+    loss within north_star's 1e-4, logits within the bf16-storage bound, per-tensor gradient norms, mask popcount."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = E.run_golden_train_case(_GOLD / f"{name}.pt")
+    assert r["loss_diff"] <= 1e-4, r
+    assert r["logits_rel"] <= 3e-2, r
+    assert r["grad_norm_rel"] <= 0.1, r
+    assert r["popcount_diff"] <= 0.02 * r["n_pixels"], r
+
+
+@pytest.mark.parametrize("name", sorted(p.stem for p in (_GOLD / "eval").glob("*.pt")))
+def test_eval_against_reference_fixture(name):
+    """Odd-sized whole-tile inference against logits / F1 the UNMODIFIED reference produced (tests/golden/eval/*.pt)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = E.run_golden_eval_case(_GOLD / "eval" / f"{name}.pt")
+    assert r["logits_rel"] <= 3e-2 and r["margin_flips"] == 0 and r["f1_diff"] <= 2e-2, r
+

@@ -123,3 +123,32 @@ def test_oracle_init_equals_dropin_init(mtype, cin):
     assert set(sd_net) == set(sd_or)
     for k in sd_net:
         assert torch.equal(sd_net[k], sd_or[k]), k
+
+
+EVAL_GOLD = GOLD / "eval"
+EVAL_CASES = sorted(p.stem for p in EVAL_GOLD.glob("*.pt"))
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_oracle_eval_odd_tiles_match_reference(name):
+    """Inference on tiles with odd-sized levels (utils/evaluation.py:9-23; MaxPool2d floor utils/networks.py:420, Up
+    centre pad :440-443): the oracle's eval-mode logits, mask and F1 against the unmodified reference
+    (oracle/make_eval_golden.py)."""
+    fix = torch.load(EVAL_GOLD / f"{name}.pt", weights_only=False)
+    cname, mtype, cin, topo, B, H, W, Hw, Ww = fix["case"]
+    cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
+    torch.manual_seed(cfg.SEED)
+    net = networks.create_network(cfg)
+    sd = O.clone_state(net.state_dict(), requires_grad=False)
+    xc = 6 if mtype in ("dualstreamunet", "whatevernet", "whatevernet2") else cin
+    warm = O.synthetic_batch(B, xc, Hw, Ww, seed=11)
+    batch = O.synthetic_batch(B, xc, H, W, seed=7)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        O.forward(mtype, sd, warm["x_t1"], warm["x_t2"], train=True, q=False)      # moves the running statistics
+        logits = O.forward(mtype, sd, batch["x_t1"], batch["x_t2"], train=False, q=False)
+    assert torch.is_tensor(logits) and tuple(logits.shape) == (B, 1, H, W)
+    assert (logits - fix["logits"]).abs().max().item() <= 1e-5
+    mask, f1 = O.change_mask_f1(logits, batch["y_change"])
+    assert int(mask.sum()) == fix["popcount"] and abs(float(f1) - fix["f1"]) <= 1e-6
+
