@@ -30,10 +30,10 @@ WGRAD_CTA_TARGET = int(__import__("os").environ.get("B200CD_WGRAD_CTAS", 148))
 # BatchNorm backward of stages with a single direct gradient source: accumulate its reduce pass in the epilogue of the
 # input-gradient convolution that produces that gradient (ops.conv_gemm_bnbwd)
 FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != "0"
-# B200CD_WGRAD_SIDE_STREAM=1: weight-gradient GEMMs on a second stream (forked after the layer's input-gradient GEMM,
-# joined before each batched reduce) so that the HBM-bound BatchNorm-backward kernels of the next layers could run
-# under them. Measured neutral on B200 (9.71-9.76 ms either way): a 198 KB-shared-memory GEMM CTA and the elementwise
-# CTAs do not share an SM, so the kernels still alternate. Off by default.
+# Weight-gradient GEMMs run on their own stream (forked after the layer's input-gradient GEMM, joined before each batched
+# reduce): nothing downstream of a layer needs its weight gradient, so it fills the ramp-up / tail / launch gaps of the
+# dependent BatchNorm-backward -> dgrad chain. Same-box A/B: Siamese B=8 3.83 -> 3.78 ms (+1.4 %), DTSiamese B=8 +0.5 %,
+# DualStream B=16 (already two trunk streams) +0.5 %. B200CD_WGRAD_SIDE_STREAM=0 turns it off.
 # The two U-Net trunks of DualStreamUNet / WhateverNet / WhateverNet2 are independent until the fusion head: with
 # B200CD_BRANCH_STREAMS=1 (default) the second trunk's launches go to a second stream (forked after the weight packing /
 # the head gradients, joined before the head / every batched split reduce), so the ramp-up, tail and launch gaps of one
@@ -44,7 +44,7 @@ FUSE_BN_BWD_REDUCE = __import__("os").environ.get("B200CD_FUSE_BN_BWD", "1") != 
 _BRANCH_MODE = __import__("os").environ.get("B200CD_BRANCH_STREAMS", "1")
 BRANCH_STREAMS = _BRANCH_MODE != "0"
 BRANCH_MAX_PIXELS = 4 << 20
-WGRAD_SIDE_STREAM = __import__("os").environ.get("B200CD_WGRAD_SIDE_STREAM", "0") == "1"
+WGRAD_SIDE_STREAM = __import__("os").environ.get("B200CD_WGRAD_SIDE_STREAM", "1") != "0"
 # transposed-conv bias gradient from the per-CTA channel sums of the dgrad launch that writes the concat-buffer gradient
 UP_BIAS_FROM_STATS = __import__("os").environ.get("B200CD_UP_BIAS_FROM_STATS", "1") != "0"
 FUSE_BN_BWD_MIN_PIXELS = int(__import__("os").environ.get("B200CD_FUSE_BN_BWD_MIN_PIXELS", 32768))
