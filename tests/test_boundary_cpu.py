@@ -166,3 +166,22 @@ def test_launcher_substitutes_reference_modules(tmp_path, monkeypatch):
     got = out.read_text().split()
     assert got[0] == "multimodal_siamese_cd_b200.networks" and got[1] == "multimodal_siamese_cd_b200.loss_functions"
     assert got[2] in ("multimodal_siamese_cd_b200.config", "fvcore.common.config")
+
+
+def test_documented_knobs_exist_in_code():
+    """Every B200CD_* environment variable named in INTEGRATION.md's knob table is read somewhere in the product (and
+    every one the product reads is documented)."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    doc = (root / "INTEGRATION.md").read_text()
+    table = doc[doc.index("## Tuning knobs"):]
+    documented = set(re.findall(r"`(B200CD_[A-Z0-9_]+)\*?`", table))
+    code = ""
+    for f in list((root / "multimodal_siamese_cd_b200").rglob("*.py")) + list((root / "multimodal_siamese_cd_b200" / "csrc").glob("*.cu")) \
+            + list((root / "multimodal_siamese_cd_b200" / "csrc").glob("*.h")) + [root / "bench.py"]:
+        code += f.read_text()
+    read = set(re.findall(r"(?:getenv|environ\.get|environ\[)\(?\s*\"(B200CD_[A-Z0-9_]+)\"", code))
+    debug = {k for k in read if k.startswith("B200CD_DEBUG_")}
+    assert documented - {"B200CD_DEBUG_"} <= read | {"B200CD_NVCC_EXTRA"}, documented - read
+    assert read - debug <= documented, read - debug - documented
+
