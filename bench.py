@@ -173,7 +173,7 @@ def profile_step(ts, steps: int = 2) -> dict:
 
     from multimodal_siamese_cd_b200 import ops
     eng = ts.eng
-    eng.branch_streams = False   # one stream: every launch is timed on its own
+    eng.branch_streams = eng.wgrad_side = False   # one stream: every launch is timed on its own
     fam = {}
     l0 = ops.LAUNCHES
     for it in range(steps + 1):

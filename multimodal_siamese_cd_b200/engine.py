@@ -205,7 +205,8 @@ class StepEngine:
         self._branch_stream = None
         self._branch_main = None
         self._branch_active = False
-        self.branch_streams = BRANCH_STREAMS      # bench.profile_step turns it off to time launches one by one
+        self.branch_streams = BRANCH_STREAMS      # bench.profile_step turns both off to time launches one by one
+        self.wgrad_side = WGRAD_SIDE_STREAM
         self.pack_fwd: list[Callable[[], None]] = []
         self.pack_bwd: list[Callable[[], None]] = []
         self.bwd_marks: list[int] = []  # per backward op: length of the flat-gradient prefix complete after it
@@ -576,7 +577,7 @@ class StepEngine:
         class _Fork:
             def __enter__(self_inner):
                 self_inner.ctx = None
-                if eng.device.type != "cuda" or not WGRAD_SIDE_STREAM:
+                if eng.device.type != "cuda" or not eng.wgrad_side:
                     return
                 if eng._side_stream is None:
                     eng._side_stream = torch.cuda.Stream(device=eng.device)
