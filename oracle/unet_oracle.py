@@ -11,6 +11,7 @@ SURVEY.md §8c). This restatement therefore calls the same torch CPU kernels (F.
 reference's order. Parity pin: tests/golden/*.pt hold outputs of the UNMODIFIED reference modules
 (utils/networks.py, utils/loss_functions.py imported from /root/reference by oracle/make_golden.py in the build
 container); tests/test_oracle_golden.py checks this file against them bit-for-bit-level (<= 1e-6) on CPU.
+tests/golden/eval/*.pt (oracle/make_eval_golden.py) pin the inference path on tiles with odd-sized levels the same way.
 
 Two modes:
   q=False  exact fp32 (or fp64 via dtype) restatement == the reference.
