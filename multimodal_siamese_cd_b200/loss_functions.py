@@ -13,8 +13,6 @@ finding 2). With one process per GPU call `set_data_parallel_group(group)`: the 
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 import torch.nn as nn
 

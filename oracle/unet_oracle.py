@@ -21,8 +21,6 @@ Two modes:
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 import torch.nn.functional as F
 
