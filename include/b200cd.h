@@ -38,7 +38,7 @@ extern "C" {
 #define B200CD_ERR_CUDA 4
 #define B200CD_ERR_DEVICE 5 /* a kernel reported a pipeline time-out (see b200cd_device_status) */
 
-#define B200CD_ABI_VERSION 1
+#define B200CD_ABI_VERSION 2
 
 int b200cd_abi_version(void);
 const char* b200cd_last_error(void);
@@ -302,6 +302,45 @@ typedef struct {
 } b200cd_adamw_job;
 int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total_blocks, double lr, double beta1,
                       double beta2, double eps, double weight_decay, int64_t step_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * "Precise" mode: split-bf16 storage (ABI version 2).
+ *
+ * north_star asks for logits / gradients within 1e-3 of the reference's fp32 path; single bf16 (or TF32) operands
+ * cannot deliver that through train-mode BatchNorm and the siamese t2 - t1 differences. In this mode
+ * every activation / gradient element is stored as TWO bf16 values, hi = bf16(x) and lo = bf16(x - hi) (16 mantissa
+ * bits together), laid out per pixel as [hi (channels) | lo (channels)]: a tensor is passed as the pointer to its hi
+ * half with its pixel stride `ld`, and its lo half lies exactly ld / 2 elements behind (so channel slices of a
+ * concatenation buffer [hi skip | hi up | lo skip | lo up] keep working). The tensor-core kernels form every product
+ * as three bf16 MMAs with fp32 accumulation (hi*hi + hi*lo + lo*hi):
+ *   - b200cd_conv_gemm with flags bit 4 (16): A and out are split tensors (ld % 16 == 0, ld / 2 >= channels), `ka`
+ *     stays the real channel count, Bw is [N][taps][3*ka] = [hi | lo | hi] per tap (b200cd_pack_weights_hp_batched),
+ *     statistics are taken from the stored hi + lo values. Needs the CTA-pair kernel (flags bit 2).
+ *   - b200cd_wgrad_gemm_hp: U and V split tensors; each pixel tile runs three times (U_hi*V_hi, U_hi*V_lo, U_lo*V_hi).
+ * The memory-bound kernels below read hi + lo, compute in fp32 exactly like their bf16-storage counterparts and write
+ * both halves. Everything that is fp32 already (statistics, loss, parameter gradients, AdamW) is shared.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_wgrad_gemm_hp(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
+                         int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
+                         int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream);
+/* b200cd_pack_input writing [pixel][hi kpad | lo kpad] rows (ld = 2 * kpad) */
+int b200cd_pack_input_hp(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B, int H,
+                         int W, int kpad, void* out_bf16, void* stream);
+/* b200cd_pack_weights_batched writing the K-tripled [hi | lo | hi] operands; same job struct, blocks per job from
+ * b200cd_pack_job_blocks_hp */
+int b200cd_pack_job_blocks_hp(int mode, int d0, int d1, int kpad);
+int b200cd_pack_weights_hp_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total_blocks, void* stream);
+/* b200cd_bn_apply / b200cd_bn_bwd / b200cd_head_fwd / b200cd_colsum on split tensors (same arguments) */
+int b200cd_bn_apply_hp(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
+                       int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
+                       void* dif, int64_t ld_d, void* pool_idx, void* stream);
+int b200cd_bn_bwd_hp(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                     const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
+                     float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream);
+int b200cd_head_fwd_hp(const void* a0, int64_t ld0, const void* a1, int64_t ld1, int C, const float* w, const float* b,
+                       int64_t npix, float* logits, void* stream);
+int b200cd_colsum_hp(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,15 @@ SIGNATURES = {
     "b200cd_confusion_counts": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "b200cd_adamw_step": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _vp]),
     "b200cd_pj_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    # split-bf16 ("precise") mode, ABI version 2
+    "b200cd_wgrad_gemm_hp": (_i, [_i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _i64, _i64, _i64, _vp]),
+    "b200cd_pack_input_hp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b200cd_pack_job_blocks_hp": (_i, [_i, _i, _i, _i]),
+    "b200cd_pack_weights_hp_batched": (_i, [_vp, _i, _i64, _vp]),
+    "b200cd_bn_apply_hp": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "b200cd_bn_bwd_hp": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, C.POINTER(GradSrc), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "b200cd_head_fwd_hp": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "b200cd_colsum_hp": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()
@@ -90,7 +99,7 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.b200cd_abi_version() != 1:
+            if lib.b200cd_abi_version() != 2:
                 raise B200CDError("libb200cd.so ABI version mismatch; rebuild")
             _lib = lib
     return _lib

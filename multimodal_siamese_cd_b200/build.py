@@ -17,7 +17,7 @@ ROOT = PKG.parent
 LIB = PKG / "libb200cd.so"
 STAMP = PKG / ".libb200cd.stamp"
 
-SOURCES = ["abi.cu", "gemm_fprop.cu", "gemm_fprop2.cu", "gemm_wgrad.cu", "elementwise.cu"]
+SOURCES = ["abi.cu", "gemm_fprop.cu", "gemm_fprop2.cu", "gemm_wgrad.cu", "elementwise.cu", "elementwise_hp.cu"]
 HEADERS = [CSRC / "kernels.h", CSRC / "ptx.cuh", ROOT / "include" / "b200cd.h"]
 
 NVCC_FLAGS = [

@@ -265,7 +265,9 @@ int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int
   p.out_mode = out_mode;
   p.taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
   p.N = N;
-  p.kchunks = ka / 64;
+  p.prec = (flags & 16) ? 1 : 0;
+  p.kreal = ka / 64;
+  p.kchunks = (p.prec ? 3 : 1) * (ka / 64);
   const int ctas = b200cd::fprop_pair_ctas(p, c.bn, c.num_tiles);
   return ctas < 0 ? -1 : 2 * ctas;            // rows per stat-group: one per (CTA, epilogue group)
 }
@@ -287,6 +289,14 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
 
   const ConvPlan cp = plan_conv(mode, out_mode, flags, n_img, H, W, N);
   const int tw = cp.tw, th = cp.th, pair = cp.pair, halo = cp.halo, bn = cp.bn;
+  // flags bit 4: split-bf16 operands. A / out rows hold [hi | lo] halves ld / 2 elements apart, Bw is [N][taps][3 * ka]
+  // packed as [hi | lo | hi] per tap (b200cd_pack_weights_hp_batched); ka stays the real channel count.
+  const int prec = (flags & 16) ? 1 : 0;
+  if (prec && (!pair || bwd_r != nullptr))
+    return fail(B200CD_ERR_SHAPE, "conv_gemm: split-bf16 operands need the CTA-pair kernel (flags bit 2) without the fused BN-backward sums");
+  if (prec && (a_ld % 16 != 0 || out_ld % 16 != 0 || a_ld / 2 < ka || out_ld / 2 < (out_mode == 1 ? cout : N)))
+    return fail(B200CD_ERR_ALIGN, "conv_gemm: split-bf16 rows need ld %% 16 == 0 and ld / 2 >= channels");
+  const int kb = prec ? 3 * ka : ka;  // K per tap of the weight matrix
   if (cp.stat_groups > 2 || (cp.stat_groups > 0 && n_img % cp.stat_groups != 0))
     return fail(B200CD_ERR_SHAPE, "conv_gemm: stat groups must be 1 or 2 and divide n_img");
   b200cd::FpropParams p;
@@ -294,8 +304,12 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
   p.mode = mode;
   p.out_mode = out_mode;
   p.taps = mode == 0 ? 9 : (mode == 1 ? 1 : 4);
-  p.kchunks = ka / 64;
-  p.ka = ka;
+  p.kchunks = kb / 64;
+  p.ka = kb;
+  p.prec = prec;
+  p.kreal = ka / 64;
+  p.a_lo = prec ? static_cast<int>(a_ld / 2) : 0;
+  p.o_lo = prec ? static_cast<int>(out_ld / 2) : 0;
   p.tw = tw;
   p.th = th;
   p.rows = halo ? tw * (th + 2) : tw * th;  // rows the A box delivers (expect_tx); the tile itself is tw*th
@@ -330,10 +344,12 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
 
   CUtensorMap mapA, mapB, mapO;
   int rc;
-  if (mode == 2) rc = make_up2_map(&mapA, A, a_ld, ka, W, H, n_img, tw, th);
-  else rc = make_nhwc_map(&mapA, A, a_ld, ka, W, H, n_img, tw, halo ? th + 2 : th);
+  const int ca = ka + p.a_lo;  // channel extent of the A map (the lo half lies a_lo channels behind the hi half)
+  if (mode == 2) rc = make_up2_map(&mapA, A, a_ld, ca, W, H, n_img, tw, th);
+  else rc = make_nhwc_map(&mapA, A, a_ld, ca, W, H, n_img, tw, halo ? th + 2 : th);
   if (rc) return rc;
   {
+    const int ka = kb;  // the weight maps below see the tripled K of the split-bf16 layout
     const uint64_t ktot = static_cast<uint64_t>(p.taps) * ka;
     const uint64_t dims[2] = {ktot, (uint64_t)N};
     const uint64_t strides[1] = {ktot * 2};
@@ -349,8 +365,8 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
     }
     if (rc) return rc;
   }
-  if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout, W, H, n_img, tw, th);
-  else rc = make_nhwc_map(&mapO, out, out_ld, N, W, H, n_img, tw, th);
+  if (out_mode == 1) rc = make_up2_map(&mapO, out, out_ld, cout + p.o_lo, W, H, n_img, tw, th);
+  else rc = make_nhwc_map(&mapO, out, out_ld, N + p.o_lo, W, H, n_img, tw, th);
   if (rc) return rc;
   if (pair)
     CUDA_TRY(b200cd::launch_fprop_pair(mapA, mapB, mapO, p, bn, num_tiles, reinterpret_cast<cudaStream_t>(stream)));
@@ -384,10 +400,12 @@ int b200cd_wgrad_ctas_per_split(int mode, int halo, int cu, int cv) {
   return (bn == 64 && halo && b200cd::wgrad_mstack(cu)) ? xy : 3 * xy;
 }
 
-int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
-                      int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
-                      int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {
+static int wgrad_gemm_impl(int prec, int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V,
+                           int64_t v_ld, int cv, int n_img, int H, int W, float* ws, int splits, int splits2,
+                           int64_t split_stride, int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {
   if (mode < 0 || mode > 2) return fail(B200CD_ERR_SHAPE, "wgrad_gemm: bad mode");
+  if (prec && (u_ld % 16 != 0 || v_ld % 16 != 0 || u_ld / 2 < cu || v_ld / 2 < cv))
+    return fail(B200CD_ERR_ALIGN, "wgrad_gemm_hp: split-bf16 rows need ld %% 16 == 0 and ld / 2 >= channels");
   if (cu < 64 || cu % 64 != 0 || cv < 64 || cv % 64 != 0)
     return fail(B200CD_ERR_SHAPE, "wgrad_gemm: cu=%d, cv=%d must be multiples of 64", cu, cv);
   if (u_ld % 8 != 0 || v_ld % 8 != 0) return fail(B200CD_ERR_ALIGN, "wgrad_gemm: ld must be a multiple of 8");
@@ -422,16 +440,33 @@ int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld,
   p.m_stride = m_stride;
   p.n_stride = n_stride;
   p.err = err;
+  p.passes = prec ? 3 : 1;
+  p.u_lo = prec ? static_cast<int>(u_ld / 2) : 0;
+  p.v_lo = prec ? static_cast<int>(v_ld / 2) : 0;
   const int bn = (cv % 128 == 0) ? 128 : 64;
 
   CUtensorMap mapU, mapV;
   int rc;
-  if ((rc = make_nhwc_map(&mapU, U, u_ld, cu, W, H, n_img, 8, 8))) return rc;
-  if (mode == 2) rc = make_up2_map(&mapV, V, v_ld, cv, W, H, n_img, 8, 8);
-  else rc = make_nhwc_map(&mapV, V, v_ld, cv, W, H, n_img, 8, halo ? 10 : 8);
+  if ((rc = make_nhwc_map(&mapU, U, u_ld, cu + p.u_lo, W, H, n_img, 8, 8))) return rc;
+  if (mode == 2) rc = make_up2_map(&mapV, V, v_ld, cv + p.v_lo, W, H, n_img, 8, 8);
+  else rc = make_nhwc_map(&mapV, V, v_ld, cv + p.v_lo, W, H, n_img, 8, halo ? 10 : 8);
   if (rc) return rc;
   CUDA_TRY(b200cd::launch_wgrad(mapU, mapV, p, bn, halo, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
+}
+
+int b200cd_wgrad_gemm(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
+                      int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
+                      int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {
+  return wgrad_gemm_impl(0, mode, sign, halo, U, u_ld, cu, V, v_ld, cv, n_img, H, W, ws, splits, splits2, split_stride,
+                         tap_stride, m_stride, n_stride, stream);
+}
+
+int b200cd_wgrad_gemm_hp(int mode, int sign, int halo, const void* U, int64_t u_ld, int cu, const void* V, int64_t v_ld,
+                         int cv, int n_img, int H, int W, float* ws, int splits, int splits2, int64_t split_stride,
+                         int64_t tap_stride, int64_t m_stride, int64_t n_stride, void* stream) {
+  return wgrad_gemm_impl(1, mode, sign, halo, U, u_ld, cu, V, v_ld, cv, n_img, H, W, ws, splits, splits2, split_stride,
+                         tap_stride, m_stride, n_stride, stream);
 }
 
 int b200cd_wgrad_reduce(const float* ws, int splits, int64_t split_stride, int layout, int d0, int d1, int taps,
@@ -653,6 +688,106 @@ int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total
                                 static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
                                 static_cast<float>(1.0 - beta2), static_cast<float>(eps), static_cast<float>(sqrt(bc2)),
                                 reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-bf16 ("precise") entry points (include/b200cd.h, ABI version 2)
+// ------------------------------------------------------------------------------------------------
+static bool split_ok(const void* p, int64_t ld, int C) { return p == nullptr || (ld % 16 == 0 && ld / 2 >= C && aligned16(p)); }
+
+int b200cd_pack_input_hp(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B, int H,
+                         int W, int kpad, void* out, void* stream) {
+  const int cin = cat_mode ? 2 * nc : nc;
+  if (nc <= 0 || c_lo < 0 || c_lo + nc > csrc || B <= 0 || H <= 0 || W <= 0)
+    return fail(B200CD_ERR_SHAPE, "pack_input_hp: bad channel/batch arguments");
+  if (kpad % 64 != 0 || 9 * cin > kpad || kpad > 256)
+    return fail(B200CD_ERR_SHAPE, "pack_input_hp: kpad=%d must be a multiple of 64 holding 9*Cin=%d", kpad, 9 * cin);
+  if (!aligned16(out)) return fail(B200CD_ERR_ALIGN, "pack_input_hp: output not 16-byte aligned");
+  CUDA_TRY(b200cd::launch_pack_input_hp(src0, src1, csrc, c_lo, nc, cat_mode, B, H, W, kpad, out,
+                                        reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_pack_job_blocks_hp(int mode, int d0, int d1, int kpad) {
+  if (mode < 0 || mode > 4 || d0 <= 0 || d1 <= 0) return 0;
+  return b200cd::pack_job_blocks_hp(mode, d0, d1, kpad);
+}
+
+int b200cd_pack_weights_hp_batched(const b200cd_pack_job* jobs_dev, int njobs, int64_t total_blocks, void* stream) {
+  if (jobs_dev == nullptr || njobs < 1 || total_blocks < 1 || total_blocks > 0x7fffffffll)
+    return fail(B200CD_ERR_SHAPE, "pack_weights_hp_batched: empty job table");
+  CUDA_TRY(b200cd::launch_pack_weights_hp_batched(reinterpret_cast<const b200cd::PackJob*>(jobs_dev), njobs, total_blocks,
+                                                  reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_bn_apply_hp(const void* r, int64_t ld_r, const float* scale, const float* shift, int n_img, int H, int W,
+                       int C, int G, int diff, void* a, int64_t ld_a, void* a2, int64_t ld_a2, void* pool, int64_t ld_p,
+                       void* dif, int64_t ld_d, void* pool_idx, void* stream) {
+  if (C % 8 != 0 || n_img % G != 0 || (diff && (n_img % 2 != 0 || G != 2)))
+    return fail(B200CD_ERR_SHAPE, "bn_apply_hp: bad C/G/diff combination");
+  if (!split_ok(r, ld_r, C) || !split_ok(a, ld_a, C) || !split_ok(a2, ld_a2, C) || !split_ok(pool, ld_p, C) ||
+      !split_ok(dif, ld_d, C))
+    return fail(B200CD_ERR_ALIGN, "bn_apply_hp: split tensors need ld %% 16 == 0, ld / 2 >= C and 16-byte alignment");
+  if (pool_idx != nullptr && (pool == nullptr || (reinterpret_cast<uintptr_t>(pool_idx) & 7u)))
+    return fail(B200CD_ERR_ALIGN, "bn_apply_hp: pool_idx needs pool and 8-byte alignment");
+  CUDA_TRY(b200cd::launch_bn_apply_hp(r, ld_r, scale, shift, n_img, H, W, C, G, diff, a, ld_a, a2, ld_a2, pool, ld_p, dif,
+                                      ld_d, pool_idx, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_bn_bwd_hp(const void* r, int64_t ld_r, const float* mean, const float* invstd, const float* scale,
+                     const float* shift, const b200cd_grad_src* srcs, int n_img, int H, int W, int C, int G, float* ws,
+                     float* dgamma, float* dbeta, void* dr, int64_t ld_dr, void* stream) {
+  if (!chan_ok(C)) return fail(B200CD_ERR_SHAPE, "bn_bwd_hp: C=%d must be a multiple of 64 with 256 %% (C/8) == 0", C);
+  if (G <= 0 || n_img % G != 0) return fail(B200CD_ERR_SHAPE, "bn_bwd_hp: n_img must be a multiple of G");
+  if (!split_ok(r, ld_r, C) || !split_ok(dr, ld_dr, C)) return fail(B200CD_ERR_ALIGN, "bn_bwd_hp: alignment");
+  if (static_cast<long long>(n_img) * H * W >= (1ll << 31)) return fail(B200CD_ERR_SHAPE, "bn_bwd_hp: more than 2^31 pixels");
+  b200cd::GradSrcs gs;
+  memset(&gs, 0, sizeof(gs));
+  for (int i = 0; i < 3; ++i) {
+    gs.s[i].kind = srcs[i].kind;
+    gs.s[i].ptr = srcs[i].ptr;
+    gs.s[i].w = srcs[i].w;
+    gs.s[i].ld = srcs[i].ld;
+    gs.s[i].n_mod = srcs[i].n_mod;
+    gs.s[i].scale_lo = srcs[i].scale_lo;
+    gs.s[i].scale_hi = srcs[i].scale_hi;
+    if (srcs[i].kind < 0 || srcs[i].kind > 3) return fail(B200CD_ERR_SHAPE, "bn_bwd_hp: bad gradient source kind");
+    if ((srcs[i].kind == 1 || srcs[i].kind == 2) && !split_ok(srcs[i].ptr, srcs[i].ld, C))
+      return fail(B200CD_ERR_ALIGN, "bn_bwd_hp: gradient source %d alignment", i);
+    if (srcs[i].kind == 2 && srcs[i].w == nullptr)
+      return fail(B200CD_ERR_SHAPE, "bn_bwd_hp: a max-pool source needs the arg-max index tensor in .w");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nblk = bn_bwd_nblk(n_img, H, W, C, G);
+  float* partial = ws;
+  float* coefA = ws + static_cast<size_t>(2) * G * C * nblk;
+  float* coefB = coefA + static_cast<size_t>(G) * C;
+  const double count = static_cast<double>(n_img / G) * H * W;
+  CUDA_TRY(b200cd::launch_bn_bwd_reduce_hp(r, ld_r, scale, shift, gs, n_img, H, W, C, G, nblk, partial, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_finalize(partial, nblk, C, G, count, mean, invstd, scale, dgamma, dbeta, coefA, coefB, st));
+  CUDA_TRY(b200cd::launch_bn_bwd_dx_hp(r, ld_r, scale, shift, coefA, coefB, gs, n_img, H, W, C, G, nblk, dr, ld_dr, st));
+  return 0;
+}
+
+int b200cd_head_fwd_hp(const void* a0, int64_t ld0, const void* a1, int64_t ld1, int C, const float* w, const float* b,
+                       int64_t npix, float* logits, void* stream) {
+  if (C % 64 != 0 || C <= 0) return fail(B200CD_ERR_SHAPE, "head_fwd_hp: C must be a multiple of 64");
+  if (!split_ok(a0, ld0, C) || !split_ok(a1, ld1, C)) return fail(B200CD_ERR_ALIGN, "head_fwd_hp: alignment");
+  CUDA_TRY(b200cd::launch_head_fwd_hp(a0, ld0, a1, ld1, C, w, b, npix, logits, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_colsum_hp(const void* x, int64_t ld, int C, const float* wgt, int64_t npix, int nblk, float* ws, float* out,
+                     void* stream) {
+  if (x == nullptr || !chan_ok(C)) return fail(B200CD_ERR_SHAPE, "colsum_hp: needs x and a supported C (got %d)", C);
+  if (nblk < 1 || npix < 1) return fail(B200CD_ERR_SHAPE, "colsum_hp: empty");
+  if (!split_ok(x, ld, C)) return fail(B200CD_ERR_ALIGN, "colsum_hp: alignment");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUDA_TRY(b200cd::launch_colsum_hp(x, ld, C, wgt, npix, nblk, ws, st));
+  CUDA_TRY(b200cd::launch_colsum_finalize(ws, nblk, C, out, st));
   return 0;
 }
 

@@ -84,7 +84,25 @@ static int pair_threads() {
   return t;
 }
 
-template <int BN, bool RESIDENT, int NKY>
+// 32 values per lane, 32 lanes -> lane l ends up with the sum over the warp of value l (transposing butterfly: 31
+// shuffles instead of 32 x 5). Fixed order, so the result is run-to-run deterministic.
+__device__ __forceinline__ float warp_transpose_sum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < n / 2) {
+        const float send = up ? x[j] : x[j + n / 2];
+        const float keep = up ? x[j + n / 2] : x[j];
+        x[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return x[0];
+}
+
+template <int BN, bool RESIDENT, int NKY, bool PREC>
 __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ CUtensorMap mapO,
@@ -174,12 +192,15 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
           TR();
           mbar_wait(&a_empty[sa], pa, p.err, DEV_ERR_EMPTY_TIMEOUT);
           TR();
+          // split-bf16: chunk kc of a tap = (pass, real chunk); passes 0 and 1 read the hi half of A (against W_hi and
+          // W_lo), pass 2 the lo half (against W_hi again)
+          const int ac = PREC ? (kc % p.kreal) * 64 + (kc >= 2 * p.kreal ? p.a_lo : 0) : kc * 64;
           if (elect_one_sync()) {
             if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * p.rows * 128);
-            if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0 + kx - 1, y0 - 1, img, 0);
-            else if (p.mode == 1) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, x0, y0, img, 0);
+            if (NKY == 3) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], ac, x0 + kx - 1, y0 - 1, img, 0);
+            else if (p.mode == 1) tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], ac, x0, y0, img, 0);
             else  // mode 2: tap kx = (dy, dx) of the 2x2 / stride-2 gather from the full-resolution tensor
-              tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], kc * 64, kx & 1, x0, kx >> 1, img * p.H + y0);
+              tma_load_5d_2cta(smem + L::kAOff + sa * kABox, &mapA, &a_full[sa], ac, kx & 1, x0, kx >> 1, img * p.H + y0);
           }
           __syncwarp();
           if (++sa == L::kSA) {
@@ -383,6 +404,101 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       mbar_wait(&acc_full[buf], (n_item >> 1) & 1, p.err, DEV_ERR_ACC_TIMEOUT);
       TR();
       tc_fence_after();
+      if constexpr (PREC) {
+        // ---- split-bf16 epilogue: every 64-channel slab is stored twice, hi = bf16(x) at channel n and
+        // lo = bf16(x - hi) at channel n + o_lo; BatchNorm statistics are taken from the stored value hi + lo in
+        // registers (transposing warp butterfly: lane l gets the column sum of channel l), not from the staged tile ----
+        const int tw_shift = p.tw == 16 ? 4 : 3;
+        const bool vrow = real && m < p.tw * p.th && (x0 + (m & (p.tw - 1)) < p.W) && (y0 + (m >> tw_shift) < p.H);
+#pragma unroll 1
+        for (int slab = 0; slab < BN / 64; ++slab) {
+          float cs[2] = {0.f, 0.f}, cq[2] = {0.f, 0.f};
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part, ++n_slab) {
+            uint8_t* sbuf = stg + (n_slab % L::kStg) * kStageSlab;
+            if (t == 0 && n_slab >= L::kStg) {
+              if (L::kStg == 2) tma_store_wait_read1();
+              else tma_store_wait_read0();
+            }
+            named_barrier_sync(bar1, 128);
+            uint8_t* row = sbuf + m * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + slab * 64 + h * 32, v);
+              tmem_ld_wait();
+              float xs[32];
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2) {
+                  const int j = cc * 8 + 2 * j2;
+                  const float f0 = __uint_as_float(v[j]) + bias_s[slab * 64 + h * 32 + j];
+                  const float f1 = __uint_as_float(v[j + 1]) + bias_s[slab * 64 + h * 32 + j + 1];
+                  const uint32_t hi2 = pack_bf16x2(f0, f1);
+                  const float l0 = f0 - bf16_lo(hi2), l1 = f1 - bf16_hi(hi2);
+                  const uint32_t lo2 = pack_bf16x2(l0, l1);
+                  w4[j2] = part == 0 ? hi2 : lo2;
+                  xs[j] = vrow ? bf16_lo(hi2) + bf16_lo(lo2) : 0.f;
+                  xs[j + 1] = vrow ? bf16_hi(hi2) + bf16_hi(lo2) : 0.f;
+                }
+                const int phys = (h * 4 + cc) ^ (m & 7);
+                *reinterpret_cast<uint4*>(row + phys * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
+              if (part == 0 && p.stats != nullptr) {
+                float xq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xq[j] = xs[j] * xs[j];
+                cs[h] = warp_transpose_sum32(xs, lane);
+                cq[h] = warp_transpose_sum32(xq, lane);
+              }
+            }
+            if (slab == BN / 64 - 1 && part == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+            }
+            fence_proxy_async_smem();
+            named_barrier_sync(bar1, 128);
+            if (t == 0) {
+              const int lo_off = part ? p.o_lo : 0;
+              if (p.out_mode == 0) {
+                tma_store_5d(&mapO, sbuf, n0 + slab * 64 + lo_off, x0, y0, img, 0);
+              } else {
+                const int n = n0 + slab * 64;
+                const int tap = n / p.cout, co = n - tap * p.cout;
+                tma_store_5d(&mapO, sbuf, co + lo_off, tap & 1, x0, tap >> 1, img * p.H + y0);
+              }
+              tma_store_commit();
+            }
+            if (part == 0 && p.stats != nullptr) {
+              float* dst = red + ((t >> 5) * 64 + lane) * 2;   // [warp][channel][sum, sum of squares]
+              dst[0] = cs[0];
+              dst[1] = cq[0];
+              dst[64] = cs[1];
+              dst[65] = cq[1];
+              named_barrier_sync(bar2, 128);
+              if (t < 64 && real) {
+                float s = 0.f, qq = 0.f;
+#pragma unroll
+                for (int r4 = 0; r4 < 4; ++r4) {
+                  s += red[((r4 * 64) + t) * 2];
+                  qq += red[((r4 * 64) + t) * 2 + 1];
+                }
+                if (cta_stats) {
+                  acc_s[0][slab] += sgrp == 0 ? s : 0.f;
+                  acc_q[0][slab] += sgrp == 0 ? qq : 0.f;
+                  acc_s[1][slab] += sgrp == 1 ? s : 0.f;
+                  acc_q[1][slab] += sgrp == 1 ? qq : 0.f;
+                } else {
+                  p.stats[static_cast<size_t>(tile) * p.N + n0 + slab * 64 + t] = make_float2(s, qq);
+                }
+              }
+            }
+          }
+        }
+      } else
 #pragma unroll
       for (int slab = 0; slab < BN / 64; ++slab, ++n_slab) {
         uint8_t* sbuf = stg + (n_slab % L::kStg) * kStageSlab;
@@ -574,12 +690,12 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
   }
 }
 
-template <int BN, bool RESIDENT, int NKY>
+template <int BN, bool RESIDENT, int NKY, bool PREC>
 cudaError_t pair_max_clusters(int* out) {
   using L = PairCfg<BN, NKY>;
   static int max_clusters = 0;
   if (max_clusters == 0) {
-    cudaError_t e = cudaFuncSetAttribute(fprop_pair_kernel<BN, RESIDENT, NKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    cudaError_t e = cudaFuncSetAttribute(fprop_pair_kernel<BN, RESIDENT, NKY, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -596,7 +712,7 @@ cudaError_t pair_max_clusters(int* out) {
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, fprop_pair_kernel<BN, RESIDENT, NKY>, &qc);
+    e = cudaOccupancyMaxActiveClusters(&n, fprop_pair_kernel<BN, RESIDENT, NKY, PREC>, &qc);
     if (e != cudaSuccess) return e;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     max_clusters = n < sms / 2 ? n : sms / 2;
@@ -605,22 +721,22 @@ cudaError_t pair_max_clusters(int* out) {
   return cudaSuccess;
 }
 
-template <int BN, bool RESIDENT, int NKY>
+template <int BN, bool RESIDENT, int NKY, bool PREC>
 cudaError_t pair_clusters(const FpropParams& p, int num_tiles, int* clusters) {
   int max_clusters = 0;
-  cudaError_t e = pair_max_clusters<BN, RESIDENT, NKY>(&max_clusters);
+  cudaError_t e = pair_max_clusters<BN, RESIDENT, NKY, PREC>(&max_clusters);
   if (e != cudaSuccess) return e;
   const int num_items = ((num_tiles + 1) / 2) * (p.N / BN);
   *clusters = num_items < max_clusters ? num_items : max_clusters;
   return cudaSuccess;
 }
 
-template <int BN, bool RESIDENT, int NKY>
+template <int BN, bool RESIDENT, int NKY, bool PREC>
 cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const FpropParams& p,
                         int num_tiles, cudaStream_t stream) {
   using L = PairCfg<BN, NKY>;
   int clusters = 0;
-  cudaError_t e = pair_clusters<BN, RESIDENT, NKY>(p, num_tiles, &clusters);
+  cudaError_t e = pair_clusters<BN, RESIDENT, NKY, PREC>(p, num_tiles, &clusters);
   if (e != cudaSuccess) return e;
   if (p.stats != nullptr && p.stat_groups > 0 && p.stat_rows != 4 * clusters) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
@@ -637,11 +753,12 @@ cudaError_t launch_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, const 
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT, NKY>, mapA, mapB, mapO, p, num_tiles);
+  return cudaLaunchKernelEx(&cfg, fprop_pair_kernel<BN, RESIDENT, NKY, PREC>, mapA, mapB, mapO, p, num_tiles);
 }
 
 static bool pair_resident(const FpropParams& p, int bn) {
   // weights resident in shared memory when one N block covers the layer and all its half-tiles fit the B ring
+  if (p.prec) return false;  // three times the weight tiles: streamed
   if (p.mode == 0) {
     const int cap = bn == 256 ? PairCfg<256>::kSB * PairCfg<256>::kG
                               : (bn == 128 ? PairCfg<128>::kSB * PairCfg<128>::kG : PairCfg<64>::kSB * PairCfg<64>::kG);
@@ -652,18 +769,28 @@ static bool pair_resident(const FpropParams& p, int bn) {
 }
 
 // (bn, resident, taps) -> instantiation
-#define B200CD_PAIR_DISPATCH(FN, ...)                                                              \
-  do {                                                                                              \
-    const bool res = pair_resident(p, bn);                                                          \
-    if (p.mode == 0) {                                                                              \
-      if (bn == 256) return res ? FN<256, true, 3>(__VA_ARGS__) : FN<256, false, 3>(__VA_ARGS__);   \
-      if (bn == 128) return res ? FN<128, true, 3>(__VA_ARGS__) : FN<128, false, 3>(__VA_ARGS__);   \
-      if (bn == 64) return res ? FN<64, true, 3>(__VA_ARGS__) : FN<64, false, 3>(__VA_ARGS__);      \
-    } else {                                                                                        \
-      if (bn == 256) return res ? FN<256, true, 1>(__VA_ARGS__) : FN<256, false, 1>(__VA_ARGS__);   \
-      if (bn == 128) return res ? FN<128, true, 1>(__VA_ARGS__) : FN<128, false, 1>(__VA_ARGS__);   \
-      if (bn == 64) return res ? FN<64, true, 1>(__VA_ARGS__) : FN<64, false, 1>(__VA_ARGS__);      \
-    }                                                                                               \
+#define B200CD_PAIR_DISPATCH(FN, ...)                                                                          \
+  do {                                                                                                          \
+    const bool res = pair_resident(p, bn);                                                                      \
+    if (p.prec) {                                                                                               \
+      if (p.mode == 0) {                                                                                        \
+        if (bn == 256) return FN<256, false, 3, true>(__VA_ARGS__);                                             \
+        if (bn == 128) return FN<128, false, 3, true>(__VA_ARGS__);                                             \
+        if (bn == 64) return FN<64, false, 3, true>(__VA_ARGS__);                                               \
+      } else {                                                                                                  \
+        if (bn == 256) return FN<256, false, 1, true>(__VA_ARGS__);                                             \
+        if (bn == 128) return FN<128, false, 1, true>(__VA_ARGS__);                                             \
+        if (bn == 64) return FN<64, false, 1, true>(__VA_ARGS__);                                               \
+      }                                                                                                         \
+    } else if (p.mode == 0) {                                                                                   \
+      if (bn == 256) return res ? FN<256, true, 3, false>(__VA_ARGS__) : FN<256, false, 3, false>(__VA_ARGS__); \
+      if (bn == 128) return res ? FN<128, true, 3, false>(__VA_ARGS__) : FN<128, false, 3, false>(__VA_ARGS__); \
+      if (bn == 64) return res ? FN<64, true, 3, false>(__VA_ARGS__) : FN<64, false, 3, false>(__VA_ARGS__);    \
+    } else {                                                                                                    \
+      if (bn == 256) return res ? FN<256, true, 1, false>(__VA_ARGS__) : FN<256, false, 1, false>(__VA_ARGS__); \
+      if (bn == 128) return res ? FN<128, true, 1, false>(__VA_ARGS__) : FN<128, false, 1, false>(__VA_ARGS__); \
+      if (bn == 64) return res ? FN<64, true, 1, false>(__VA_ARGS__) : FN<64, false, 1, false>(__VA_ARGS__);    \
+    }                                                                                                           \
   } while (0)
 
 }  // namespace
@@ -674,6 +801,7 @@ cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, 
                               const FpropParams& p, int bn, int num_tiles, cudaStream_t stream) {
   if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1 || (p.mode == 2 && p.out_mode == 0))) return cudaErrorInvalidValue;
   if (p.stat_groups < 0 || p.stat_groups > 2) return cudaErrorInvalidValue;
+  if (p.prec && (p.kreal < 1 || p.kchunks != 3 * p.kreal || p.bwd_r != nullptr)) return cudaErrorInvalidValue;
   B200CD_PAIR_DISPATCH(launch_pair, mapA, mapB, mapO, p, num_tiles, stream);
   return cudaErrorInvalidValue;
 }

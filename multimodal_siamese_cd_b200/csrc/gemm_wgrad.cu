@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
   }
   const int t_begin = static_cast<int>(static_cast<long long>(p.total_tiles) * split / nsplit);
   const int t_end = static_cast<int>(static_cast<long long>(p.total_tiles) * (split + 1) / nsplit);
-  const int iters = t_end - t_begin;
+  const int iters = (t_end - t_begin) * p.passes;  // split-bf16 operands: every pixel tile runs p.passes = 3 times
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapU);
@@ -164,11 +164,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
     int tx = tile % p.tiles_x;
     int ty = (tile / p.tiles_x) % p.tiles_y;
     int img = tile / (p.tiles_x * p.tiles_y);
+    int pass = 0;  // split-bf16: 0 = U_hi * V_hi, 1 = U_hi * V_lo, 2 = U_lo * V_hi
     for (int it = 0; it < iters; ++it) {
       WTR();
       mbar_wait(&empty[s], ph, p.err, DEV_ERR_EMPTY_TIMEOUT);
       WTR();
       const int x0 = tx * 8, y0 = ty * 8;
+      const int mu = m0 + (pass == 2 ? p.u_lo : 0), nv = n0 + (pass == 1 ? p.v_lo : 0);
       uint8_t* u_dst = smem + s * C::kStageBytes;
       uint8_t* v_dst = u_dst + C::kUBytesC;
       if (elect_one_sync()) {
@@ -179,16 +181,16 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
           if (NKX == 3) {
 #pragma unroll
             for (int a = 0; a < 3; ++a)  // U tile a pairs with the unshifted V box as filter column kx = a
-              tma_load_5d(u_dst + a * 8192, &mapU, &full[s], m0, x0 - p.sign * (a - 1), y0, img, 0);
+              tma_load_5d(u_dst + a * 8192, &mapU, &full[s], mu, x0 - p.sign * (a - 1), y0, img, 0);
           } else {
 #pragma unroll
             for (int slab = 0; slab < 2; ++slab)
-              tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], m0 + slab * 64, x0, y0, img, 0);
+              tma_load_5d(u_dst + slab * 8192, &mapU, &full[s], mu + slab * 64, x0, y0, img, 0);
           }
         }
         if (!do_v) {
         } else if (NKX == 3) {
-          tma_load_5d(v_dst, &mapV, &full[s], n0, x0, y0 - 1, img, 0);
+          tma_load_5d(v_dst, &mapV, &full[s], nv, x0, y0 - 1, img, 0);
         } else if (MODE == 0) {
           if (HALO) {
 #pragma unroll
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
                 const int sx = p.sign * (kx + b - 1);
 #pragma unroll
                 for (int slab = 0; slab < BN / 64; ++slab)
-                  tma_load_5d(v_dst + (b * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx,
+                  tma_load_5d(v_dst + (b * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], nv + slab * 64, x0 + sx,
                               y0 - 1, img, 0);
               }
             }
@@ -207,19 +209,19 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
             for (int j = 0; j < 3; ++j)
 #pragma unroll
               for (int slab = 0; slab < BN / 64; ++slab)
-                tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0 + sx,
+                tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], nv + slab * 64, x0 + sx,
                             y0 + j - 1, img, 0);
           }
         } else if (MODE == 1) {
 #pragma unroll
           for (int slab = 0; slab < BN / 64; ++slab)
-            tma_load_5d(v_dst + slab * C::kVSlab, &mapV, &full[s], n0 + slab * 64, x0, y0, img, 0);
+            tma_load_5d(v_dst + slab * C::kVSlab, &mapV, &full[s], nv + slab * 64, x0, y0, img, 0);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int slab = 0; slab < BN / 64; ++slab)
-              tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], n0 + slab * 64, j & 1, x0,
+              tma_load_5d(v_dst + (j * (BN / 64) + slab) * C::kVSlab, &mapV, &full[s], nv + slab * 64, j & 1, x0,
                           j >> 1, img * p.H + y0);
         }
       }
@@ -228,11 +230,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const __grid_constant__
         s = 0;
         ph ^= 1;
       }
-      if (++tx == p.tiles_x) {
-        tx = 0;
-        if (++ty == p.tiles_y) {
-          ty = 0;
-          ++img;
+      if (++pass == p.passes) {
+        pass = 0;
+        if (++tx == p.tiles_x) {
+          tx = 0;
+          if (++ty == p.tiles_y) {
+            ty = 0;
+            ++img;
+          }
         }
       }
     }

@@ -57,6 +57,11 @@ struct FpropParams {
   long long bwd_ld;
   const float* bwd_scale;
   const float* bwd_shift;
+  // Split-bf16 ("precise") operands, CTA-pair kernel only. Every activation row holds its values twice: the bf16
+  // rounding `hi` in channels [0, C) and the bf16-rounded remainder `lo = bf16(x - hi)` a_lo / o_lo elements further
+  // (hi + lo carries 16 mantissa bits). The K loop then has 3 * kreal chunks per tap — A_hi * W_hi, A_hi * W_lo,
+  // A_lo * W_hi against weights packed as [hi | lo | hi] per tap — and the epilogue stores both halves of the output.
+  int prec, kreal, a_lo, o_lo;
   int* err;
 };
 // CTAs the CTA-pair kernel launches for this problem (needs the current device: occupancy query on first use)
@@ -89,6 +94,9 @@ struct WgradParams {
   int cu, cv;
   float* ws;
   long long split_stride, tap_stride, m_stride, n_stride;
+  // split-bf16 operands (see FpropParams): passes = 3 runs every pixel tile three times, U_hi * V_hi, U_hi * V_lo and
+  // U_lo * V_hi, into the same accumulators; u_lo / v_lo = channel offset of the lo halves. passes = 1 otherwise.
+  int passes, u_lo, v_lo;
   int* err;
 };
 cudaError_t launch_wgrad(const CUtensorMap& mapU, const CUtensorMap& mapV, const WgradParams& p, int bn, int halo,
@@ -188,5 +196,25 @@ struct AdamWJob {       // layout == b200cd_adamw_job (include/b200cd.h)
 };
 cudaError_t launch_adamw(const AdamWJob* jobs, int njobs, long long total_blocks, float decay, float step_size, float omb1,
                          float b2, float omb2, float eps, float sqrt_bc2, cudaStream_t st);
+
+
+// split-bf16 ("precise") variants (elementwise_hp.cu); same arguments as the bf16-storage launchers above
+cudaError_t launch_pack_input_hp(const float* src0, const float* src1, int csrc, int c_lo, int nc, int cat_mode, int B,
+                                 int H, int W, int kpad, void* out, cudaStream_t st);
+int pack_job_blocks_hp(int mode, int d0, int d1, int kpad);
+cudaError_t launch_pack_weights_hp_batched(const PackJob* jobs, int njobs, long long total_blocks, cudaStream_t st);
+cudaError_t launch_bn_apply_hp(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
+                               int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
+                               void* pool, long long ld_p, void* dif, long long ld_d, void* pool_idx, cudaStream_t st);
+cudaError_t launch_bn_bwd_reduce_hp(const void* r, long long ld_r, const float* scale, const float* shift,
+                                    const GradSrcs& srcs, int n_img, int H, int W, int C, int G, int nblk,
+                                    float* partial, cudaStream_t st);
+cudaError_t launch_bn_bwd_dx_hp(const void* r, long long ld_r, const float* scale, const float* shift,
+                                const float* coefA, const float* coefB, const GradSrcs& srcs, int n_img, int H, int W,
+                                int C, int G, int nblk, void* dr, long long ld_dr, cudaStream_t st);
+cudaError_t launch_head_fwd_hp(const void* a0, long long ld0, const void* a1, long long ld1, int C, const float* w,
+                               const float* b, long long npix, float* logits, cudaStream_t st);
+cudaError_t launch_colsum_hp(const void* x, long long ld, int C, const float* wgt, long long npix, int nblk,
+                             float* partial, cudaStream_t st);
 
 }  // namespace b200cd

@@ -185,13 +185,16 @@ class StepEngine:
     """Builds and runs the plan for `net` (one of the drop-in classes in networks.py)."""
 
     def __init__(self, net: nn.Module, B: int, H: int, W: int, train: bool, device: torch.device,
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, precise: bool = False):
         if train and (H % 16 != 0 or W % 16 != 0):
             raise ValueError(f"b200cd engine: training tiles must be multiples of 16 (got {H}x{W})")
         if H < 16 or W < 16:
             raise ValueError(f"b200cd engine: tiles smaller than 16x16 vanish in the four MaxPool levels (got {H}x{W})")
         self.net, self.B, self.H, self.W, self.train, self.device = net, B, H, W, train, device
         self.use_graphs = use_graphs
+        # precise: split-bf16 storage (hi + lo halves, 16 mantissa bits) and three-MMA products — the mode that meets
+        # the reference-fp32 tolerance (include/b200cd.h, ABI version 2); default is single-bf16 storage (fast)
+        self.precise = bool(precise)
         self.stages: list[Stage] = []
         self.upconvs: list[UpConv] = []
         self.heads: list[Head] = []
@@ -247,6 +250,13 @@ class StepEngine:
         self.mem_bytes += t.numel() * t.element_size()
         return t
 
+    def _act(self, n: int, H: int, W: int, C: int) -> torch.Tensor:
+        """An NHWC bf16 activation / gradient buffer; in the precise mode the hi half of a [hi | lo] row."""
+        if not self.precise:
+            return self._new(n, H, W, C)
+        self.mem_bytes += 4 * n * H * W * C
+        return ops.split_alloc((n, H, W, C), self.device)
+
     # ------------------------------------------------------------------------------------------------
     # building blocks
     # ------------------------------------------------------------------------------------------------
@@ -256,23 +266,25 @@ class StepEngine:
         C = conv.out_channels
         if C % 64 != 0 or (not first and conv.in_channels % 64 != 0):
             raise ValueError(f"b200cd engine: channel counts must be multiples of 64 ({name}: {conv.in_channels}->{C})")
-        st.r = self._new(n_img, H, W, C)
+        km = 3 if self.precise else 1   # K-tripled [hi | lo | hi] weight operands in the precise mode
+        st.r = self._act(n_img, H, W, C)
         for k in ("mean", "invstd", "scale", "shift"):
             setattr(st, k, self._new(G, C, dtype=torch.float32))
         if first:
-            st.Wf = self._new(C, in_view.shape[3])
+            st.Wf = self._new(C, km * in_view.shape[3])
         else:
-            st.Wf = self._new(C, 9 * conv.in_channels)
+            st.Wf = self._new(C, km * 9 * conv.in_channels)
             if self.train:
-                st.Wd = self._new(conv.in_channels, 9 * C)
+                st.Wd = self._new(conv.in_channels, km * 9 * C)
         if self.train:
-            st.dr = self._new(n_img, H, W, C)
+            st.dr = self._act(n_img, H, W, C)
         tiles = ops.conv_gemm_tiles(H, W)
         # statistics rows per stat-group: one per 128-pixel tile, or (CTA-pair kernel) one per CTA and epilogue group
         st.stat_rows, st.stat_per_cta = (n_img // G) * tiles, False
         if self.device.type == "cuda":
             ka = in_view.shape[3] if first else conv.in_channels
-            st.stat_rows, st.stat_per_cta = ops.conv_stat_rows(n_img, H, W, ka, C, G, mode=1 if first else 0)
+            st.stat_rows, st.stat_per_cta = ops.conv_stat_rows(n_img, H, W, ka, C, G, mode=1 if first else 0,
+                                                               prec=self.precise)
         self._ws_need["stats"] = max(self._ws_need["stats"], G * st.stat_rows * C * 2)
         self._ws_need["stats2"] = max(self._ws_need["stats2"], 32 * G * C * 2)
         if self.train:
@@ -284,11 +296,11 @@ class StepEngine:
         """dc.conv = Sequential(conv, bn, relu, conv, bn, relu). Returns (stage1, stage2); stage2.outs is set by the caller."""
         seq = dc.conv
         s1 = self._stage(f"{name}.0", seq[0], seq[1], in_view, n_img, H, W, G, order_rev, first)
-        a1 = self._new(n_img, H, W, s1.cout)
+        a1 = self._act(n_img, H, W, s1.cout)
         s1.outs = {"a": a1}
         s2 = self._stage(f"{name}.3", seq[3], seq[4], a1, n_img, H, W, G, order_rev)
         if self.train:
-            s2.d_in = self._new(n_img, H, W, s1.cout)
+            s2.d_in = self._act(n_img, H, W, s1.cout)
             s1.srcs = [{"kind": 1, "t": s2.d_in}]
         return s1, s2
 
@@ -300,8 +312,9 @@ class StepEngine:
         cin = nc if siamese else 2 * nc
         assert inc.conv.conv[0].in_channels == cin, f"{tag}: first conv expects {inc.conv.conv[0].in_channels} channels, data has {cin}"
         kpad = _kpad(cin)
-        cols = self._new(n_img, H, W, kpad)
-        self.fwd_ops.append(lambda: ops.pack_input(self.x_t1, self.x_t2, c_lo, nc, 0 if siamese else 1, kpad, out=cols))
+        cols = self._act(n_img, H, W, kpad)
+        self.fwd_ops.append(lambda: ops.pack_input(self.x_t1, self.x_t2, c_lo, nc, 0 if siamese else 1, kpad, out=cols,
+                                                   prec=self.precise))
         self.fwd_branch.append(self._cur_branch)
         levels = []
         s1, s2 = self._double_conv(f"{tag}.inc", inc.conv, cols, n_img, H, W, G, first=True)
@@ -309,14 +322,14 @@ class StepEngine:
         h, w = H, W
         prev = s2
         for lname, down in encoder.down_seq.items():
-            pool = self._new(n_img, h // 2, w // 2, prev.cout)
+            pool = self._act(n_img, h // 2, w // 2, prev.cout)
             prev.outs["pool"] = pool
             pidx = self._new(n_img, h // 2, w // 2, prev.cout, dtype=torch.uint8) if self.train else None
             prev.outs["pool_idx"] = pidx
             h, w = h // 2, w // 2
             d1, d2 = self._double_conv(f"{tag}.{lname}", down.mpconv[1], pool, n_img, h, w, G)
             if self.train:
-                d1.d_in = self._new(n_img, h, w, prev.cout)  # gradient w.r.t. the pooled tensor
+                d1.d_in = self._act(n_img, h, w, prev.cout)  # gradient w.r.t. the pooled tensor
                 prev.srcs.append({"kind": 2, "t": d1.d_in, "w": pidx})
             levels.append(d2)
             prev = d2
@@ -332,14 +345,14 @@ class StepEngine:
         deep = levels[-1]
         # x entering the first Up: deepest feature (or its difference)
         if mode == "diff":
-            x = self._new(nb, deep.H, deep.W, deep.cout)
+            x = self._act(nb, deep.H, deep.W, deep.cout)
             deep.outs["dif"] = x
             deep.outs["diff"] = True
             deep.outs.setdefault("a", None)
         else:
             x = deep.outs.get("a")
             if x is None:
-                x = self._new(enc_n, deep.H, deep.W, deep.cout)
+                x = self._act(enc_n, deep.H, deep.W, deep.cout)
                 deep.outs["a"] = x
         last = None
         d_x_prev_consumer = None  # (stage whose srcs receive d_x)
@@ -350,7 +363,7 @@ class StepEngine:
             c = up.up.in_channels
             assert skip_stage.cout == c, f"{tag}.{uname}: skip has {skip_stage.cout} channels, Up expects {c}"
             Hs, Ws = skip_stage.H, skip_stage.W
-            cat = self._new(nb, Hs, Ws, 2 * c)
+            cat = self._act(nb, Hs, Ws, 2 * c)
             # skip half of the concat buffer, written by the encoder's apply kernel
             if mode == "diff":
                 # the activation itself is not materialised: pool and t2 - t1 are produced from registers
@@ -372,16 +385,17 @@ class StepEngine:
                 # MaxPool floored an odd level: the reference pads the up-sampled tensor to the skip's size with
                 # diff // 2 on the top / left (utils/networks.py:440-443)
                 assert not self.train and 0 <= Hs - 2 * hx <= 1 and 0 <= Ws - 2 * wx <= 1
-                uc.dense = self._new(nb, 2 * hx, 2 * wx, c)
+                uc.dense = self._act(nb, 2 * hx, 2 * wx, c)
                 uc.pad = ((Hs - 2 * hx) // 2, (Ws - 2 * wx) // 2)
-            uc.Wf = self._new(4 * c, c)
+            km = 3 if self.precise else 1
+            uc.Wf = self._new(4 * c, km * c)
             self.upconvs.append(uc)
             d_cat = None
             if self.train:
-                d_cat = self._new(nb, Hs, Ws, 2 * c)
-                uc.Wd = self._new(c, 4 * c)
+                d_cat = self._act(nb, Hs, Ws, 2 * c)
+                uc.Wd = self._new(c, km * 4 * c)
                 uc.d_out = d_cat[..., c:]
-                uc.d_x = self._new(nb, Hs // 2, Ws // 2, c)
+                uc.d_x = self._act(nb, Hs // 2, Ws // 2, c)
                 # gradient of the skip half flows back into the encoder stage
                 if mode == "diff":
                     skip_stage.srcs.append({"kind": 1, "t": d_cat[..., :c], "n_mod": nb, "scale_lo": -1.0, "scale_hi": 1.0})
@@ -396,7 +410,7 @@ class StepEngine:
             s1, s2 = self._double_conv(f"{tag}.{uname}", up.conv, cat, nb, Hs, Ws, G, order_rev)
             if self.train:
                 s1.d_in = d_cat
-            xo = self._new(nb, Hs, Ws, s2.cout)
+            xo = self._act(nb, Hs, Ws, s2.cout)
             s2.outs = {"a": xo}
             self._up_plan.append((uc, s1, s2))
             x = xo
@@ -486,9 +500,9 @@ class StepEngine:
         # gradient) by ONE launch at the start of the forward pass: the fp32 master weights belong to the optimizer and
         # change every step, and they are read once
         if self.device.type == "cuda" and self._pack_specs:
-            tab, nj, blocks, elems = ops.make_pack_jobs(self._pack_specs, self.device)
+            tab, nj, blocks, elems = ops.make_pack_jobs(self._pack_specs, self.device, prec=self.precise)
             src = sum(sp[1].numel() for sp in self._pack_specs)
-            self.pack_fwd.append(lambda: ops.pack_weights_batched(tab, nj, blocks, elems, src))
+            self.pack_fwd.append(lambda: ops.pack_weights_batched(tab, nj, blocks, elems, src, prec=self.precise))
 
     # ------------------------------------------------------------------------------------------------
     def _alloc_ws(self) -> None:
@@ -527,15 +541,17 @@ class StepEngine:
         spl = max(1, min(32, tpg // 64))
         sg = st.G if st.stat_per_cta else 0
         outs = st.outs
+        prec = eng.precise
 
         def run():
             stats = eng.ws_stats[st.branch] if train else None
-            ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats, stat_groups=sg)
+            ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats, stat_groups=sg, prec=prec)
             ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2[st.branch], bn.weight, bn.bias, bn.running_mean,
                          bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
                          st.order_rev, st.mean, st.invstd, st.scale, st.shift)
             ops.bn_apply(st.r, st.scale, st.shift, st.G, bool(outs.get("diff", False)), a=outs.get("a"),
-                         a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"), pool_idx=outs.get("pool_idx"))
+                         a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"), pool_idx=outs.get("pool_idx"),
+                         prec=prec)
 
         eng.fwd_ops.append(run)
         eng.fwd_branch.append(st.branch)
@@ -550,19 +566,20 @@ class StepEngine:
                 else:
                     self._pack_specs.append((3, uc.up.weight, uc.Wf, 0))
                 if uc.dense is None:
-                    self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias))
+                    self.fwd_ops.append(lambda uc=uc: ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.out, bias=uc.up.bias,
+                                                                    prec=self.precise))
                     self.fwd_branch.append(10 if uc.fork_before_fwd else uc.branch)
                 else:
                     def run_up(uc=uc):
-                        ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.dense, bias=uc.up.bias)
-                        ops.pad_copy(uc.dense, uc.out, uc.pad[0], uc.pad[1])
+                        ops.conv_gemm(1, 1, uc.x, uc.Wf, uc.dense, bias=uc.up.bias, prec=self.precise)
+                        ops.pad_copy(uc.dense, uc.out, uc.pad[0], uc.pad[1], prec=self.precise)
                     self.fwd_ops.append(run_up)
                     self.fwd_branch.append(10 if uc.fork_before_fwd else uc.branch)
             self._emit_stage_fwd(st)
         for hd in self.heads:
             def run(hd=hd):
                 a1 = hd.inputs[1] if len(hd.inputs) > 1 else None
-                ops.head_fwd(hd.inputs[0], a1, hd.conv.weight.view(-1), hd.conv.bias, hd.logits)
+                ops.head_fwd(hd.inputs[0], a1, hd.conv.weight.view(-1), hd.conv.bias, hd.logits, prec=self.precise)
             self.fwd_ops.append(run)
             self.fwd_branch.append(-1)
 
@@ -635,7 +652,7 @@ class StepEngine:
         """The stage whose BatchNorm backward has `grad` as its one and only (direct, unscaled) gradient source and the
         same dense layout: its reduce pass can run in the epilogue of the kernel that writes `grad`. Allocates the
         stage's partial-sum buffer on first use."""
-        if not FUSE_BN_BWD_REDUCE or self.device.type != "cuda" or not ops.FPROP_PAIR:
+        if not FUSE_BN_BWD_REDUCE or self.device.type != "cuda" or not ops.FPROP_PAIR or self.precise:
             return None
         for ps in self.stages:
             if len(ps.srcs) == 1 and ps.srcs[0]["kind"] == 1 and ps.srcs[0]["t"] is grad and not ps.srcs[0].get("n_mod"):
@@ -675,14 +692,16 @@ class StepEngine:
         up_rows = 0
         uc_of = {id(s1): uc for (uc, s1, s2) in eng._up_plan}.get(id(st))
         if uc_of is not None and prod is None and eng.device.type == "cuda" and ops.FPROP_PAIR and UP_BIAS_FROM_STATS:
-            rows, per_cta = ops.conv_stat_rows(st.n_img, st.H, st.W, st.cout, st.cin, 1)
+            rows, per_cta = ops.conv_stat_rows(st.n_img, st.H, st.W, st.cout, st.cin, 1, prec=eng.precise)
             if per_cta:
                 up_rows = uc_of.bias_rows = rows
                 eng._ws_need["upstats"] = max(eng._ws_need.get("upstats", 0), rows * st.cin * 2)
 
+        prec = eng.precise
+
         def run():
             ops.bn_bwd(st.r, st.mean, st.invstd, st.scale, st.shift, ops.make_srcs(srcs), st.G, eng.ws_bnbwd[st.branch], ggam, gbet,
-                       st.dr, sums=st.bwd_sums, sum_rows=st.bwd_sum_rows)
+                       st.dr, sums=st.bwd_sums, sum_rows=st.bwd_sum_rows, prec=prec)
             ws = eng.ws_wgrad.narrow(0, off, size)
             # input gradient first (the next layer's BatchNorm backward waits for it), then the weight gradient on the
             # side stream: it starts when the dgrad kernel leaves the SMs and runs under the next HBM-bound kernels
@@ -692,17 +711,19 @@ class StepEngine:
                 elif up_rows:
                     # d_in is the concat-buffer gradient of an Up: its per-channel pixel sums (upper half = the
                     # transposed-conv bias gradient) come out of this launch's per-CTA statistics
-                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats[st.branch], stat_groups=1)
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, stats=eng.ws_upstats[st.branch], stat_groups=1, prec=prec)
                 else:
-                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in)
+                    ops.conv_gemm(0, 0, st.dr, st.Wd, st.d_in, prec=prec)
             with eng._side():
                 if role == "first":
-                    ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1)
+                    ops.wgrad_gemm(1, 1, 0, st.dr, st.in_view, ws, splits, cout * kp, 0, kp, 1, prec=prec)
                     ops.wgrad_reduce(ws, splits, cout * kp, 1, cout, cin, 9, gw)
                 elif role == "pos":
-                    ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1, splits2)
+                    ops.wgrad_gemm(0, 1, 1, st.dr, st.in_view, ws, splits, 9 * cout * cin, cout * cin, cin, 1, splits2,
+                                   prec=prec)
                 else:
-                    ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2)
+                    ops.wgrad_gemm(0, -1, 1, st.in_view, st.dr, ws, splits, 9 * cout * cin, cout * cin, 1, cin, splits2,
+                                   prec=prec)
 
         eng.bwd_ops.append(run)
         eng.bwd_branch.append(-10 if st.join_before_bwd else st.branch)
@@ -730,13 +751,14 @@ class StepEngine:
             if uc.bias_rows:
                 ops.stat_rowsum(eng.ws_upstats[uc.branch], uc.bias_rows, 2 * c, c, c, gb)
             else:
-                ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum[uc.branch], gb)
+                ops.colsum(uc.d_out, None, npix, nblk, eng.ws_colsum[uc.branch], gb, prec=eng.precise)
             if prod is not None:
                 ops.conv_gemm_bnbwd(2, uc.d_out, uc.Wd, uc.d_x, prod.r, prod.scale, prod.shift, prod.bwd_sums, prod.G)
             else:
-                ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x)
+                ops.conv_gemm(2, 0, uc.d_out, uc.Wd, uc.d_x, prec=eng.precise)
             with eng._side():
-                ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1)
+                ops.wgrad_gemm(2, 1, 0, uc.x, uc.d_out, eng.ws_wgrad.narrow(0, off, size), splits, 4 * c * c, c * c, c, 1,
+                               prec=eng.precise)
 
         eng.bwd_ops.append(run)
         eng.bwd_branch.append(uc.branch)
@@ -764,7 +786,7 @@ class StepEngine:
             def run(hd=hd, C=C, npix=npix, nblk=nblk, gw=gw, gb=gb):
                 dz = hd.dz.view(-1)
                 for i, a in enumerate(hd.inputs):
-                    ops.colsum(a, dz, npix, nblk, self.ws_colsum[0], gw[i * C:(i + 1) * C])
+                    ops.colsum(a, dz, npix, nblk, self.ws_colsum[0], gw[i * C:(i + 1) * C], prec=self.precise)
                 ops.colsum(None, dz, npix, nblk, self.ws_colsum[0], gb)
             self.bwd_ops.append(run)
             self.bwd_branch.append(-1)

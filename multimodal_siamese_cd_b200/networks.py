@@ -10,6 +10,7 @@ There is no CPU path: calling a network on CPU tensors raises.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from pathlib import Path
 
@@ -134,9 +135,20 @@ class B200Net(nn.Module):
         self.cfg = cfg
         self._engines: "OrderedDict[tuple, StepEngine]" = OrderedDict()
         self.use_cuda_graphs = True
+        # "fast": single-bf16 storage / operands (the throughput mode). "precise": split-bf16 storage and three-MMA
+        # products, which meets the reference-fp32 tolerance. Default from B200CD_PRECISION.
+        self.precision = os.environ.get("B200CD_PRECISION", "fast")
+
+    def set_precision(self, mode: str) -> "B200Net":
+        if mode not in ("fast", "precise"):
+            raise ValueError(f"precision must be 'fast' or 'precise' (got {mode!r})")
+        self.precision = mode
+        return self
 
     def engine_for(self, B: int, H: int, W: int, train: bool, device: torch.device) -> StepEngine:
-        key = (B, H, W, train, device.index)
+        if self.precision not in ("fast", "precise"):
+            raise ValueError(f"B200CD_PRECISION / net.precision must be 'fast' or 'precise' (got {self.precision!r})")
+        key = (B, H, W, train, device.index, self.precision)
         eng = self._engines.get(key)
         if eng is not None and eng.params_moved():
             del self._engines[key]
@@ -145,7 +157,8 @@ class B200Net(nn.Module):
             while len(self._engines) >= self._MAX_ENGINES:
                 self._engines.popitem(last=False)
             with torch.cuda.device(device):
-                eng = StepEngine(self, B, H, W, train, device, use_graphs=self.use_cuda_graphs)
+                eng = StepEngine(self, B, H, W, train, device, use_graphs=self.use_cuda_graphs,
+                                 precise=self.precision == "precise")
             self._engines[key] = eng
         else:
             self._engines.move_to_end(key)

@@ -4,6 +4,9 @@ Activations are torch bf16 tensors of logical shape [n, H, W, C] whose last dim 
 pixel stride `ld = t.stride(2)` may exceed C (a channel slice of a concat buffer). These functions only
 extract pointers/strides and launch on torch's current CUDA stream; they never compute on the CPU and
 raise on CPU tensors.
+
+`prec=True` selects the split-bf16 ("precise") kernels: the tensor passed is the hi half of a [hi | lo] row and its
+lo half lies ld / 2 elements behind it (see include/b200cd.h, ABI version 2, and `split_alloc` / `lo_half` below).
 """
 from __future__ import annotations
 
@@ -86,6 +89,32 @@ def _nhwc(t: torch.Tensor) -> tuple[int, int, int, int, int]:
     return n, H, W, Cc, ld
 
 
+def split_alloc(shape, device, zero: bool = False) -> torch.Tensor:
+    """A split-bf16 activation [n, H, W, C]: allocates [n, H, W, 2C] and returns the hi half (a view with pixel stride
+    2C); the lo half is `lo_half(view)`. Channel slices of the returned view keep the ld / 2 relation."""
+    n, H, W, Cc = shape
+    buf = (torch.zeros if zero else torch.empty)((n, H, W, 2 * Cc), device=device, dtype=torch.bfloat16)
+    return buf[..., :Cc]
+
+
+def lo_half(t: torch.Tensor) -> torch.Tensor:
+    """The lo half of a split-bf16 view (same shape / strides, ld / 2 elements further)."""
+    return t.as_strided(t.shape, t.stride(), t.storage_offset() + t.stride(2) // 2)
+
+
+def split_from_float(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [n, H, W, C] -> split-bf16 view holding hi = bf16(x), lo = bf16(x - hi) (tests and tools)."""
+    out = split_alloc(tuple(x.shape), x.device)
+    hi = x.to(torch.bfloat16)
+    out.copy_(hi)
+    lo_half(out).copy_((x - hi.float()).to(torch.bfloat16))
+    return out
+
+
+def split_to_float(t: torch.Tensor) -> torch.Tensor:
+    return t.float() + lo_half(t).float()
+
+
 def device_status(dev: Optional[int] = None) -> None:
     """Synchronise and raise if any tensor-core kernel reported a pipeline time-out."""
     dev = torch.cuda.current_device() if dev is None else dev
@@ -95,17 +124,22 @@ def device_status(dev: Optional[int] = None) -> None:
 
 # ---------------------------------------------------------------------------------------------------------
 def pack_input(x0: torch.Tensor, x1: torch.Tensor, c_lo: int, nc: int, cat_mode: int, kpad: int,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, prec: bool = False) -> torch.Tensor:
     _require_cuda(x0, x1)
     assert x0.dtype == torch.float32 and x0.is_contiguous() and x1.is_contiguous() and x0.shape == x1.shape
     B, cs, H, W = x0.shape
     n_img = B if cat_mode else 2 * B
     if out is None:
-        out = torch.empty((n_img, H, W, kpad), device=x0.device, dtype=torch.bfloat16)
+        out = split_alloc((n_img, H, W, kpad), x0.device) if prec else \
+            torch.empty((n_img, H, W, kpad), device=x0.device, dtype=torch.bfloat16)
+    if prec:
+        assert _nhwc(out)[4] == 2 * kpad, "split im2col rows are [hi kpad | lo kpad]"
+    else:
+        assert out.is_contiguous()
     _count(1)
-    with _Prof("pack_input", 0.0, _nbytes(out) + 4.0 * 2 * B * nc * H * W):
-        _lib.check(_lib.load().b200cd_pack_input(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad,
-                                                 out.data_ptr(), _stream()))
+    fn = _lib.load().b200cd_pack_input_hp if prec else _lib.load().b200cd_pack_input
+    with _Prof("pack_input", 0.0, _nbytes(out) * (2 if prec else 1) + 4.0 * 2 * B * nc * H * W):
+        _lib.check(fn(x0.data_ptr(), x1.data_ptr(), cs, c_lo, nc, cat_mode, B, H, W, kpad, out.data_ptr(), _stream()))
     return out
 
 
@@ -135,7 +169,22 @@ def pack_weights(mode: int, w: torch.Tensor, kpad: int = 0, out: Optional[torch.
 _PACK_JOB_DTYPE = None
 
 
-def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int, int]:
+def packed_weight_shape(mode: int, d0: int, d1: int, kpad: int = 0, prec: bool = False) -> tuple[int, int]:
+    """Shape of the bf16 GEMM operand `mode` of a weight with leading dims (d0, d1); K is tripled ([hi | lo | hi] per
+    tap) in the split-bf16 mode."""
+    m = 3 if prec else 1
+    if mode == 0:
+        return (d0, 9 * d1 * m)
+    if mode == 1:
+        return (d1, 9 * d0 * m)
+    if mode == 2:
+        return (d0, kpad * m)
+    if mode == 3:
+        return (4 * d1, d0 * m)
+    return (d0, 4 * d1 * m)
+
+
+def make_pack_jobs(specs: Sequence[tuple], device, prec: bool = False) -> tuple[torch.Tensor, int, int, int]:
     """specs: (mode, weight fp32 tensor, out bf16 tensor, kpad[, mode2, out2 bf16 tensor]). Returns (device job table,
     njobs, total thread blocks, packed elements) for pack_weights_batched (b200cd_pack_job layout: three pointers,
     six int32, one int64 = 56 bytes)."""
@@ -158,7 +207,8 @@ def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, i
         assert out.data_ptr() % 4 == 0 and (out2 is None or out2.data_ptr() % 4 == 0), "packed operands are written 4 bytes at a time"
         arr[i] = (w.data_ptr(), out.data_ptr(), 0 if out2 is None else out2.data_ptr(), mode, mode2, w.shape[0],
                   w.shape[1], kpad, 0, blocks)
-        nb = lib.b200cd_pack_job_blocks(mode, w.shape[0], w.shape[1], kpad)
+        assert tuple(out.shape) == packed_weight_shape(mode, w.shape[0], w.shape[1], kpad, prec), (mode, out.shape)
+        nb = (lib.b200cd_pack_job_blocks_hp if prec else lib.b200cd_pack_job_blocks)(mode, w.shape[0], w.shape[1], kpad)
         assert nb > 0
         blocks += nb
         elems += out.numel() * (1 if out2 is None else 2)
@@ -166,11 +216,13 @@ def make_pack_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, i
     return table, len(specs), blocks, elems
 
 
-def pack_weights_batched(table: torch.Tensor, njobs: int, blocks: int, elems: int = 0, src_elems: int = 0) -> None:
+def pack_weights_batched(table: torch.Tensor, njobs: int, blocks: int, elems: int = 0, src_elems: int = 0,
+                         prec: bool = False) -> None:
     _require_cuda(table)
     _count(1)
+    fn = _lib.load().b200cd_pack_weights_hp_batched if prec else _lib.load().b200cd_pack_weights_batched
     with _Prof("pack_weights", 0.0, 2.0 * elems + 4.0 * src_elems):
-        _lib.check(_lib.load().b200cd_pack_weights_batched(table.data_ptr(), njobs, blocks, _stream()))
+        _lib.check(fn(table.data_ptr(), njobs, blocks, _stream()))
 
 
 def conv_gemm_tiles(H: int, W: int) -> int:
@@ -200,10 +252,11 @@ def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, sta
     return (1 if (halo and mode == 0) else 0) | (2 if wide else 0)
 
 
-def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int, mode: int = 0) -> tuple[int, bool]:
+def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int, mode: int = 0,
+                   prec: bool = False) -> tuple[int, bool]:
     """(rows per stat-group of the statistics buffer a 3x3 conv of this shape writes, per-CTA layout?). With the
     CTA-pair kernel the rows are per CTA and epilogue group (<= 296); otherwise one row per 128-pixel tile."""
-    flags = _conv_flags(mode, 0, N, ka, None, None, None, stat_groups)
+    flags = _conv_flags(mode, 0, N, ka, None, None, None, stat_groups) | (16 if prec else 0)
     rows = _lib.load().b200cd_conv_gemm_stat_rows(mode, 0, flags, n_img, H, W, ka, N)
     if rows < 0:
         raise _lib.B200CDError("conv_gemm_stat_rows: unsupported shape")
@@ -214,15 +267,16 @@ def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int
 def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
               halo: Optional[bool] = None, wide: Optional[bool] = None, pair: Optional[bool] = None,
-              stat_groups: int = 0) -> None:
-    """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x)."""
+              stat_groups: int = 0, prec: bool = False) -> None:
+    """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x).
+    prec: A / out are split-bf16 views, Bw is the K-tripled [hi | lo | hi] operand."""
     _require_cuda(A, Bw, out)
     n, Ha, Wa, ka, a_ld = _nhwc(A)
     H, W = (Ha // 2, Wa // 2) if mode == 2 else (Ha, Wa)
     no, Ho, Wo, Co, o_ld = _nhwc(out)
     N = Bw.shape[0]
     taps = 9 if mode == 0 else (1 if mode == 1 else 4)
-    assert Bw.dtype == torch.bfloat16 and Bw.is_contiguous() and Bw.shape[1] == taps * ka
+    assert Bw.dtype == torch.bfloat16 and Bw.is_contiguous() and Bw.shape[1] == taps * ka * (3 if prec else 1)
     if out_mode == 1:
         assert (no, Ho, Wo) == (n, 2 * H, 2 * W) and N == 4 * Co
         cout = Co
@@ -230,9 +284,14 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
     flags = _conv_flags(mode, out_mode, N, ka, halo, wide, pair, stat_groups if stats is not None else 0)
+    if prec:
+        assert flags & 4, "split-bf16 operands need the CTA-pair kernel"
+        flags |= 16
     _count(1)
     fam = "fprop3x3" if mode == 0 else ("gemm1tap" if mode == 1 else "convT_dgrad")
-    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out, Bw), f"{n}x{H}x{W} k{ka}->n{N} om{out_mode} halo{flags}"):
+    # algorithmic flops: the reference's contraction (the three split MMAs are how it is computed, not extra work)
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out) * (2 if prec else 1) + _nbytes(Bw),
+               f"{n}x{H}x{W} k{ka}->n{N} om{out_mode} halo{flags}"):
         _lib.check(_lib.load().b200cd_conv_gemm(mode, out_mode, flags, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N, cout,
                                                 out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
@@ -273,8 +332,9 @@ def wgrad_ctas_per_split(mode: int, halo: int, cu: int, cv: int) -> int:
 
 
 def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor, ws: torch.Tensor, splits: int,
-               split_stride: int, tap_stride: int, m_stride: int, n_stride: int, splits2: int = 0) -> None:
-    """G2. U: NHWC view at the GEMM resolution; V: NHWC view (mode 2: at 2x)."""
+               split_stride: int, tap_stride: int, m_stride: int, n_stride: int, splits2: int = 0,
+               prec: bool = False) -> None:
+    """G2. U: NHWC view at the GEMM resolution; V: NHWC view (mode 2: at 2x). prec: split-bf16 views."""
     _require_cuda(U, V, ws)
     n, H, W, cu, u_ld = _nhwc(U)
     nv, Hv, Wv, cv, v_ld = _nhwc(V)
@@ -282,11 +342,11 @@ def wgrad_gemm(mode: int, sign: int, halo: int, U: torch.Tensor, V: torch.Tensor
     assert ws.dtype == torch.float32
     _count(1)
     taps = 9 if mode == 0 else (1 if mode == 1 else 4)
-    with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) + 4.0 * splits * taps * cu * cv,
+    fn = _lib.load().b200cd_wgrad_gemm_hp if prec else _lib.load().b200cd_wgrad_gemm
+    with _Prof("wgrad", 2.0 * n * H * W * cu * cv * taps, _nbytes(U, V) * (2 if prec else 1) + 4.0 * splits * taps * cu * cv,
                f"{n}x{H}x{W} m{cu} n{cv} mode{mode} sign{sign} splits{splits}+{splits2}"):
-        _lib.check(_lib.load().b200cd_wgrad_gemm(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W,
-                                                 ws.data_ptr(), splits, splits2, split_stride, tap_stride, m_stride,
-                                                 n_stride, _stream()))
+        _lib.check(fn(mode, sign, halo, U.data_ptr(), u_ld, cu, V.data_ptr(), v_ld, cv, n, H, W, ws.data_ptr(), splits,
+                      splits2, split_stride, tap_stride, m_stride, n_stride, _stream()))
 
 
 def wgrad_reduce(ws: torch.Tensor, splits: int, split_stride: int, layout: int, d0: int, d1: int, taps: int,
@@ -356,7 +416,7 @@ def bn_stats(partial: Optional[torch.Tensor], ld: int, C_: int, tiles_per_group:
 
 def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, diff: bool,
              a: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None, pool: Optional[torch.Tensor] = None,
-             dif: Optional[torch.Tensor] = None, pool_idx: Optional[torch.Tensor] = None) -> None:
+             dif: Optional[torch.Tensor] = None, pool_idx: Optional[torch.Tensor] = None, prec: bool = False) -> None:
     _require_cuda(r, scale, shift)
     n, H, W, Cc, ld_r = _nhwc(r)
 
@@ -364,11 +424,11 @@ def bn_apply(r: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, G: int, 
         return 0 if t is None else _nhwc(t)[4]
 
     _count(1)
-    with _Prof("bn_apply", 0.0, _nbytes(r, a, a2, pool, dif),
+    fn = _lib.load().b200cd_bn_apply_hp if prec else _lib.load().b200cd_bn_apply
+    with _Prof("bn_apply", 0.0, _nbytes(r, a, a2, pool, dif) * (2 if prec else 1),
                f"{n}x{H}x{W}x{Cc} G{G} diff{int(diff)} pool{int(pool is not None)}"):
-        _lib.check(_lib.load().b200cd_bn_apply(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G,
-                                               int(diff), _ptr(a), ld(a), _ptr(a2), ld(a2), _ptr(pool), ld(pool),
-                                               _ptr(dif), ld(dif), _ptr(pool_idx), _stream()))
+        _lib.check(fn(r.data_ptr(), ld_r, scale.data_ptr(), shift.data_ptr(), n, H, W, Cc, G, int(diff), _ptr(a), ld(a),
+                      _ptr(a2), ld(a2), _ptr(pool), ld(pool), _ptr(dif), ld(dif), _ptr(pool_idx), _stream()))
 
 
 def make_srcs(srcs: Sequence[dict]) -> C.Array:
@@ -393,10 +453,20 @@ def bn_bwd_ws_floats(n: int, H: int, W: int, C_: int, G: int) -> int:
 
 def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
            srcs: C.Array, G: int, ws: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, dr: torch.Tensor,
-           sums: Optional[torch.Tensor] = None, sum_rows: int = 0) -> None:
+           sums: Optional[torch.Tensor] = None, sum_rows: int = 0, prec: bool = False) -> None:
     _require_cuda(r, dr, ws)
     n, H, W, Cc, ld_r = _nhwc(r)
     nsrc = sum(1.0 if s.kind == 1 else (0.25 if s.kind == 2 else 0.0) for s in srcs)
+    if prec:
+        assert sums is None, "the fused BatchNorm-backward reduce is a bf16-storage feature"
+        _count(3)
+        with _Prof("bn_bwd", 0.0, 2.0 * _nbytes(r) * (2.0 + 2.0 * nsrc + 1.0),
+                   f"{n}x{H}x{W}x{Cc} G{G} srcs{[s.kind for s in srcs]} hp"):
+            _lib.check(_lib.load().b200cd_bn_bwd_hp(r.data_ptr(), ld_r, mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(),
+                                                    shift.data_ptr(), srcs, n, H, W, Cc, G, ws.data_ptr(),
+                                                    dgamma.data_ptr(), dbeta.data_ptr(), dr.data_ptr(), _nhwc(dr)[4],
+                                                    _stream()))
+        return
     if sums is not None:
         # the reduce pass ran in the epilogue of the convolution that produced the gradient: finalize + dx only
         _count(2)
@@ -416,20 +486,25 @@ def bn_bwd(r: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, scale: tor
 
 
 def head_fwd(a0: torch.Tensor, a1: Optional[torch.Tensor], w: torch.Tensor, b: torch.Tensor,
-             logits: torch.Tensor) -> None:
+             logits: torch.Tensor, prec: bool = False) -> None:
     _require_cuda(a0, w, b, logits)
     n, H, W, Cc, ld0 = _nhwc(a0)
     ld1 = 0 if a1 is None else _nhwc(a1)[4]
     _count(1)
-    with _Prof("head_fwd", 0.0, _nbytes(a0, a1, logits)):
-        _lib.check(_lib.load().b200cd_head_fwd(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(),
-                                               n * H * W, logits.data_ptr(), _stream()))
+    fn = _lib.load().b200cd_head_fwd_hp if prec else _lib.load().b200cd_head_fwd
+    with _Prof("head_fwd", 0.0, _nbytes(a0, a1) * (2 if prec else 1) + _nbytes(logits)):
+        _lib.check(fn(a0.data_ptr(), ld0, _ptr(a1), ld1, Cc, w.data_ptr(), b.data_ptr(), n * H * W, logits.data_ptr(),
+                      _stream()))
 
 
-def pad_copy(src: torch.Tensor, dst: torch.Tensor, top: int, left: int) -> None:
+def pad_copy(src: torch.Tensor, dst: torch.Tensor, top: int, left: int, prec: bool = False) -> None:
     """dst (NHWC view, e.g. the upper half of a concat buffer) = src placed at (top, left), zero border:
     Up's centre pad, utils/networks.py:440-443."""
     _require_cuda(src, dst)
+    if prec:   # both halves of the split tensors: two plain copies
+        pad_copy(src, dst, top, left)
+        pad_copy(lo_half(src), lo_half(dst), top, left)
+        return
     n, h, w, Cc, ld_s = _nhwc(src)
     n2, H, W, C2, ld_d = _nhwc(dst)
     assert n == n2 and Cc == C2
@@ -440,16 +515,17 @@ def pad_copy(src: torch.Tensor, dst: torch.Tensor, top: int, left: int) -> None:
 
 
 def colsum(x: Optional[torch.Tensor], wgt: Optional[torch.Tensor], npix: int, nblk: int, ws: torch.Tensor,
-           out: torch.Tensor) -> None:
+           out: torch.Tensor, prec: bool = False) -> None:
     _require_cuda(ws, out)
     if x is None:
         Cc, ld = 1, 0
     else:
         Cc, ld = x.shape[3], x.stride(2)
     _count(2)
-    with _Prof("colsum", 0.0, npix * (2.0 * Cc if x is not None else 0.0) + (4.0 * npix if wgt is not None else 0.0)):
-        _lib.check(_lib.load().b200cd_colsum(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(),
-                                             _stream()))
+    hp = prec and x is not None
+    fn = _lib.load().b200cd_colsum_hp if hp else _lib.load().b200cd_colsum
+    with _Prof("colsum", 0.0, npix * ((4.0 if hp else 2.0) * Cc if x is not None else 0.0) + (4.0 * npix if wgt is not None else 0.0)):
+        _lib.check(fn(_ptr(x), ld, Cc, _ptr(wgt), npix, nblk, ws.data_ptr(), out.data_ptr(), _stream()))
 
 
 def stat_rowsum(stats: torch.Tensor, rows: int, ld: int, c_off: int, Cc: int, out: torch.Tensor) -> None:

@@ -44,12 +44,16 @@ def grad_report(got: dict, ref: dict) -> dict:
 
 
 def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alpha: float = 0.5, path: str = "dropin",
-             corr: bool = False, graphs: bool = True, steps: int = 1) -> dict:
-    """Returns error metrics of the CUDA path vs the bf16-storage oracle (q) and the exact fp32 oracle (x)."""
+             corr: bool = False, graphs: bool = True, steps: int = 1, precision: str = "fast", fp64: bool = False,
+             skip_q: bool = False) -> dict:
+    """Returns error metrics of the CUDA path vs the bf16-storage oracle (q) and the exact fp32 oracle (x = the
+    reference's arithmetic). fp64=True adds (d): the same step in float64, plus the reference's OWN fp32-vs-fp64
+    error (`floor_*`) — the yardstick north_star's tolerance has to be read against."""
     dev = torch.device("cuda", 0)
     cfg = synthetic_cfg(mtype, in_channels=cin, topology=topo)
     torch.manual_seed(cfg.SEED)
     net = networks.create_network(cfg)
+    net.module.set_precision(precision)
     sd0 = {k: v.clone() for k, v in net.state_dict().items()}
     xc = 6 if mtype in TWO_STREAM else cin
     batch = O.synthetic_batch(B, xc, H, W, seed=7, corr=corr)
@@ -102,10 +106,25 @@ def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alph
     # analytically-zero gradients are emitted as exact zeros; the reference carries ~1e-9 noise there
     res["prebn_bias_grad_max"] = max(g.abs().max().item() for n, g in got_grads.items() if is_prebn_bias(n))
     sd_after = {k[len("module."):]: v.detach().cpu() for k, v in net.state_dict().items()}
-    for tag, q in (("q", True), ("x", False)):
-        sd = O.clone_state(sd0)
-        ref = O.train_step(mtype, sd, batch, kind=kind, alpha=alpha, q=q)
+    ref_x = None
+    for tag, q in (("q", True), ("x", False), ("d", False)):
+        if (tag == "q" and skip_q) or (tag == "d" and not fp64):
+            continue
+        if tag == "d":
+            sd = O.clone_state(sd0, dtype=torch.float64)
+            b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+            ref = O.train_step(mtype, sd, b64, kind=kind, alpha=alpha, q=False)
+        else:
+            sd = O.clone_state(sd0)
+            ref = O.train_step(mtype, sd, batch, kind=kind, alpha=alpha, q=q)
         ro = ref["outs"] if isinstance(ref["outs"], tuple) else (ref["outs"],)
+        if tag == "x":
+            ref_x = (ro, ref)
+        if tag == "d" and ref_x is not None:   # the reference's own fp32 arithmetic against fp64
+            res["floor_logits"] = max(rel(a.detach(), b.detach()) for a, b in zip(ref_x[0], ro))
+            res["floor_loss"] = abs(ref_x[1]["loss"].item() - ref["loss"].item())
+            res["floor_grads"] = grad_report(ref_x[1]["grads"], ref["grads"])
+            res["floor_mask_flips"] = int(((ref_x[0][0].detach() > 0) != (ro[0].detach() > 0)).sum())
         res[f"logits_{tag}"] = max(rel(g, r.detach()) for g, r in zip(got_outs, ro))
         res[f"loss_{tag}"] = abs(got_loss - ref["loss"].item())
         res[f"grads_{tag}"] = grad_report(got_grads, ref["grads"])
@@ -115,8 +134,9 @@ def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alph
         res[f"mask_flips_{tag}"] = int((pm != gm).sum())
         # flips on pixels whose reference logit has margin (identity is only meaningful away from 0)
         res[f"margin_flips_{tag}"] = int(((pm != gm) & (ro[0].detach().abs() >= 0.05)).sum())
+        res[f"margin3_flips_{tag}"] = int(((pm != gm) & (ro[0].detach().abs() >= 1e-3)).sum())
         res[f"f1_diff_{tag}"] = abs(gf1.item() - rf1.item())
-        if q:
+        if tag == ("x" if precision == "precise" else "q"):   # running statistics against the oracle of the same storage
             bn_err = 0.0
             for k, v in sd.items():
                 if k.endswith("running_mean") or k.endswith("running_var"):

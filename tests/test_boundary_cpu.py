@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/b200cd.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.b200cd_abi_version() == 1
+    assert lib.b200cd_abi_version() == 2
     # pure host helpers may be called without a GPU
     assert lib.b200cd_conv_gemm_tiles(256, 256) == 512
     assert lib.b200cd_wgrad_tiles(2, 32, 32) == 32

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import gpu_checks as gc
+import gpu_checks_hp as gch
 
 pytestmark = pytest.mark.gpu
 
@@ -17,6 +18,15 @@ def test_kernel(name):
     assert res["ok"], res
     if "ulp_frac" in res:
         assert res["ulp_frac"] < res.get("ulp_tol", 5e-3) and res["rel_l2_rounded"] < 5e-4, res
+
+
+@pytest.mark.parametrize("name", list(gch.HP_CHECKS))
+def test_kernel_split_bf16(name):
+    """The "precise" (split-bf16, ABI version 2) kernels against torch fp64 on the values the split tensors hold."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    res = gch.HP_CHECKS[name]()
+    assert res["ok"], res
 
 
 def test_device_prefetcher_order_and_contents():
