@@ -10,8 +10,8 @@
  * Conventions
  *   - plain pointers and sizes; no torch / C++ types cross this boundary.
  *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory (inputs, outputs,
- *     workspaces); the library allocates nothing in steady state (one 4-byte error flag per device at
- *     b200cd_init).
+ *     workspaces); the library allocates nothing in steady state (one 4-byte host-mapped error flag per
+ *     device at b200cd_init).
  *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
  *   - activations are NHWC bf16 with an explicit element stride per pixel (`ld`, multiple of 8), so
  *     channel slices of a concatenation buffer are addressed without copies; base pointers must be
@@ -36,7 +36,7 @@ extern "C" {
 #define B200CD_ERR_ALIGN 2
 #define B200CD_ERR_ARCH 3
 #define B200CD_ERR_CUDA 4
-#define B200CD_ERR_DEVICE 5 /* a kernel reported a pipeline time-out (see b200cd_device_status) */
+#define B200CD_ERR_DEVICE 5 /* a kernel's pipeline timed out and trapped (see b200cd_device_status) */
 
 #define B200CD_ABI_VERSION 2
 
@@ -47,8 +47,10 @@ const char* b200cd_last_error(void);
  * resolves cuTensorMapEncodeTiled, allocates the per-device error flag. Idempotent. */
 int b200cd_init(int device);
 
-/* Synchronises `stream` and returns 0, or B200CD_ERR_DEVICE if any kernel launched so far on this device
- * recorded a pipeline time-out (wrong descriptor / byte count); the flag is cleared. Test/debug aid. */
+/* Synchronises `stream` and returns 0, or B200CD_ERR_DEVICE with the time-out code if a tensor-core kernel waited
+ * ~10 s on an mbarrier (wrong descriptor / byte count). Such a kernel records its code in a host-mapped flag and
+ * TRAPS: the launch fails with a sticky CUDA error, every later CUDA call of the process fails, and nothing can train,
+ * log or checkpoint on top of it. This call only adds the diagnosis. */
 int b200cd_device_status(int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------

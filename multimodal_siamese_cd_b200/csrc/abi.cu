@@ -167,9 +167,11 @@ int b200cd_init(int device) {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   if (g_err_flag[device] == nullptr) {
+    // pinned, mapped host memory (device-accessible through UVA): a kernel that times out records its code here and
+    // traps, and the code is still readable after the trap has poisoned the context
     int* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, sizeof(int)));
-    CUDA_TRY(cudaMemset(p, 0, sizeof(int)));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&p), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *p = 0;
     g_err_flag[device] = p;
   }
   return 0;
@@ -179,13 +181,13 @@ int b200cd_device_status(int device, void* stream) {
   if (device < 0 || device >= kMaxDevices || g_err_flag[device] == nullptr)
     return fail(B200CD_ERR_ARCH, "b200cd_init(%d) has not been called", device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaStreamSynchronize(st));
-  int v = 0;
-  CUDA_TRY(cudaMemcpy(&v, g_err_flag[device], sizeof(int), cudaMemcpyDeviceToHost));
-  if (v != 0) {
-    CUDA_TRY(cudaMemset(g_err_flag[device], 0, sizeof(int)));
-    return fail(B200CD_ERR_DEVICE, "a tensor-core kernel timed out waiting on an mbarrier (device code %d)", v);
-  }
+  const cudaError_t e = cudaStreamSynchronize(st);
+  const int v = *reinterpret_cast<volatile int*>(g_err_flag[device]);
+  if (v != 0)
+    return fail(B200CD_ERR_DEVICE,
+                "a tensor-core kernel timed out waiting on an mbarrier (device code %d) and trapped; the CUDA context "
+                "of this process is no longer usable (%s)", v, cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(B200CD_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
   return 0;
 }
 

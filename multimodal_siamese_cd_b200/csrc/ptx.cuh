@@ -22,7 +22,7 @@ enum DevErr : int {
 };
 
 #ifndef B200CD_WAIT_TIMEOUT_CYCLES
-#define B200CD_WAIT_TIMEOUT_CYCLES (2000000000ll)  // ~1 s at 2 GHz
+#define B200CD_WAIT_TIMEOUT_CYCLES (20000000000ll)  // ~10 s at 2 GHz: far beyond any legitimate wait, even under a sanitizer
 #endif
 
 // Programmatic dependent launch: every kernel of the step is launched with the programmatic-serialization attribute
@@ -68,19 +68,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait: a wrong byte count or descriptor must not hang the GPU. On time-out (or when
-// another CTA has already reported an error) record the code and fall through; the host checks
-// the flag after the launch and fails loudly. The spin loop is out of line so that the issue loops of the
-// single-warp MMA / TMA roles stay short (they are instruction-issue bound otherwise).
+// Bounded wait: a wrong byte count or descriptor must not hang the GPU, and must not let the step run on
+// unsynchronised either. On time-out the code is recorded in the per-device flag and the kernel TRAPS: the launch fails
+// with a sticky CUDA error, so the very next runtime call on the host (and torch's next synchronisation) raises — a
+// training loop cannot continue, checkpoint or log on top of a pipeline that lost its ordering. The spin loop is out of
+// line so that the issue loops of the single-warp MMA / TMA roles stay short (they are instruction-issue bound).
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* err, int code) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0) {
-      if (*reinterpret_cast<volatile int*>(err) != 0) return;
       if (clock64() - t0 > B200CD_WAIT_TIMEOUT_CYCLES) {
         atomicCAS(err, 0, code);
-        return;
+        __threadfence_system();
+        __trap();
       }
     }
   }

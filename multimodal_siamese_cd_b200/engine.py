@@ -227,6 +227,11 @@ class StepEngine:
         self._g_fwd = None
         self._g_bwd = None
         self._runs = 0
+        self.generation = 0          # training forwards run so far (the drop-in autograd node checks it in backward)
+        self._dp_plan = None         # data-parallel backward: bucket plan, per-bucket graphs, communication stream
+        self._dp_graphs = None
+        self._dp_stream = None
+        self._dp_runs = 0
 
     # ------------------------------------------------------------------------------------------------
     def _input_channels(self) -> int:
@@ -920,7 +925,7 @@ class StepEngine:
             if self._g_fwd is None:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._run_fwd_eager()
                 self._g_fwd = g
             self._g_fwd.replay()
@@ -934,12 +939,65 @@ class StepEngine:
             if self._g_bwd is None:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._run_bwd_eager()
                 self._g_bwd = g
             self._g_bwd.replay()
         else:
             self._run_bwd_eager()
+        self._runs += 1
+
+    # ------------------------------------------------------------------------------------------------
+    # data-parallel backward (one process per GPU): the plan runs in segments of roughly equal gradient volume and each
+    # finished prefix of the flat gradient buffer is all-reduced (SUM, nn.DataParallel's reduce-add) on a side stream
+    # while the next segment runs. Used by the fused TrainStep and by the drop-in autograd node alike.
+    # ------------------------------------------------------------------------------------------------
+    def plan_buckets(self, nbuckets: int) -> list:
+        marks = self.bwd_marks
+        total = marks[-1]
+        nb = max(1, min(nbuckets, len(marks)))
+        cuts, lo = [], 0
+        for b in range(1, nb + 1):
+            want = total * b // nb
+            i = next(i for i, m in enumerate(marks) if m >= want)
+            i = max(i, cuts[-1][1] if cuts else 0)
+            cuts.append((cuts[-1][1] if cuts else 0, i + 1, lo, marks[i]))
+            lo = marks[i]
+        # (op_begin, op_end, grad_lo, grad_hi); drop empty segments
+        return [c for c in cuts if c[1] > c[0]]
+
+    def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False) -> None:
+        import torch.distributed as dist
+        if self._dp_plan is None:
+            self._dp_plan = self.plan_buckets(nbuckets)
+            self._dp_graphs = [None] * len(self._dp_plan)
+            self._dp_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        comm = self._dp_stream
+        for f in self.pack_bwd:
+            f()
+        for bi, (o0, o1, g0, g1) in enumerate(self._dp_plan):
+            if self.use_graphs and self._dp_runs >= 1:
+                if self._dp_graphs[bi] is None:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    # thread_local: a DataLoader pin-memory thread calling cudaHostAlloc / event functions during a
+                    # global-mode capture would invalidate it
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self.run_bwd_range(o0, o1)   # forks / joins the second trunk's stream inside the segment
+                    self._dp_graphs[bi] = g
+                self._dp_graphs[bi].replay()
+            else:
+                self.run_bwd_range(o0, o1)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            comm.wait_event(ev)
+            if skip_allreduce:   # measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1): wrong gradients
+                continue
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=group)
+        main.wait_stream(comm)
+        self._dp_runs += 1
         self._runs += 1
 
     def output_tensors(self) -> list[torch.Tensor]:

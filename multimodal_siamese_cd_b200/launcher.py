@@ -5,7 +5,11 @@
     e.g.  ... launcher /path/to/multimodal_siamese_cd train_supervised.py -c baseline_siamese -o OUT -d DATA
 
 The reference tree is only read. Under torchrun (WORLD_SIZE > 1) the process group is initialised and the reference's
-nn.DataParallel semantics are enabled (parallel.enable_data_parallel): global-batch loss, SUM-reduced gradients.
+nn.DataParallel semantics are enabled in "gather" mode (parallel.enable_data_parallel(mode="gather")): every rank's
+unchanged DataLoader yields the same full batch (same seed), the network runs this rank's DataParallel chunk and
+returns the gathered full-batch logits, the script's loss code runs on the global batch as written, and gradients are
+SUM-reduced in buckets overlapped with backward. Side effects of the scripts happen on rank 0 only: checkpoints
+(networks.save_checkpoint) are written by rank 0, wandb is disabled on the other ranks.
 """
 from __future__ import annotations
 
@@ -49,7 +53,18 @@ def main(argv=None) -> None:
         from . import parallel
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
-        parallel.enable_data_parallel()
+        parallel.enable_data_parallel(mode="gather")
+        if dist.get_rank() != 0:
+            os.environ["WANDB_MODE"] = "disabled"
+        from . import networks
+        _save = networks.save_checkpoint
+
+        def save_checkpoint_rank0(*args, **kwargs):
+            if dist.get_rank() == 0:
+                _save(*args, **kwargs)
+            dist.barrier()                                 # nobody reads a checkpoint that is still being written
+
+        networks.save_checkpoint = save_checkpoint_rank0
     os.chdir(ref_root)                                     # the scripts read configs/<name>.yaml relative to cwd
     sys.argv = [script, *rest]
     runpy.run_path(os.path.join(ref_root, script), run_name="__main__")

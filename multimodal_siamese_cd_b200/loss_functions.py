@@ -2,7 +2,8 @@
 returns a callable `(logits, target) -> 0-d tensor` (utils/loss_functions.py:6-33).
 
 `'PowerJaccardLoss'` — the loss every reference config selects (configs/base.yaml:17,44) — runs in the sm_100a
-kernels (b200cd_pj_fwd / _loss / _bwd) behind a torch autograd node and the `b200cd::power_jaccard` custom op.
+kernels (b200cd_pj_fwd / _loss / _bwd) behind the `b200cd::power_jaccard` / `b200cd::power_jaccard_backward` custom
+ops (torch.library, fake implementations, register_autograd).
 Gradients flow to the logits and, when it requires grad, to the target (the MMCR consistency term passes
 sigmoid(logits_stream2) as target, train_semisupervised.py:75-105). The other names map to the same torch
 compositions the reference uses; they are not on the hot path.
@@ -12,6 +13,8 @@ finding 2). With one process per GPU call `set_data_parallel_group(group)`: the 
 (SUM) between the forward and backward kernels so every rank sees the global ratio.
 """
 from __future__ import annotations
+
+from typing import Tuple
 
 import torch
 import torch.nn as nn
@@ -43,67 +46,76 @@ def _nblk(numel: int) -> int:
     return max(1, min(296, numel // 4096))
 
 
-class _PowerJaccard(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, z: torch.Tensor, t: torch.Tensor):
-        if not z.is_cuda:
-            raise RuntimeError("PowerJaccardLoss (b200cd) runs on CUDA tensors only; there is no CPU fallback")
-        zc = z.detach().float().contiguous()
-        tc = t.detach().float().contiguous()
-        if zc.numel() != tc.numel():
-            raise ValueError(f"power_jaccard_loss: logits {tuple(z.shape)} and target {tuple(t.shape)} differ in size")
-        n = zc.numel()
-        if n % 4 != 0:
-            raise NotImplementedError("power_jaccard_loss kernel needs a multiple of 4 elements")
-        sums = torch.zeros(3, device=z.device, dtype=torch.float64)
-        loss = torch.empty((), device=z.device, dtype=torch.float32)
-        with torch.cuda.device(z.device):
-            if n > 0:
-                nblk = _nblk(n)
-                ws = torch.empty(nblk * 3, device=z.device, dtype=torch.float64)
-                ops.pj_fwd(zc.view(1, -1), tc.view(1, -1), False, None, 0, nblk, ws, sums)
-            _allreduce_sums(sums)
-            ops.pj_loss(sums, loss)
-        ctx.save_for_backward(zc, tc, sums)
-        ctx.shapes = (z.shape, t.shape)
-        return loss
+# torch.library custom ops (namespace b200cd::): forward and backward of the loss as two ops with fake
+# (meta) implementations, wired together with register_autograd. `torch.ops.b200cd.power_jaccard(logits, target)`
+# returns (loss, sums); gradients flow to the logits and, when it requires grad, to the target.
+@torch.library.custom_op("b200cd::power_jaccard", mutates_args=(), device_types="cuda")
+def _pj_forward(logits: torch.Tensor, target: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    zc = logits.detach().float().contiguous()
+    tc = target.detach().float().contiguous()
+    n = zc.numel()
+    sums = torch.zeros(3, device=logits.device, dtype=torch.float64)
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    with torch.cuda.device(logits.device):
+        if n > 0:
+            nblk = _nblk(n)
+            ws = torch.empty(nblk * 3, device=logits.device, dtype=torch.float64)
+            ops.pj_fwd(zc.view(1, -1), tc.view(1, -1), False, None, 0, nblk, ws, sums)
+        _allreduce_sums(sums)   # unconditional for every term, empty row sets included: ranks cannot diverge
+        ops.pj_loss(sums, loss)
+    return loss, sums
 
-    @staticmethod
-    def backward(ctx, g: torch.Tensor):
-        zc, tc, sums = ctx.saved_tensors
-        need_z, need_t = ctx.needs_input_grad
-        dz = torch.empty_like(zc)
-        dt = torch.empty_like(tc) if need_t else None
-        if zc.numel() > 0:
-            with torch.cuda.device(zc.device):
-                ops.pj_bwd(zc.view(1, -1), tc.view(1, -1), False, None, 0, sums, g.float().contiguous(), 1.0, False,
-                           dz.view(1, -1), None if dt is None else dt.view(1, -1))
-        dz = dz.view(ctx.shapes[0]) if need_z else None
-        dt = dt.view(ctx.shapes[1]) if need_t else None
-        return dz, dt
+
+@_pj_forward.register_fake
+def _pj_forward_fake(logits, target):
+    return logits.new_empty((), dtype=torch.float32), logits.new_empty((3,), dtype=torch.float64)
+
+
+@torch.library.custom_op("b200cd::power_jaccard_backward", mutates_args=(), device_types="cuda")
+def _pj_backward(logits: torch.Tensor, target: torch.Tensor, sums: torch.Tensor, grad: torch.Tensor,
+                 need_target_grad: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    zc = logits.detach().float().contiguous()
+    tc = target.detach().float().contiguous()
+    dz = torch.empty_like(zc)
+    dt = torch.empty_like(tc) if need_target_grad else torch.empty(0, device=zc.device)
+    if zc.numel() > 0:
+        with torch.cuda.device(zc.device):
+            ops.pj_bwd(zc.view(1, -1), tc.view(1, -1), False, None, 0, sums, grad.float().contiguous(), 1.0, False,
+                       dz.view(1, -1), dt.view(1, -1) if need_target_grad else None)
+    return dz, dt
+
+
+@_pj_backward.register_fake
+def _pj_backward_fake(logits, target, sums, grad, need_target_grad):
+    return (logits.new_empty(logits.shape, dtype=torch.float32),
+            target.new_empty(target.shape if need_target_grad else (0,), dtype=torch.float32))
+
+
+def _pj_setup(ctx, inputs, output):
+    logits, target = inputs
+    ctx.save_for_backward(logits, target, output[1])
+
+
+def _pj_autograd(ctx, g_loss, g_sums):
+    logits, target, sums = ctx.saved_tensors
+    need_z, need_t = ctx.needs_input_grad
+    dz, dt = torch.ops.b200cd.power_jaccard_backward(logits, target, sums, g_loss, bool(need_t))
+    return (dz.view(logits.shape).to(logits.dtype) if need_z else None,
+            dt.view(target.shape).to(target.dtype) if need_t else None)
+
+
+torch.library.register_autograd("b200cd::power_jaccard", _pj_autograd, setup_context=_pj_setup)
 
 
 def power_jaccard_loss(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:  # noqa: A002 (reference arg name)
     """1 - I / (sum p^2 + sum t^2 - I + 1e-6), p = sigmoid(input), I = sum p*t, over the whole (global) batch."""
-    return _PowerJaccard.apply(input, target)
-
-
-# torch.library registration: `torch.ops.b200cd.power_jaccard(logits, target)` (forward only; the autograd path is
-# the Function above, which is what get_criterion returns).
-try:
-    _lib_def = torch.library.Library("b200cd", "DEF")
-    _lib_def.define("power_jaccard(Tensor logits, Tensor target) -> Tensor")
-
-    def _pj_cuda(logits, target):
-        return _PowerJaccard.apply(logits.detach(), target.detach())
-
-    def _pj_meta(logits, target):
-        return logits.new_empty(())
-
-    _lib_def.impl("power_jaccard", _pj_cuda, "CUDA")
-    _lib_def.impl("power_jaccard", _pj_meta, "Meta")
-except Exception:  # noqa: BLE001  (re-import in the same interpreter)
-    pass
+    if not input.is_cuda:
+        raise RuntimeError("PowerJaccardLoss (b200cd) runs on CUDA tensors only; there is no CPU fallback")
+    if input.numel() != target.numel():
+        raise ValueError(f"power_jaccard_loss: logits {tuple(input.shape)} and target {tuple(target.shape)} differ in size")
+    if input.numel() % 4 != 0:
+        raise NotImplementedError("power_jaccard_loss kernel needs a multiple of 4 elements")
+    return torch.ops.b200cd.power_jaccard(input, target)[0]
 
 
 # ---- non-hot-path names kept for API parity (same formulas as utils/loss_functions.py:36-197) ----------------
@@ -140,7 +152,7 @@ def iou_loss(y_logit, y_true):
 def soft_dice_loss_balanced(input, target):  # noqa: A002
     p, t = _flat_prob(input, target)
     eps = 1e-6
-    dice_pos = (2.0 * (p * t).sum() + eps) / (p.sum() + t.sum() + eps)
+    dice_pos = (2.0 * (p * t).sum()) / (p.sum() + t.sum() + eps)   # no eps in the numerator (utils/loss_functions.py:192)
     np_, nt = 1 - p, 1 - t
     dice_neg = (2.0 * (np_ * nt).sum()) / (np_.sum() + nt.sum() + eps)
     return 1 - dice_pos - dice_neg

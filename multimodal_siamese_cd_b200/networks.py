@@ -13,6 +13,7 @@ from __future__ import annotations
 import os
 from collections import OrderedDict
 from pathlib import Path
+from typing import List, Sequence
 
 import torch
 import torch.nn as nn
@@ -99,36 +100,116 @@ class Decoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------------
-class _StepFunction(torch.autograd.Function):
-    """Whole-network autograd node: forward and backward are the engine's (graph-replayed) kernel plans."""
+# torch.library custom ops of the network path (namespace b200cd::): the whole forward plan and the whole
+# backward plan of a StepEngine as two ops with fake (meta) implementations, wired together with register_autograd.
+# The engine — static buffers, TMA descriptors baked into CUDA graphs — is passed as an integer token.
+# ------------------------------------------------------------------------------------------------------
+_ENGINE_TOKENS: "dict[int, StepEngine]" = {}
+_NEXT_TOKEN = [1]
 
-    @staticmethod
-    def forward(ctx, eng: StepEngine, x_t1, x_t2, *params):
+
+def _engine_token(eng: StepEngine) -> int:
+    tok = getattr(eng, "_token", None)
+    if tok is None:
+        tok = _NEXT_TOKEN[0]
+        _NEXT_TOKEN[0] += 1
+        eng._token = tok
+        _ENGINE_TOKENS[tok] = eng
+    return tok
+
+
+def _engine_of(token: int) -> StepEngine:
+    try:
+        return _ENGINE_TOKENS[token]
+    except KeyError:
+        raise RuntimeError(f"b200cd::network_step: engine token {token} is not alive (released or evicted)") from None
+
+
+@torch.library.custom_op("b200cd::network_step", mutates_args=(), device_types="cuda")
+def network_step(engine: int, x_t1: torch.Tensor, x_t2: torch.Tensor, params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Forward plan of engine `engine` on (x_t1, x_t2) fp32 NCHW -> the network's logits (fp32 NCHW, one per output).
+    `params` are the network's parameters (read through the engine's own views; listed so that autograd tracks them)."""
+    eng = _engine_of(engine)
+    with torch.cuda.device(x_t1.device):
         eng.forward(x_t1, x_t2)
-        ctx.eng = eng
-        ctx.n_params = len(params)
-        return tuple(o.clone() for o in eng.output_tensors())
+        if eng.train:
+            eng.generation += 1
+    return [o.clone() for o in eng.output_tensors()]
 
-    @staticmethod
-    def backward(ctx, *grad_outs):
-        eng: StepEngine = ctx.eng
-        touched = set()
+
+@network_step.register_fake
+def _network_step_fake(engine, x_t1, x_t2, params):
+    eng = _engine_of(engine)
+    return [x_t1.new_empty(tuple(o.shape), dtype=torch.float32) for o in eng.output_tensors()]
+
+
+@torch.library.custom_op("b200cd::network_step_backward", mutates_args=(), device_types="cuda")
+def network_step_backward(engine: int, generation: int, grad_outs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Backward plan of engine `engine` from the logit gradients -> ONE fresh flat fp32 buffer holding every parameter
+    gradient (GradArena layout), all-reduced (SUM) across the data-parallel group when one is enabled."""
+    eng = _engine_of(engine)
+    if eng.generation != generation:
+        raise RuntimeError(
+            "b200cd: backward() of a network call whose engine has run another training forward since "
+            f"(forward #{generation}, engine is at #{eng.generation}). The engine keeps ONE set of saved activations "
+            "per (batch, size): call backward() before the next forward of the same shape, or sum the losses of one "
+            "forward.")
+    with torch.cuda.device(eng.device):
         for (hd, sl), g in zip(eng.outputs, grad_outs):
             tgt = hd.dz if sl is None else hd.dz[sl]
-            if g is None:
-                tgt.zero_()
-            else:
-                tgt.copy_(g.reshape(tgt.shape))
-            touched.add(id(hd))
-        eng.backward_static()
-        parallel.allreduce_gradients(eng.grads.flat)   # SUM over replicas when data parallelism is enabled
-        return (None, None, None, *eng.grads.detached_copy_views())
+            tgt.copy_(g.reshape(tgt.shape))
+        if parallel.is_enabled():
+            eng.backward_dp(parallel.group(), _GRAD_BUCKETS)
+        else:
+            eng.backward_static()
+    return eng.grads.flat.clone()
+
+
+@network_step_backward.register_fake
+def _network_step_backward_fake(engine, generation, grad_outs):
+    eng = _engine_of(engine)
+    return grad_outs[0].new_empty((eng.grads.flat.numel(),), dtype=torch.float32)
+
+
+_GRAD_BUCKETS = int(os.environ.get("B200CD_GRAD_BUCKETS", 4))
+
+
+def _network_step_setup(ctx, inputs, output):
+    engine, x_t1, x_t2, params = inputs
+    ctx.engine = engine
+    ctx.generation = _engine_of(engine).generation
+    ctx.ref = x_t1
+
+
+def _network_step_bwd(ctx, grads):
+    eng = _engine_of(ctx.engine)
+    outs = eng.output_tensors()
+    gl = [g if g is not None else torch.zeros_like(o) for g, o in zip(grads, outs)]
+    flat = torch.ops.b200cd.network_step_backward(ctx.engine, ctx.generation, gl)
+    # per-parameter views of the ONE fresh buffer: autograd's AccumulateGrad adopts a gradient it holds the only
+    # reference to without a copy kernel (~160 launches per DualStream step otherwise)
+    ga = eng.grads
+    pg = []
+    for n, p in ga.params:
+        if n in ga.skip:
+            pg.append(None)          # outc_sem_change: grad stays None as in the reference (AdamW skips it)
+        else:
+            o = ga.offsets[n]
+            pg.append(flat[o:o + p.numel()].view(p.shape))
+    return None, None, None, pg
+
+
+torch.library.register_autograd("b200cd::network_step", _network_step_bwd, setup_context=_network_step_setup)
 
 
 class B200Net(nn.Module):
     """Common forward for every network type: route to the engine for this (batch, size, mode)."""
 
-    _MAX_ENGINES = 2
+    # engines are cached per (batch, H, W, mode, device, precision). Training engines and inference engines have
+    # separate LRU lists: utils/evaluation.py feeds whole tiles of varying size at batch 1 every LOG_FREQ steps, and
+    # that must never evict (and so rebuild / re-capture) the training engine.
+    _MAX_TRAIN_ENGINES = 2
+    _MAX_EVAL_ENGINES = 8
 
     def __init__(self, cfg):
         super().__init__()
@@ -138,6 +219,17 @@ class B200Net(nn.Module):
         # "fast": single-bf16 storage / operands (the throughput mode). "precise": split-bf16 storage and three-MMA
         # products, which meets the reference-fp32 tolerance. Default from B200CD_PRECISION.
         self.precision = os.environ.get("B200CD_PRECISION", "fast")
+        self._check_shapes()
+
+    def _check_shapes(self) -> None:
+        """The kernels' channel constraints, reported at construction (a warning: such a network can still be built,
+        checkpointed and loaded — it cannot run; the engine raises at the first forward)."""
+        topo = list(self.cfg.MODEL.TOPOLOGY)
+        if any(c % 64 != 0 for c in topo) or int(getattr(self.cfg.MODEL, "OUT_CHANNELS", 1)) != 1:
+            import warnings
+            warnings.warn(f"b200cd networks run MODEL.TOPOLOGY widths that are multiples of 64 and OUT_CHANNELS == 1 "
+                          f"(got {topo}, {getattr(self.cfg.MODEL, 'OUT_CHANNELS', 1)}): this network can hold and "
+                          "load parameters but its forward will raise", stacklevel=3)
 
     def set_precision(self, mode: str) -> "B200Net":
         if mode not in ("fast", "precise"):
@@ -145,17 +237,23 @@ class B200Net(nn.Module):
         self.precision = mode
         return self
 
+    def _drop(self, key) -> None:
+        eng = self._engines.pop(key)
+        _ENGINE_TOKENS.pop(getattr(eng, "_token", None), None)
+
     def engine_for(self, B: int, H: int, W: int, train: bool, device: torch.device) -> StepEngine:
         if self.precision not in ("fast", "precise"):
             raise ValueError(f"B200CD_PRECISION / net.precision must be 'fast' or 'precise' (got {self.precision!r})")
         key = (B, H, W, train, device.index, self.precision)
         eng = self._engines.get(key)
         if eng is not None and eng.params_moved():
-            del self._engines[key]
+            self._drop(key)
             eng = None
         if eng is None:
-            while len(self._engines) >= self._MAX_ENGINES:
-                self._engines.popitem(last=False)
+            same = [k for k in self._engines if k[3] == train]
+            cap = self._MAX_TRAIN_ENGINES if train else self._MAX_EVAL_ENGINES
+            while len(same) >= cap:
+                self._drop(same.pop(0))
             with torch.cuda.device(device):
                 eng = StepEngine(self, B, H, W, train, device, use_graphs=self.use_cuda_graphs,
                                  precise=self.precision == "precise")
@@ -165,7 +263,8 @@ class B200Net(nn.Module):
         return eng
 
     def release_engines(self) -> None:
-        self._engines.clear()
+        for key in list(self._engines):
+            self._drop(key)
 
     def _outputs(self, outs: tuple):
         return outs[0] if len(outs) == 1 else tuple(outs)
@@ -177,14 +276,24 @@ class B200Net(nn.Module):
         x_t1 = x_t1.float().contiguous()
         x_t2 = x_t2.float().contiguous()
         B, _, H, W = x_t1.shape
+        gather = self.training and parallel.gather_mode()
+        if gather:
+            # replicated inputs (unchanged reference scripts under torchrun): this rank runs its DataParallel chunk
+            rank, world = parallel.rank_world()
+            rows = parallel.shard_rows(B, rank, world)
+            if rows.stop <= rows.start:
+                raise RuntimeError(f"b200cd data parallel: batch of {B} rows leaves rank {rank} of {world} without work")
+            x_t1, x_t2 = x_t1[rows].contiguous(), x_t2[rows].contiguous()
         with torch.cuda.device(x_t1.device):
-            eng = self.engine_for(B, H, W, self.training, x_t1.device)
+            eng = self.engine_for(x_t1.shape[0], H, W, self.training, x_t1.device)
             if self.training and torch.is_grad_enabled():
-                outs = _StepFunction.apply(eng, x_t1, x_t2, *[p for _, p in eng.grads.params])
+                outs = torch.ops.b200cd.network_step(_engine_token(eng), x_t1, x_t2, [p for _, p in eng.grads.params])
             else:
                 eng.forward(x_t1, x_t2)
-                outs = tuple(o.clone() for o in eng.output_tensors())
-        return self._outputs(outs)
+                outs = [o.clone() for o in eng.output_tensors()]
+        if gather:
+            outs = [parallel.GatherRows.apply(o, B) for o in outs]
+        return self._outputs(tuple(outs))
 
     # engines hold device buffers and graphs: never part of a state_dict / deepcopy / pickle
     def __getstate__(self):

@@ -8,9 +8,19 @@
   * parameter gradients are all-reduced with SUM (not mean): DataParallel reduce-adds replica gradients of a loss that
     is already global.
 
-`enable_data_parallel()` switches the drop-in modules (unchanged training scripts launched with torchrun) to this
-behaviour; the fused `TrainStep` picks the default process group up by itself and additionally overlaps the gradient
-all-reduce with the rest of backward in buckets.
+Two ways to feed the ranks:
+
+  * `enable_data_parallel()` ("sharded" inputs): every rank passes its OWN rows (`shard_rows`) to the network and the
+    loss; logits stay local and the loss all-reduces its three partial sums. What the fused `TrainStep`, bench.py and a
+    training script with a DistributedSampler-style loader use.
+  * `enable_data_parallel(mode="gather")` (replicated inputs): what the launcher selects for the reference's UNCHANGED
+    scripts under torchrun, whose DataLoader hands every rank the same full batch. The network shards the batch by rank
+    inside `forward` (DataParallel's scatter), all-gathers the logits (DataParallel's gather) and returns full-batch
+    logits on every rank, so the scripts' loss code — including the boolean row indexing of train_semisupervised.py —
+    runs as written on the global batch; backward takes this rank's rows of the logit gradient. Evaluation
+    (`net.eval()`) runs the whole batch on every rank.
+
+In both modes the gradient all-reduce is bucketed and overlapped with the rest of backward (StepEngine.backward_dp).
 """
 from __future__ import annotations
 
@@ -18,26 +28,69 @@ import torch
 
 from . import loss_functions
 
-_STATE = {"enabled": False, "group": None}
+_STATE = {"enabled": False, "group": None, "mode": "sharded"}
 
 
-def enable_data_parallel(group=None) -> None:
+def enable_data_parallel(group=None, mode: str = "sharded") -> None:
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
+    if mode not in ("sharded", "gather"):
+        raise ValueError(f"enable_data_parallel: mode must be 'sharded' or 'gather' (got {mode!r})")
     _STATE["enabled"] = dist.get_world_size(group) > 1
     _STATE["group"] = group
-    loss_functions.set_data_parallel_group("default" if group is None else group)
+    _STATE["mode"] = mode
+    # gathered logits: the loss already sees the global batch on every rank, nothing to all-reduce there
+    loss_functions.set_data_parallel_group(("default" if group is None else group) if mode == "sharded" else None)
 
 
 def disable_data_parallel() -> None:
     _STATE["enabled"] = False
     _STATE["group"] = None
+    _STATE["mode"] = "sharded"
     loss_functions.set_data_parallel_group(None)
 
 
 def is_enabled() -> bool:
     return _STATE["enabled"]
+
+
+def group():
+    return _STATE["group"]
+
+
+def gather_mode() -> bool:
+    return _STATE["enabled"] and _STATE["mode"] == "gather"
+
+
+def rank_world() -> tuple[int, int]:
+    import torch.distributed as dist
+    return dist.get_rank(_STATE["group"]), dist.get_world_size(_STATE["group"])
+
+
+class GatherRows(torch.autograd.Function):
+    """nn.DataParallel's gather for one-process-per-GPU replicas: every rank contributes its rows of an output and
+    receives the full batch; backward keeps this rank's rows of the incoming gradient (the loss is computed on the
+    global batch on every rank, so that slice IS d(global loss) / d(local logits))."""
+
+    @staticmethod
+    def forward(ctx, local: torch.Tensor, batch_size: int):
+        import torch.distributed as dist
+        rank, world = rank_world()
+        rows = shard_rows(batch_size, rank, world)
+        chunk = -(-batch_size // world)
+        assert local.shape[0] == rows.stop - rows.start, (local.shape, rows)
+        pad = local.new_zeros((chunk,) + tuple(local.shape[1:]))
+        pad[:local.shape[0]].copy_(local)
+        full = local.new_empty((world * chunk,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(full, pad, group=_STATE["group"])
+        ctx.rows = rows
+        # ranks own contiguous chunks of `chunk` rows and only the last non-empty chunk can be short
+        return full[:batch_size].contiguous() if world * chunk != batch_size else full
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        return g[ctx.rows].contiguous(), None
 
 
 def allreduce_gradients(flat: torch.Tensor) -> None:

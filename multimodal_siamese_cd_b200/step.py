@@ -105,9 +105,6 @@ class TrainStep:
         elif dp_group is not None:
             self.dp = dp_group
         self.grad_buckets = max(1, int(__import__("os").environ.get("B200CD_GRAD_BUCKETS", grad_buckets)))
-        self._comm_stream = torch.cuda.Stream(device=dev) if self.dp is not None else None
-        self._bucket_plan = None
-        self._bwd_graphs = None
 
     # ------------------------------------------------------------------------------------------------
     def _target_of(self, term: _Term) -> torch.Tensor:
@@ -137,59 +134,10 @@ class TrainStep:
         if g is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 fn()
             setattr(self, attr, g)
         g.replay()
-
-    # ------------------------------------------------------------------------------------------------
-    def _plan_buckets(self):
-        """Split the backward ops into contiguous segments of roughly equal gradient volume."""
-        marks = self.eng.bwd_marks
-        total = marks[-1]
-        nb = min(self.grad_buckets, len(marks))
-        cuts, lo = [], 0
-        for b in range(1, nb + 1):
-            want = total * b // nb
-            i = next(i for i, m in enumerate(marks) if m >= want)
-            i = max(i, cuts[-1][1] if cuts else 0)
-            cuts.append((cuts[-1][1] if cuts else 0, i + 1, lo, marks[i]))
-            lo = marks[i]
-        # (op_begin, op_end, grad_lo, grad_hi); drop empty segments
-        return [c for c in cuts if c[1] > c[0]]
-
-    def _backward_dp(self) -> None:
-        """Backward in segments; each finished gradient prefix is all-reduced (SUM) on a side stream while the
-        next segment runs."""
-        import torch.distributed as dist
-        eng = self.eng
-        if self._bucket_plan is None:
-            self._bucket_plan = self._plan_buckets()
-            self._bwd_graphs = [None] * len(self._bucket_plan)
-        main = torch.cuda.current_stream()
-        for f in eng.pack_bwd:
-            f()
-        for bi, (o0, o1, g0, g1) in enumerate(self._bucket_plan):
-            def seg(o0=o0, o1=o1):
-                eng.run_bwd_range(o0, o1)   # forks / joins the second trunk's stream inside the segment
-            if eng.use_graphs and self._steps >= 2:
-                if self._bwd_graphs[bi] is None:
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        seg()
-                    self._bwd_graphs[bi] = g
-                self._bwd_graphs[bi].replay()
-            else:
-                seg()
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._comm_stream.wait_event(ev)
-            if _DEBUG_SKIP_ALLREDUCE:   # measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1): wrong gradients
-                continue
-            with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(eng.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=self.dp)
-        main.wait_stream(self._comm_stream)
 
     # ------------------------------------------------------------------------------------------------
     def set_inputs(self, x_t1: torch.Tensor, x_t2: torch.Tensor, is_labeled=None, **targets) -> None:
@@ -227,8 +175,7 @@ class TrainStep:
             dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.dp)
         self._graphed("_g_loss_bwd", self._loss_bwd)
         if self.dp is not None:
-            self._backward_dp()
-            eng._runs += 1
+            eng.backward_dp(self.dp, self.grad_buckets, skip_allreduce=_DEBUG_SKIP_ALLREDUCE)
         else:
             eng.backward_static()
         self._steps += 1

@@ -117,12 +117,9 @@ def test_branch_plan_respects_dependencies(mtype, two):
 
 
 def test_bucket_plan_covers_gradient_buffer_once():
-    from multimodal_siamese_cd_b200.step import TrainStep
     net = networks.create_network(synthetic_cfg("dtsiameseunet", in_channels=6)).module
     eng = StepEngine(net, 2, 64, 64, True, torch.device("meta"))
-    ts = TrainStep.__new__(TrainStep)
-    ts.eng, ts.grad_buckets = eng, 4
-    plan = ts._plan_buckets()
+    plan = eng.plan_buckets(4)
     assert plan[0][0] == 0 and plan[-1][1] == len(eng.bwd_ops)
     assert plan[0][2] == 0 and plan[-1][3] == eng.grads.flat.numel()
     for (o0, o1, g0, g1), (p0, p1, h0, h1) in zip(plan, plan[1:]):
