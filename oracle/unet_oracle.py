@@ -28,25 +28,42 @@ import torch.nn.functional as F
 # ----------------------------------------------------------------------------------------------------------
 # bf16 storage emulation
 # ----------------------------------------------------------------------------------------------------------
+# Storage format the q=True mode emulates: "bf16" (the fast mode: one bf16 per element) or "split" (the precise mode:
+# hi = bf16(x), lo = bf16(x - hi), 16 mantissa bits; include/b200cd.h ABI version 2).
+_STORAGE = ["bf16"]
+
+
+def set_storage(fmt: str) -> None:
+    assert fmt in ("bf16", "split"), fmt
+    _STORAGE[0] = fmt
+
+
+def _store(x):
+    hi = x.to(torch.bfloat16).to(x.dtype)
+    if _STORAGE[0] == "bf16":
+        return hi
+    return hi + (x - hi).to(torch.bfloat16).to(x.dtype)
+
+
 class _RoundBoth(torch.autograd.Function):
-    """value and incoming gradient both rounded to bf16 (a tensor the pipeline stores in bf16 whose gradient is
-    stored in bf16 too)."""
+    """value and incoming gradient both rounded to the storage format (a tensor the pipeline stores in bf16 / split-bf16
+    whose gradient is stored the same way)."""
 
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return _store(x)
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(torch.bfloat16).to(g.dtype)
+        return _store(g)
 
 
 class _RoundFwd(torch.autograd.Function):
-    """value rounded to bf16, gradient passed through (weights; inputs of the fp32 1x1 heads)."""
+    """value rounded to the storage format, gradient passed through (weights; inputs of the fp32 1x1 heads)."""
 
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).to(x.dtype)
+        return _store(x)
 
     @staticmethod
     def backward(ctx, g):
