@@ -142,7 +142,8 @@ def cpu_step_rate(cfgname: str, sample_pairs: int, steps: int, warmup: int, thre
         nets, losses = mods
         cfg = synthetic_cfg(mtype, in_channels=cin)
         torch.manual_seed(cfg.SEED)
-        net = nets.create_network(cfg).module.train()       # .module: nn.DataParallel would fan out to visible GPUs
+        # .module: nn.DataParallel would fan out to the visible GPUs (and moves the module to cuda:0 when it sees one)
+        net = nets.create_network(cfg).module.cpu().train()
         sd0 = {k: v.clone() for k, v in net.state_dict().items()}
         for i in range(warmup + steps):
             net.load_state_dict(sd0)

@@ -83,7 +83,7 @@ class GatherRows(torch.autograd.Function):
         pad = local.new_zeros((chunk,) + tuple(local.shape[1:]))
         pad[:local.shape[0]].copy_(local)
         full = local.new_empty((world * chunk,) + tuple(local.shape[1:]))
-        dist.all_gather_into_tensor(full, pad, group=_STATE["group"])
+        dist.all_gather(list(full.split(chunk, 0)), pad, group=_STATE["group"])   # views of `full`: filled in place
         ctx.rows = rows
         # ranks own contiguous chunks of `chunk` rows and only the last non-empty chunk can be short
         return full[:batch_size].contiguous() if world * chunk != batch_size else full

@@ -234,6 +234,45 @@ def check_conv3x3_dgrad(n=2, H=32, W=32, cin=64, cout=128, seed=4, tol=6e-3) -> 
     return res
 
 
+def check_stat_rowsum(n=2, H=32, W=32, c=64, cout=128, seed=71, prec=False) -> dict:
+    """The transposed-conv BIAS gradient as the engine computes it by default (engine.py: UP_BIAS_FROM_STATS): the input
+    gradient convolution that writes the concat-buffer gradient d_cat [n, H, W, 2c] runs with per-CTA statistics
+    (stat_groups = 1, the `up_rows` side output), and b200cd_stat_rowsum sums the rows of the UPPER c channels:
+    out[j] = sum over pixels of d_cat[..., c + j]. Checked against the pixel sums of the stored gradient (all 2c
+    channels of the side output, then the rowsum of the upper half), in both numerics modes."""
+    g = _gen(seed)
+    w = torch.randn(cout, 2 * c, 3, 3, device=DEV, generator=g) / (3.0 * cout ** 0.5)
+    dr = torch.randn(n, H, W, cout, device=DEV, generator=g)
+    if prec:
+        import gpu_checks_hp as hp
+        Bd = hp.pack_hp(1, w)
+        A = ops.split_from_float(dr)
+        d_cat = ops.split_alloc((n, H, W, 2 * c), DEV)
+    else:
+        Bd = ops.pack_weights(1, bf16r(w))
+        A = dr.to(torch.bfloat16)
+        d_cat = torch.empty(n, H, W, 2 * c, device=DEV, dtype=torch.bfloat16)
+    rows, per_cta = ops.conv_stat_rows(n, H, W, cout, 2 * c, 1, prec=prec)
+    stats = torch.full((rows, 2 * c, 2), float("nan"), device=DEV)
+    ops.conv_gemm(0, 0, A, Bd, d_cat, stats=stats, stat_groups=1, prec=prec)
+    gb = torch.full((c,), float("nan"), device=DEV)
+    ops.stat_rowsum(stats, rows, 2 * c, c, c, gb)
+    ops.device_status()
+    stored = (ops.split_to_float(d_cat) if prec else d_cat.float()).double()
+    ref_all = stored.sum((0, 1, 2))
+    scale = stored.abs().sum((0, 1, 2)).max().item()     # sums cancel: compare against the size of what was summed
+    res = {"per_cta": per_cta, "rows": rows,
+           "side_output_abs": ((stats[..., 0].double().sum(0) - ref_all).abs().max().item()) / scale,
+           "bias_grad_abs": ((gb.double() - ref_all[c:]).abs().max().item()) / scale,
+           "finite": bool(torch.isfinite(gb).all().item())}
+    # against what autograd computes for ConvTranspose2d.bias: the pixel sum of the exact upstream gradient
+    exact = F.conv_transpose2d(nchw(dr).double(), w.double(), padding=1).sum((0, 2, 3))[c:]
+    res["vs_exact_rel"] = ((gb.double() - exact).norm() / exact.norm()).item()
+    res["ok"] = res["per_cta"] and res["finite"] and res["side_output_abs"] < 2e-6 and res["bias_grad_abs"] < 2e-6 and \
+        res["vs_exact_rel"] < (1e-4 if prec else 2e-2)
+    return res
+
+
 def check_dgrad_bnbwd(n=4, H=32, W=32, cin=64, cout=128, G=2, seed=66, mode=0) -> dict:
     """Input-gradient convolution with the BatchNorm-backward reduce pass fused into its epilogue: the gradient it
     stores must equal the plain dgrad launch bit for bit, the per-CTA sums (S1, S2) must equal sum dy*m and sum dy*m*r
@@ -755,6 +794,9 @@ def decode_wgrad() -> dict:
 
 
 ALL_CHECKS = {
+    "stat_rowsum_up_bias": check_stat_rowsum,
+    "stat_rowsum_up_bias_256": lambda: check_stat_rowsum(n=3, H=16, W=16, c=128, cout=128, seed=72),
+    "stat_rowsum_up_bias_split_bf16": lambda: check_stat_rowsum(prec=True, seed=73),
     "pack_weights": check_pack_weights,
     "pack_input": check_pack_input,
     "pj": check_pj,

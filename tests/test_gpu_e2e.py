@@ -39,15 +39,89 @@ CASES = {
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_step_parity(name):
+    """FAST mode (single-bf16 storage). It does NOT meet north_star's 1e-3 on logits / gradients — by construction
+    (bf16 operands -> 8e-3 logits, 0.08 global / 0.44 per-parameter gradient error at random init) — so
+    the bounds below are its own measured envelope, asserted against BOTH oracles, globally and per parameter; the
+    tolerance-meeting mode is tested in test_step_parity_precise."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     r = E.run_case(**CASES[name])
     assert r["loss_q"] <= 1e-4 and r["loss_x"] <= 1e-4, r
     assert r["logits_q"] <= 1.5e-2 and r["logits_x"] <= 3e-2, r
-    assert r["grads_q"]["global"] <= 0.2, r
+    # against the bf16-emulating oracle (isolates the kernels from the format) and against the reference's arithmetic
+    assert r["grads_q"]["global"] <= 0.2 and r["grads_q"]["max"] <= 0.7, r
+    assert r["grads_x"]["global"] <= 0.25 and r["grads_x"]["max"] <= 0.8, r
     assert r["prebn_bias_grad_max"] == 0.0, r
     assert r["bn_running_maxabs"] <= 2e-3, r
     assert r["margin_flips_x"] == 0 and r["f1_diff_x"] <= 2e-2, r
+
+
+# ---- PRECISE mode: split-bf16 storage, three-MMA products (include/b200cd.h ABI version 2) -------------------------
+# Bounds, read against the reference's OWN fp32-vs-fp64 error measured in the same test (`floor_*`):
+#  * logits: <= 1e-4 vs the reference's fp32 arithmetic (north_star: 1e-3) on independent inputs, <= 1e-3 on correlated
+#    t1 / t2 (the realistic bi-temporal case: feature differences amplify rounding ~10x, SURVEY App. C);
+#  * loss: <= 1e-5 (north_star: 1e-4);
+#  * gradients vs the fp64 run: global <= 8 x floor, per-parameter max <= 5 x floor (measured 3.2-3.6 x / 1.8-3.1 x).
+#    Why not 1 x: a forward perturbation eps flips ~eps of the ReLU masks / max-pool arg-maxes and the gradient error
+#    grows like sqrt(eps); 16 mantissa bits (eps ~1e-5) against fp32's 24 bits (6e-8) leave a factor ~3-5 that the CPU
+#    oracle reproduces exactly with split storage and fp64 arithmetic (oracle.set_storage("split"), DESIGN.md §3);
+#  * masks: identical wherever the reference's |logit| >= 1e-3; F1 within 1e-4;
+#  * BatchNorm running statistics within 2e-5.
+PRECISE_CASES = {
+    "siamese": dict(mtype="siameseunet", cin=4, topo=SMALL, B=3, H=32, W=32, kind="supervised"),
+    "unet": dict(mtype="unet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="supervised"),
+    "dualstream_fused_graph": dict(mtype="dualstreamunet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="supervised", path="fused", steps=3),
+    "dtsiamese_fused_graph": dict(mtype="dtsiameseunet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="dualtask", path="fused", steps=3),
+    "whatevernet_mmcr": dict(mtype="whatevernet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="mmcr"),
+    "whatevernet2_mmcr_fused": dict(mtype="whatevernet2", cin=6, topo=SMALL, B=3, H=32, W=32, kind="mmcr", path="fused"),
+    "dtsiamese_ssl_as_written": dict(mtype="dtsiameseunet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="mmcr", alpha=0.1, path="fused"),
+    "siamese_full_256": dict(mtype="siameseunet", cin=4, topo=FULL, B=2, H=256, W=256, kind="supervised", path="fused", steps=2),
+    "siamese_full_256_corr": dict(mtype="siameseunet", cin=4, topo=FULL, B=2, H=256, W=256, kind="supervised", corr=True),
+    "dtsiamese_full_64_corr": dict(mtype="dtsiameseunet", cin=6, topo=FULL, B=2, H=64, W=64, kind="dualtask", corr=True),
+}
+
+
+def _assert_precise(r, corr=False):
+    assert r["loss_x"] <= 1e-5, r
+    assert r["logits_x"] <= (1e-3 if corr else 1e-4), r
+    fl = r["floor_grads"]
+    assert r["grads_d"]["global"] <= max(8 * fl["global"], 2e-3), (r["grads_d"], fl)
+    assert r["grads_d"]["max"] <= max(5 * fl["max"], 1e-2), (r["grads_d"], fl)
+    assert r["prebn_bias_grad_max"] == 0.0, r
+    assert r["margin3_flips_x"] == 0 and r["f1_diff_x"] <= 1e-4, r
+    if "bn_running_maxabs" in r:
+        assert r["bn_running_maxabs"] <= 2e-5, r
+
+
+@pytest.mark.parametrize("name", list(PRECISE_CASES))
+def test_step_parity_precise(name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    kw = PRECISE_CASES[name]
+    r = E.run_case(**kw, precision="precise", fp64=True, skip_q=True)
+    _assert_precise(r, corr=kw.get("corr", False))
+
+
+# ---- every BASELINE.json config at its REAL shape (full topology, 256 x 256) against the oracle, both modes --------
+BASELINE_SHAPES = {
+    "cfg2_dualstream_b16": dict(mtype="dualstreamunet", cin=6, topo=FULL, B=16, H=256, W=256, kind="supervised", path="fused"),
+    "cfg3_dtsiamese_b8": dict(mtype="dtsiameseunet", cin=6, topo=FULL, B=8, H=256, W=256, kind="dualtask", path="fused"),
+    "cfg5_whatevernet_mmcr_b4": dict(mtype="whatevernet", cin=6, topo=FULL, B=4, H=256, W=256, kind="mmcr", path="fused"),
+}
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("name", list(BASELINE_SHAPES))
+def test_baseline_shape_against_oracle(name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    kw = BASELINE_SHAPES[name]
+    r = E.run_case(**kw, precision="precise", fp64=True, skip_q=True)
+    _assert_precise(r)
+    f = E.run_case(**kw, precision="fast", fp64=True, skip_q=True)      # oracle runs shared with the precise case
+    assert f["loss_x"] <= 1e-4 and f["logits_x"] <= 3e-2, f
+    assert f["grads_x"]["global"] <= 0.25 and f["grads_x"]["max"] <= 0.8, f
+    assert f["margin_flips_x"] == 0 and f["f1_diff_x"] <= 2e-2, f
 
 
 EVAL_CASES = {
@@ -71,6 +145,9 @@ def test_eval_parity(name):
     assert r["logits_q"] <= 1.5e-2 and r["logits_x"] <= 3e-2, r
     assert r["replay_equal"] and r["bn_unchanged_in_eval"], r
     assert r["margin_flips_x"] == 0 and r["f1_diff_x"] <= 2e-2, r
+    p = E.run_eval_case(**EVAL_CASES[name], precision="precise")
+    assert p["logits_x"] <= 1e-4 and p["replay_equal"] and p["bn_unchanged_in_eval"], p
+    assert p["margin3_flips_x"] == 0 and p["f1_diff_x"] <= 1e-4, p
 
 
 @pytest.mark.parametrize("optimizer", ["torch", "fused"])
@@ -115,6 +192,19 @@ def test_step_against_reference_fixture(name):
     assert r["popcount_diff"] <= 0.02 * r["n_pixels"], r
 
 
+@pytest.mark.parametrize("name", sorted(p.stem for p in _GOLD.glob("*.pt")))
+def test_step_against_reference_fixture_precise(name):
+    """PRECISE mode against the UNMODIFIED reference's numbers: loss 1e-5, logits 1e-4, identical masks, and EVERY
+    gradient tensor's fingerprint (norm and leading values) within 2 % of its norm — per tensor, not aggregated."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    r = E.run_golden_train_case(_GOLD / f"{name}.pt", precision="precise")
+    assert r["loss_diff"] <= 1e-5, r
+    assert r["logits_rel"] <= 1e-4, r
+    assert r["grad_norm_rel"] <= 2e-3 and r["grad_fingerprint_worst"] <= 2e-2, r
+    assert r["mask_flips"] == 0, r
+
+
 @pytest.mark.parametrize("name", sorted(p.stem for p in (_GOLD / "eval").glob("*.pt")))
 def test_eval_against_reference_fixture(name):
     """Odd-sized whole-tile inference against logits / F1 the UNMODIFIED reference produced (tests/golden/eval/*.pt)."""
@@ -122,4 +212,6 @@ def test_eval_against_reference_fixture(name):
         pytest.skip("no CUDA device")
     r = E.run_golden_eval_case(_GOLD / "eval" / f"{name}.pt")
     assert r["logits_rel"] <= 3e-2 and r["margin_flips"] == 0 and r["f1_diff"] <= 2e-2, r
+    p = E.run_golden_eval_case(_GOLD / "eval" / f"{name}.pt", precision="precise")
+    assert p["logits_rel"] <= 1e-4 and p["margin3_flips"] == 0 and p["f1_diff"] <= 1e-4, p
 
