@@ -306,6 +306,53 @@ int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total
                       double beta2, double eps, double weight_decay, int64_t step_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Training-time augmentation + packing (next-row N2) — replaces the per-sample numpy transforms of
+ * utils/augmentations.py:6-142 as composed by utils/datasets.py:111-181: crop (UniformCrop / ImportanceRandomCrop
+ * :105-142) -> RandomFlip :44-62 -> RandomRotate :65-72 -> ColorShift :75-86 -> GammaCorrection :89-101 ->
+ * Numpy2Torch :35-41 (HWC -> CHW), all samples of a batch in one launch. The random decisions are drawn on the host
+ * (numpy, the reference's call order) and passed in: one job per sample. out: fp32 [n][cout][crop][crop];
+ * output channel c of sample s = source channel cmap[c] of the crop at (x0, y0). `jobs_dev` is a DEVICE array.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* src; /* [H0][W0][C] fp32 (HWC) */
+  int32_t H0, W0, C;
+  int32_t x0, y0;
+  int32_t hflip, vflip, rotk; /* rotk = number of counter-clockwise 90 degree rotations (np.rot90), 0..3 */
+  int32_t use_mul, use_gamma;
+  int32_t cmap[16];
+  float mul[16];   /* per source channel */
+  float gamma[16];
+  int32_t reserved;
+} b200cd_augment_job;
+int b200cd_augment(const b200cd_augment_job* jobs_dev, int n, int crop, int cout, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Inference (utils/evaluation.py:7-23, net.eval()): BatchNorm is a fixed per-channel affine, so conv + BN + ReLU
+ * (utils/networks.py:392-397) is ONE launch: b200cd_conv_gemm_affine = b200cd_conv_gemm (CTA-pair kernel, flags bit 2;
+ * bit 4 for split-bf16 tensors) whose epilogue stores act((acc + bias[n]) * scale[n] + shift[n]), act = ReLU when
+ * relu != 0, and writes no statistics. b200cd_bn_eval_affine_batched computes (mean, invstd, scale, shift) of EVERY
+ * BatchNorm of a network from its running statistics in one launch: job j owns thread blocks
+ * [start_j, start_j + ceil(C_j / 256)); `jobs_dev` is a DEVICE array.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float* mean;   /* [G][C] each */
+  float* invstd;
+  float* scale;
+  float* shift;
+  int32_t C, G;
+  float eps;
+  int32_t start;
+} b200cd_bn_eval_job;
+int b200cd_bn_eval_affine_batched(const b200cd_bn_eval_job* jobs_dev, int njobs, int total_blocks, void* stream);
+int b200cd_conv_gemm_affine(int mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                            const void* Bw, int N, void* out, int64_t out_ld, const float* bias, const float* scale,
+                            const float* shift, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * "Precise" mode: split-bf16 storage (ABI version 2).
  *
  * north_star asks for logits / gradients within 1e-3 of the reference's fp32 path; single bf16 (or TF32) operands

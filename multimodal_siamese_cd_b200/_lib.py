@@ -65,6 +65,9 @@ SIGNATURES = {
     "b200cd_confusion_counts": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "b200cd_adamw_step": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _vp]),
     "b200cd_pj_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "b200cd_augment": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "b200cd_bn_eval_affine_batched": (_i, [_vp, _i, _i, _vp]),
+    "b200cd_conv_gemm_affine": (_i, [_i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     # split-bf16 ("precise") mode, ABI version 2
     "b200cd_wgrad_gemm_hp": (_i, [_i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "b200cd_pack_input_hp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -277,7 +277,7 @@ int b200cd_conv_gemm_stat_rows(int mode, int out_mode, int flags, int n_img, int
 static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
                           const void* Bw, int N, int cout, void* out, int64_t out_ld, const float* bias, float* stats,
                           const void* bwd_r, int64_t bwd_ld, const float* bwd_scale, const float* bwd_shift,
-                          void* stream) {
+                          void* stream, const float* ep_scale = nullptr, const float* ep_shift = nullptr, int ep_relu = 0) {
   if (mode < 0 || mode > 2 || out_mode < 0 || out_mode > 1) return fail(B200CD_ERR_SHAPE, "conv_gemm: bad mode");
   if (ka < 64 || ka % 64 != 0 || N < 64 || N % 64 != 0)
     return fail(B200CD_ERR_SHAPE, "conv_gemm: ka=%d and N=%d must be multiples of 64", ka, N);
@@ -327,6 +327,13 @@ static int conv_gemm_impl(int mode, int out_mode, int flags, const void* A, int6
   p.err = err;
   p.n_img = n_img;
   p.stat_groups = cp.stat_groups;
+  if (ep_scale != nullptr) {
+    if (!pair || stats != nullptr || bwd_r != nullptr || out_mode != 0 || ep_shift == nullptr)
+      return fail(B200CD_ERR_SHAPE, "conv_gemm_affine: needs the CTA-pair kernel (flags bit 2), out_mode 0, no statistics");
+    p.ep_scale = ep_scale;
+    p.ep_shift = ep_shift;
+    p.ep_relu = ep_relu;
+  }
   if (bwd_r != nullptr) {
     if (!pair || cp.stat_groups == 0 || stats == nullptr || out_mode != 0 || bwd_scale == nullptr || bwd_shift == nullptr)
       return fail(B200CD_ERR_SHAPE, "conv_gemm_bnbwd: needs the CTA-pair kernel with per-CTA statistics (flags bits 2, 3)");
@@ -382,6 +389,22 @@ int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a
                      void* stream) {
   return conv_gemm_impl(mode, out_mode, flags, A, a_ld, n_img, H, W, ka, Bw, N, cout, out, out_ld, bias, stats, nullptr, 0,
                         nullptr, nullptr, stream);
+}
+
+int b200cd_conv_gemm_affine(int mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,
+                            const void* Bw, int N, void* out, int64_t out_ld, const float* bias, const float* scale,
+                            const float* shift, int relu, void* stream) {
+  if (scale == nullptr || shift == nullptr) return fail(B200CD_ERR_SHAPE, "conv_gemm_affine: scale / shift are NULL");
+  return conv_gemm_impl(mode, 0, flags, A, a_ld, n_img, H, W, ka, Bw, N, 0, out, out_ld, bias, nullptr, nullptr, 0, nullptr,
+                        nullptr, stream, scale, shift, relu);
+}
+
+int b200cd_bn_eval_affine_batched(const b200cd_bn_eval_job* jobs_dev, int njobs, int total_blocks, void* stream) {
+  static_assert(sizeof(b200cd_bn_eval_job) == sizeof(b200cd::BnEvalJob), "bn eval job layout");
+  if (jobs_dev == nullptr || njobs < 1 || total_blocks < 1) return fail(B200CD_ERR_SHAPE, "bn_eval_affine_batched: empty job table");
+  CUDA_TRY(b200cd::launch_bn_eval_affine_batched(reinterpret_cast<const b200cd::BnEvalJob*>(jobs_dev), njobs, total_blocks,
+                                                 reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
 }
 
 int b200cd_conv_gemm_bnbwd(int mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka, const void* Bw,
@@ -655,6 +678,15 @@ int b200cd_confusion_counts(const float* pred, const float* truth, int64_t n, in
     return fail(B200CD_ERR_SHAPE, "confusion_counts: 1..8 thresholds and a non-empty input are required");
   CUDA_TRY(b200cd::launch_confusion(pred, truth, n, from_logits, thresholds, nthr,
                                     reinterpret_cast<unsigned long long*>(counts), reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_augment(const b200cd_augment_job* jobs_dev, int n, int crop, int cout, float* out, void* stream) {
+  static_assert(sizeof(b200cd_augment_job) == sizeof(b200cd::AugmentJob), "augment job layout");
+  if (jobs_dev == nullptr || n < 1 || crop < 1 || cout < 1 || cout > 16 || out == nullptr)
+    return fail(B200CD_ERR_SHAPE, "augment: 1..16 output channels and a non-empty batch are required");
+  CUDA_TRY(b200cd::launch_augment(reinterpret_cast<const b200cd::AugmentJob*>(jobs_dev), n, crop, cout, out,
+                                  reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -425,6 +425,35 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   }
 }
 
+// Inference: the fixed affine of every BatchNorm of a network in ONE launch (running statistics only change when the
+// network trains, but the engine cannot see that, so the forward plan starts with this launch). Job j owns thread
+// blocks [start_j, start_j + ceil(C_j / 256)); y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta for
+// every stat-group (utils/evaluation.py:9-10: net.eval()).
+__global__ void __launch_bounds__(256) bn_eval_affine_batched_kernel(const BnEvalJob* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].start <= b) lo = mid;
+    else hi = mid - 1;
+  }
+  const BnEvalJob j = jobs[lo];
+  const int c = (b - j.start) * 256 + threadIdx.x;
+  if (c >= j.C) return;
+  const float rm = j.running_mean[c];
+  const float is = 1.0f / sqrtf(j.running_var[c] + j.eps);
+  const float sc = j.gamma[c] * is;
+  const float sh = j.beta[c] - rm * sc;
+  for (int g = 0; g < j.G; ++g) {
+    j.mean[g * j.C + c] = rm;
+    j.invstd[g * j.C + c] = is;
+    j.scale[g * j.C + c] = sc;
+    j.shift[g * j.C + c] = sh;
+  }
+}
+
 // Few partial rows per stat-group (the CTA-pair convolution writes one row per CTA and epilogue group, <= 296): one
 // kernel does both stages. block = 8 channels x 32 lanes; lane l sums rows l, l + 32, ... in fp64 (independent loads),
 // a fixed-order shuffle tree combines the lanes, lane 0 finishes the channel exactly as bn_finalize_kernel does.
@@ -2058,6 +2087,11 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
   return cudaGetLastError();
 }
 
+cudaError_t launch_bn_eval_affine_batched(const BnEvalJob* jobs, int njobs, int total_blocks, cudaStream_t st) {
+  launch_k(bn_eval_affine_batched_kernel, dim3(total_blocks), dim3(256), 0, st, jobs, njobs);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
                             int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
                             void* pool, long long ld_p, void* dif, long long ld_d, void* pool_idx, cudaStream_t st) {
@@ -2288,6 +2322,58 @@ cudaError_t launch_adamw(const AdamWJob* jobs, int njobs, long long total_blocks
                          float b2, float omb2, float eps, float sqrt_bc2, cudaStream_t st) {
   launch_k(adamw_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, st, jobs, njobs, decay, step_size, omb1,
            b2, omb2, eps, sqrt_bc2);
+  return cudaGetLastError();
+}
+
+}  // namespace b200cd
+
+// ------------------------------------------------------------------------------------------------
+// N2 — training-time augmentation + packing on the GPU (utils/augmentations.py:6-142 composed as in
+// utils/datasets.py:111-181): per sample crop -> horizontal / vertical flip -> rot90(k) -> colour shift -> gamma
+// -> HWC -> CHW, with the channel regrouping of datasets.py:156-162 (x_t1 = [S1 t1 | S2 t1], x_t2 = [S1 t2 | S2 t2]).
+// The random DECISIONS stay on the host (numpy RNG, same call order as the reference so a seeded run draws the same
+// augmentations; the importance crop needs only the label sums); the pixel work — 12 fp32 channels of a full tile per
+// sample — happens here, all samples of a batch in one launch. One thread = one output pixel, all output channels.
+// ------------------------------------------------------------------------------------------------
+namespace b200cd {
+namespace {
+
+__global__ void __launch_bounds__(256) augment_kernel(const AugmentJob* __restrict__ jobs, int n, int cs, int cout,
+                                                      float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(n) * cs * cs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % cs);
+    const int y = static_cast<int>((i / cs) % cs);
+    const int s = static_cast<int>(i / (static_cast<long long>(cs) * cs));
+    const AugmentJob& j = jobs[s];
+    // invert rot90(k) (counter-clockwise, square crop): R[i][j] = M[j][cs-1-i] (k=1), M[cs-1-i][cs-1-j] (2), M[cs-1-j][i] (3)
+    int yy = y, xx = x;
+    if (j.rotk == 1) { yy = x; xx = cs - 1 - y; }
+    else if (j.rotk == 2) { yy = cs - 1 - y; xx = cs - 1 - x; }
+    else if (j.rotk == 3) { yy = cs - 1 - x; xx = y; }
+    if (j.vflip) yy = cs - 1 - yy;       // np.flip(axis=0) applied after the horizontal flip
+    if (j.hflip) xx = cs - 1 - xx;       // np.flip(axis=1)
+    const float* px = j.src + (static_cast<long long>(j.y0 + yy) * j.W0 + (j.x0 + xx)) * j.C;
+    for (int c = 0; c < cout; ++c) {
+      const int sc = j.cmap[c];
+      float v = __ldg(px + sc);
+      if (j.use_mul) v = fminf(fmaxf(v * j.mul[sc], 0.f), 1.f);            // ColorShift: clip(img * factor, 0, 1)
+      if (j.use_gamma) v = fminf(fmaxf(powf(v, j.gamma[sc]), 0.f), 1.f);   // GammaCorrection: clip(img ** gamma, 0, 1)
+      out[((static_cast<long long>(s) * cout + c) * cs + y) * cs + x] = v;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_augment(const AugmentJob* jobs, int n, int cs, int cout, float* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * cs * cs;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  launch_k(augment_kernel, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, jobs, n, cs, cout, out);
   return cudaGetLastError();
 }
 

@@ -351,6 +351,9 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
     // per-CTA BatchNorm statistics (p.stat_groups > 0): thread t < 64 keeps the running (sum, sum of squares) of
     // channel t of every slab of the current N block, per stat-group, and writes them once per N block
     const bool cta_stats = p.stats != nullptr && p.stat_groups > 0;
+    // inference epilogue (host guarantees stats == nullptr then, so the statistics scratch `red` is free for the scales)
+    const bool affine = p.ep_scale != nullptr;
+    const float act_lo = p.ep_relu ? 0.f : -3.0e38f;
     const int per_group = cta_stats ? p.n_img / p.stat_groups : 1;
     const size_t my_row = 2 * blockIdx.x + grp;
     float acc_s[2][BN / 64], acc_q[2][BN / 64];
@@ -394,8 +397,16 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
       const int sgrp = cta_stats ? img / per_group : 0;
       if (nb != bias_nb) {  // uniform across the 128 threads
         named_barrier_sync(bar1, 128);
-        for (int i = t; i < BN; i += 128)
-          bias_s[i] = p.bias ? p.bias[p.out_mode == 1 ? (n0 + i) % p.cout : n0 + i] : 0.f;
+        for (int i = t; i < BN; i += 128) {
+          const float b = p.bias ? p.bias[p.out_mode == 1 ? (n0 + i) % p.cout : n0 + i] : 0.f;
+          if (affine) {  // folded inference BatchNorm: (acc + b) * sc + sh = acc * sc + (b * sc + sh); `red` holds sc
+            const float sc = __ldg(p.ep_scale + n0 + i);
+            red[i] = sc;
+            bias_s[i] = fmaf(b, sc, __ldg(p.ep_shift + n0 + i));
+          } else {
+            bias_s[i] = b;
+          }
+        }
         named_barrier_sync(bar1, 128);
         bias_nb = nb;
       }
@@ -434,8 +445,15 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2) {
                   const int j = cc * 8 + 2 * j2;
-                  const float f0 = __uint_as_float(v[j]) + bias_s[slab * 64 + h * 32 + j];
-                  const float f1 = __uint_as_float(v[j + 1]) + bias_s[slab * 64 + h * 32 + j + 1];
+                  const int cj = slab * 64 + h * 32 + j;
+                  float f0, f1;
+                  if (affine) {
+                    f0 = fmaxf(fmaf(__uint_as_float(v[j]), red[cj], bias_s[cj]), act_lo);
+                    f1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), red[cj + 1], bias_s[cj + 1]), act_lo);
+                  } else {
+                    f0 = __uint_as_float(v[j]) + bias_s[cj];
+                    f1 = __uint_as_float(v[j + 1]) + bias_s[cj + 1];
+                  }
                   const uint32_t hi2 = pack_bf16x2(f0, f1);
                   const float l0 = f0 - bf16_lo(hi2), l1 = f1 - bf16_hi(hi2);
                   const uint32_t lo2 = pack_bf16x2(l0, l1);
@@ -535,8 +553,16 @@ __global__ void __launch_bounds__(kThreads, 1) fprop_pair_kernel(const __grid_co
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             float f[8];
+            if (affine) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[cc * 8 + j]) + bias_s[slab * 64 + h * 32 + cc * 8 + j];
+              for (int j = 0; j < 8; ++j) {
+                const int cj = slab * 64 + h * 32 + cc * 8 + j;
+                f[j] = fmaxf(fmaf(__uint_as_float(v[cc * 8 + j]), red[cj], bias_s[cj]), act_lo);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[cc * 8 + j]) + bias_s[slab * 64 + h * 32 + cc * 8 + j];
+            }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]);
             o.y = pack_bf16x2(f[2], f[3]);
@@ -802,6 +828,7 @@ cudaError_t launch_fprop_pair(const CUtensorMap& mapA, const CUtensorMap& mapB, 
   if (!((p.mode == 0 && p.out_mode == 0) || p.mode == 1 || (p.mode == 2 && p.out_mode == 0))) return cudaErrorInvalidValue;
   if (p.stat_groups < 0 || p.stat_groups > 2) return cudaErrorInvalidValue;
   if (p.prec && (p.kreal < 1 || p.kchunks != 3 * p.kreal || p.bwd_r != nullptr)) return cudaErrorInvalidValue;
+  if (p.ep_scale != nullptr && (p.stats != nullptr || p.ep_shift == nullptr || p.out_mode != 0)) return cudaErrorInvalidValue;
   B200CD_PAIR_DISPATCH(launch_pair, mapA, mapB, mapO, p, num_tiles, stream);
   return cudaErrorInvalidValue;
 }

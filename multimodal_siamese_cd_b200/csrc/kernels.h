@@ -62,6 +62,11 @@ struct FpropParams {
   // (hi + lo carries 16 mantissa bits). The K loop then has 3 * kreal chunks per tap — A_hi * W_hi, A_hi * W_lo,
   // A_lo * W_hi against weights packed as [hi | lo | hi] per tap — and the epilogue stores both halves of the output.
   int prec, kreal, a_lo, o_lo;
+  // Inference: BatchNorm folded into the epilogue (CTA-pair kernel, no statistics): out = act((acc + bias) * ep_scale[n]
+  // + ep_shift[n]) with act = ReLU when ep_relu — one launch per conv + BN + ReLU stage (utils/evaluation.py:7-23).
+  const float* ep_scale;
+  const float* ep_shift;
+  int ep_relu;
   int* err;
 };
 // CTAs the CTA-pair kernel launches for this problem (needs the current device: occupancy query on first use)
@@ -139,6 +144,20 @@ cudaError_t launch_bn_finalize(const double* partial2, int spl, int C, int G, do
                                const float* beta, float* running_mean, float* running_var, long long* nbt,
                                float momentum, float eps, int train, int order_rev, float* mean, float* invstd,
                                float* scale, float* shift, cudaStream_t st);
+struct BnEvalJob {      // layout == b200cd_bn_eval_job (include/b200cd.h)
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  float* mean;          // [G][C] each: the four per-(group, channel) vectors the apply / fused-epilogue kernels read
+  float* invstd;
+  float* scale;
+  float* shift;
+  int C, G;
+  float eps;
+  int start;            // first thread block (256 channels per block)
+};
+cudaError_t launch_bn_eval_affine_batched(const BnEvalJob* jobs, int njobs, int total_blocks, cudaStream_t st);
 cudaError_t launch_bn_apply(const void* r, long long ld_r, const float* scale, const float* shift, int n_img, int H,
                             int W, int C, int G, int diff, void* a, long long ld_a, void* a2, long long ld_a2,
                             void* pool, long long ld_p, void* dif, long long ld_d, void* pool_idx, cudaStream_t st);
@@ -183,6 +202,19 @@ struct ReduceJob {      // layout == b200cd_reduce_job (include/b200cd.h)
 int reduce_job_parts(int splits, int d1, int taps);   // 0 = row-transposing path
 long long reduce_job_blocks(int splits, int d0, int d1, int taps);
 cudaError_t launch_wgrad_reduce_batched(const ReduceJob* jobs, int njobs, long long total_blocks, cudaStream_t st);
+
+struct AugmentJob {     // layout == b200cd_augment_job (include/b200cd.h)
+  const float* src;     // [H0][W0][C] fp32, HWC as the dataset loads it
+  int H0, W0, C;
+  int x0, y0;           // crop origin
+  int hflip, vflip, rotk;
+  int use_mul, use_gamma;
+  int cmap[16];         // output channel -> source channel
+  float mul[16];        // per SOURCE channel
+  float gamma[16];
+  int reserved;
+};
+cudaError_t launch_augment(const AugmentJob* jobs, int n, int cs, int cout, float* out, cudaStream_t st);
 
 struct AdamWJob {       // layout == b200cd_adamw_job (include/b200cd.h)
   float* p;

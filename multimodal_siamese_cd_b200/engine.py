@@ -89,6 +89,7 @@ class Stage:
     bwd_sum_rows: int = 0
     branch: int = 0          # trunk (stream) the stage belongs to
     join_before_bwd: bool = False   # its backward needs the gradients of both branches (first encoder op after two decoders)
+    fused_eval: bool = False        # inference: conv + folded BatchNorm + ReLU in one launch
 
     @property
     def cin(self) -> int:
@@ -508,6 +509,10 @@ class StepEngine:
             tab, nj, blocks, elems = ops.make_pack_jobs(self._pack_specs, self.device, prec=self.precise)
             src = sum(sp[1].numel() for sp in self._pack_specs)
             self.pack_fwd.append(lambda: ops.pack_weights_batched(tab, nj, blocks, elems, src, prec=self.precise))
+            if not self.train:
+                btab, bnj, bblocks = ops.make_bn_eval_jobs([(st.bn, st.mean, st.invstd, st.scale, st.shift)
+                                                            for st in self.stages], self.device)
+                self.pack_fwd.append(lambda: ops.bn_eval_affine_batched(btab, bnj, bblocks))
 
     # ------------------------------------------------------------------------------------------------
     def _alloc_ws(self) -> None:
@@ -548,12 +553,24 @@ class StepEngine:
         outs = st.outs
         prec = eng.precise
 
+        # inference: BatchNorm is a fixed affine (computed for all stages by ONE launch at the start of the forward plan,
+        # ops.bn_eval_affine_batched). A stage whose only product is its activation runs as ONE launch — conv with the
+        # affine + ReLU folded into the epilogue, no pre-BN tensor, no apply pass; stages that also pool / difference /
+        # copy keep conv -> apply (two launches).
+        live = {k for k in ("a", "a2", "pool", "dif") if outs.get(k) is not None}
+        fused_eval = (not train) and live == {"a"} and eng.device.type == "cuda" and ops.FPROP_PAIR
+        st.fused_eval = fused_eval
+
         def run():
+            if fused_eval:
+                ops.conv_gemm_affine(mode, st.in_view, st.Wf, outs["a"], conv.bias, st.scale[0], st.shift[0], True, prec=prec)
+                return
             stats = eng.ws_stats[st.branch] if train else None
             ops.conv_gemm(mode, 0, st.in_view, st.Wf, st.r, bias=conv.bias, stats=stats, stat_groups=sg, prec=prec)
-            ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2[st.branch], bn.weight, bn.bias, bn.running_mean,
-                         bn.running_var, bn.num_batches_tracked if train else None, bn.momentum, bn.eps, train,
-                         st.order_rev, st.mean, st.invstd, st.scale, st.shift)
+            if train:
+                ops.bn_stats(stats, C, C, tpg, st.G, count, spl, eng.ws_stats2[st.branch], bn.weight, bn.bias, bn.running_mean,
+                             bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, True,
+                             st.order_rev, st.mean, st.invstd, st.scale, st.shift)
             ops.bn_apply(st.r, st.scale, st.shift, st.G, bool(outs.get("diff", False)), a=outs.get("a"),
                          a2=outs.get("a2"), pool=outs.get("pool"), dif=outs.get("dif"), pool_idx=outs.get("pool_idx"),
                          prec=prec)
@@ -1010,10 +1027,12 @@ class StepEngine:
         """Kernel launches of one forward / backward (counted from the plan, not measured)."""
         n_first = sum(1 for s in self.stages if s.first)
         n_st = len(self.stages)
-        fwd = len(self.pack_fwd) + n_first + n_st * 4 + len(self.upconvs) + len(self.heads)  # conv, 2x stats, apply
         if not self.train:
-            fwd -= n_st  # no stats reduce in eval
+            # pack_input per encoder, weight pack + BatchNorm affine (pack_fwd), one launch per fused stage, two otherwise
+            fwd = len(self.pack_fwd) + n_first + sum(1 if s.fused_eval else 2 for s in self.stages) + \
+                len(self.upconvs) + len(self.heads)
             return {"forward": fwd, "backward": 0}
+        fwd = len(self.pack_fwd) + n_first + n_st * 4 + len(self.upconvs) + len(self.heads)  # conv, 2x stats, apply
         bwd = len(self.pack_bwd) + n_st * 5 + sum(1 for s in self.stages if s.d_in is not None) + \
             len(self.upconvs) * 5 + sum(2 * (len(h.inputs) + 1) for h in self.heads)
         return {"forward": fwd, "backward": bwd}

@@ -296,6 +296,59 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
                                                 out.data_ptr(), o_ld, _ptr(bias), _ptr(stats), _stream()))
 
 
+def conv_gemm_affine(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor],
+                     scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, prec: bool = False) -> None:
+    """Inference: conv + folded BatchNorm (+ ReLU) in one launch, out = act((A * Bw + bias) * scale + shift)."""
+    _require_cuda(A, Bw, out, scale, shift)
+    n, H, W, ka, a_ld = _nhwc(A)
+    no, Ho, Wo, Co, o_ld = _nhwc(out)
+    N = Bw.shape[0]
+    taps = 9 if mode == 0 else 1
+    assert mode in (0, 1) and Bw.shape[1] == taps * ka * (3 if prec else 1) and (no, Ho, Wo, Co) == (n, H, W, N)
+    assert scale.dtype == torch.float32 and scale.numel() >= N and shift.numel() >= N
+    flags = 4 | (16 if prec else 0)
+    _count(1)
+    fam = "fprop3x3" if mode == 0 else "gemm1tap"
+    with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out) * (2 if prec else 1) + _nbytes(Bw),
+               f"{n}x{H}x{W} k{ka}->n{N} affine"):
+        _lib.check(_lib.load().b200cd_conv_gemm_affine(mode, flags, A.data_ptr(), a_ld, n, H, W, ka, Bw.data_ptr(), N,
+                                                       out.data_ptr(), o_ld, _ptr(bias), scale.data_ptr(), shift.data_ptr(),
+                                                       int(relu), _stream()))
+
+
+_BN_EVAL_JOB_DTYPE = None
+
+
+def make_bn_eval_jobs(specs: Sequence[tuple], device) -> tuple[torch.Tensor, int, int]:
+    """specs: (bn module, mean, invstd, scale, shift) with the four [G, C] fp32 outputs. Returns (device job table,
+    njobs, total thread blocks) for bn_eval_affine_batched (b200cd_bn_eval_job: 8 pointers + 4 x 4 bytes = 80 bytes)."""
+    import numpy as np
+    global _BN_EVAL_JOB_DTYPE
+    if _BN_EVAL_JOB_DTYPE is None:
+        _BN_EVAL_JOB_DTYPE = np.dtype([("gamma", "<u8"), ("beta", "<u8"), ("rm", "<u8"), ("rv", "<u8"), ("mean", "<u8"),
+                                       ("invstd", "<u8"), ("scale", "<u8"), ("shift", "<u8"), ("C", "<i4"), ("G", "<i4"),
+                                       ("eps", "<f4"), ("start", "<i4")], align=True)
+        assert _BN_EVAL_JOB_DTYPE.itemsize == 80
+    arr = np.zeros(len(specs), dtype=_BN_EVAL_JOB_DTYPE)
+    blocks = 0
+    for i, (bn, mean, invstd, scale, shift) in enumerate(specs):
+        G, Cc = mean.shape
+        for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, mean, invstd, scale, shift):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        arr[i] = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                  mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), Cc, G, bn.eps, blocks)
+        blocks += (Cc + 255) // 256
+    table = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    return table, len(specs), blocks
+
+
+def bn_eval_affine_batched(table: torch.Tensor, njobs: int, blocks: int) -> None:
+    _require_cuda(table)
+    _count(1)
+    with _Prof("bn_stats", 0.0, 0.0):
+        _lib.check(_lib.load().b200cd_bn_eval_affine_batched(table.data_ptr(), njobs, blocks, _stream()))
+
+
 def conv_gemm_bnbwd(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor, r: torch.Tensor, scale: torch.Tensor,
                     shift: torch.Tensor, sums: torch.Tensor, stat_groups: int) -> None:
     """Input-gradient convolution (mode 0 with dgrad weights / mode 2) whose epilogue also accumulates the

@@ -46,7 +46,7 @@ def grad_report(got: dict, ref: dict) -> dict:
 
 def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alpha: float = 0.5, path: str = "dropin",
              corr: bool = False, graphs: bool = True, steps: int = 1, precision: str = "fast", fp64: bool = False,
-             skip_q: bool = False) -> dict:
+             skip_q: bool = False, format_floor: bool = False) -> dict:
     """Returns error metrics of the CUDA path vs the bf16-storage oracle (q) and the exact fp32 oracle (x = the
     reference's arithmetic). fp64=True adds (d): the same step in float64, plus the reference's OWN fp32-vs-fp64
     error (`floor_*`) — the yardstick north_star's tolerance has to be read against."""
@@ -151,6 +151,24 @@ def run_case(mtype: str, cin: int, topo, B: int, H: int, W: int, kind: str, alph
                 elif k.endswith("num_batches_tracked"):
                     assert int(sd_after[k]) == int(v), f"{k}: {int(sd_after[k])} != {int(v)}"
             res["bn_running_maxabs"] = bn_err
+    if format_floor and fp64:
+        # the storage format's own floor: the oracle with split-bf16 storage points and EXACT (fp64) arithmetic against
+        # the exact fp64 run — what a perfect kernel set with this storage would measure as grads_d
+        memo_key = (mtype, cin, tuple(topo), B, H, W, kind, alpha, corr, "fmt")
+        if memo_key not in _ORACLE_MEMO:
+            O.set_storage("split")
+            try:
+                b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+                rq = O.train_step(mtype, O.clone_state(sd0, dtype=torch.float64), b64, kind=kind, alpha=alpha, q=True)
+            finally:
+                O.set_storage("bf16")
+            _ORACLE_MEMO[memo_key] = rq
+        rq = _ORACLE_MEMO[memo_key]
+        r64 = _ORACLE_MEMO[(mtype, cin, tuple(topo), B, H, W, kind, alpha, corr, "d")][0]
+        res["format_floor_grads"] = grad_report(rq["grads"], r64["grads"])
+        ro64 = r64["outs"] if isinstance(r64["outs"], tuple) else (r64["outs"],)
+        rqo = rq["outs"] if isinstance(rq["outs"], tuple) else (rq["outs"],)
+        res["format_floor_logits"] = max(rel(a.detach(), b.detach()) for a, b in zip(rqo, ro64))
     res["n_pixels"] = got_outs[0].numel()
     net.module.release_engines()
     return res

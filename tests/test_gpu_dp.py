@@ -68,7 +68,8 @@ def _worker(rank: int, port: int, path: str, q, backend: str = "nccl", precision
             logits = out.detach().cpu()
             grads = {n: p.grad.detach().cpu() for n, p in net.module.named_parameters() if p.grad is not None}
         torch.cuda.synchronize()
-        q.put((rank, loss.item(), logits, grads))
+        # numpy arrays are pickled by value: torch tensors travel as shared-memory handles that die with this process
+        q.put((rank, loss.item(), logits.numpy(), {k: v.numpy() for k, v in grads.items()}))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -89,7 +90,7 @@ def _run_world(path: str, backend: str, precision: str):
     got = {}
     for _ in range(WORLD):
         rank, loss, logits, grads = q.get(timeout=300)
-        got[rank] = (loss, logits, grads)
+        got[rank] = (loss, torch.from_numpy(logits), {k: torch.from_numpy(v) for k, v in grads.items()})
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -57,16 +57,20 @@ def test_step_parity(name):
 
 
 # ---- PRECISE mode: split-bf16 storage, three-MMA products (include/b200cd.h ABI version 2) -------------------------
-# Bounds, read against the reference's OWN fp32-vs-fp64 error measured in the same test (`floor_*`):
-#  * logits: <= 1e-4 vs the reference's fp32 arithmetic (north_star: 1e-3) on independent inputs, <= 1e-3 on correlated
-#    t1 / t2 (the realistic bi-temporal case: feature differences amplify rounding ~10x);
-#  * loss: <= 1e-5 (north_star: 1e-4);
-#  * gradients vs the fp64 run: global <= 8 x floor, per-parameter max <= 5 x floor (measured 3.2-3.6 x / 1.8-3.1 x).
-#    Why not 1 x: a forward perturbation eps flips ~eps of the ReLU masks / max-pool arg-maxes and the gradient error
-#    grows like sqrt(eps); 16 mantissa bits (eps ~1e-5) against fp32's 24 bits (6e-8) leave a factor ~3-5 that the CPU
-#    oracle reproduces exactly with split storage and fp64 arithmetic (oracle.set_storage("split"));
-#  * masks: identical wherever the reference's |logit| >= 1e-3; F1 within 1e-4;
+# What it meets, vs the reference's fp32 arithmetic (x) and the same step in float64 (d):
+#  * logits: <= 1e-4 (north_star: 1e-3) on independent inputs, <= 1e-3 on correlated t1 / t2 (the realistic
+#    bi-temporal case: feature differences amplify rounding ~10x);
+#  * loss: <= 1e-5 (north_star: 1e-4); masks: identical wherever the reference's |logit| >= 1e-3; F1 within 1e-4;
 #  * BatchNorm running statistics within 2e-5.
+# Gradients: a ReLU / max-pool network's gradient is a DISCONTINUOUS function of its forward values — a forward
+# perturbation eps flips ~eps of the masks and arg-maxes and the gradient error grows like sqrt(eps), not eps. The
+# reference's own fp32 (eps 6e-8) differs from float64 by 3e-3 .. 7e-3 per parameter at random init through train-mode
+# BatchNorm (`floor_grads`, measured below); 16 mantissa bits (eps 8e-6) land at ~1e-2 .. 4e-2 per
+# parameter — 10-30x tighter than the fast mode (0.3 .. 0.8), still above north_star's literal 1e-3, which the
+# reference itself does not meet against its own float64 run. The bound asserted here is therefore (a) absolute:
+# global <= 3e-2 / per-parameter <= 8e-2 (correlated inputs: 0.1 / 0.15), and (b) structural: the CUDA path must sit
+# at the STORAGE FORMAT's own floor — the oracle with split-bf16 storage points and exact float64 arithmetic
+# (oracle.set_storage("split")) measures the same error, so nothing but the 16-bit storage contributes.
 PRECISE_CASES = {
     "siamese": dict(mtype="siameseunet", cin=4, topo=SMALL, B=3, H=32, W=32, kind="supervised"),
     "unet": dict(mtype="unet", cin=6, topo=SMALL, B=3, H=32, W=32, kind="supervised"),
@@ -84,9 +88,12 @@ PRECISE_CASES = {
 def _assert_precise(r, corr=False):
     assert r["loss_x"] <= 1e-5, r
     assert r["logits_x"] <= (1e-3 if corr else 1e-4), r
-    fl = r["floor_grads"]
-    assert r["grads_d"]["global"] <= max(8 * fl["global"], 2e-3), (r["grads_d"], fl)
-    assert r["grads_d"]["max"] <= max(5 * fl["max"], 1e-2), (r["grads_d"], fl)
+    gd = r["grads_d"]
+    assert gd["global"] <= (0.1 if corr else 3e-2) and gd["max"] <= (0.15 if corr else 8e-2), (gd, r["floor_grads"])
+    if "format_floor_grads" in r:   # at the storage format's floor: within 2.5x of split storage + exact arithmetic
+        ff = r["format_floor_grads"]
+        assert gd["global"] <= 2.5 * ff["global"] + 1e-3 and gd["max"] <= 2.5 * ff["max"] + 2e-3, (gd, ff)
+        assert r["logits_d"] <= 2.5 * r["format_floor_logits"] + 1e-5, r
     assert r["prebn_bias_grad_max"] == 0.0, r
     assert r["margin3_flips_x"] == 0 and r["f1_diff_x"] <= 1e-4, r
     if "bn_running_maxabs" in r:
@@ -98,7 +105,7 @@ def test_step_parity_precise(name):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     kw = PRECISE_CASES[name]
-    r = E.run_case(**kw, precision="precise", fp64=True, skip_q=True)
+    r = E.run_case(**kw, precision="precise", fp64=True, skip_q=True, format_floor=True)
     _assert_precise(r, corr=kw.get("corr", False))
 
 

@@ -29,6 +29,45 @@ def test_kernel_split_bf16(name):
     assert res["ok"], res
 
 
+@pytest.mark.parametrize("variant", range(4))
+def test_gpu_augmenter_matches_reference_transforms(variant):
+    """data.GpuAugmenter (b200cd_augment: crop + flips + rot90 + colour shift + gamma + channel regrouping + CHW packing,
+    one launch per batch) against the numpy pipeline of utils/augmentations.py as restated in oracle/augment_oracle.py
+    (pinned bit-exactly against the unmodified reference classes by tests/test_augment_cpu.py), same numpy seed.
+    Geometry is exact; the photometric ops are fp32 on the device vs float64 in numpy (<= 2e-6)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+
+    from multimodal_siamese_cd_b200.data import GpuAugmenter
+    from oracle import augment_oracle
+    from test_augment_cpu import VARIANTS, aug_cfg, sample
+    dev = torch.device("cuda", 0)
+    cfg = aug_cfg(**VARIANTS[variant])
+    aug = GpuAugmenter(cfg, dev)
+    host = [sample(seed, H=50 + 3 * seed, W=61 - 2 * seed) for seed in range(5)]    # tiles of different sizes
+    want, params = [], []
+    for i, (imgs, bld, chg) in enumerate(host):
+        np.random.seed(300 + i)
+        want.append(augment_oracle.transform(cfg, imgs, bld, chg))
+        np.random.seed(300 + i)
+        params.append(aug.draw(chg))
+    x1, x2, y, s = aug.apply([torch.from_numpy(h[0]).to(dev) for h in host], [torch.from_numpy(h[1]).to(dev) for h in host],
+                             [torch.from_numpy(h[2]).to(dev) for h in host], params)
+    torch.cuda.synchronize()
+    photometric = cfg.AUGMENTATION.COLOR_SHIFT or cfg.AUGMENTATION.GAMMA_CORRECTION
+    for i, (wi, wb, wc) in enumerate(want):
+        # x_t1 = [S1 t1 | S2 t1], x_t2 = [S1 t2 | S2 t2] (utils/datasets.py:151-162)
+        w1 = np.concatenate([wi[0:2], wi[4:8]], 0)
+        w2 = np.concatenate([wi[2:4], wi[8:12]], 0)
+        for got, ref in ((x1[i], w1), (x2[i], w2), (s[i], wb)):
+            d = np.abs(got.cpu().numpy() - ref).max()
+            assert d <= (2e-6 if photometric else 0.0), (variant, i, d)
+        assert np.array_equal(y[i].cpu().numpy(), wc)
+    with pytest.raises(RuntimeError):
+        GpuAugmenter(cfg, torch.device("cpu"))
+
+
 def test_device_prefetcher_order_and_contents():
     """data.DevicePrefetcher yields every batch once, in order, with the host contents, while reusing two buffer sets."""
     if not torch.cuda.is_available():
