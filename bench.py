@@ -195,15 +195,19 @@ def run_reference_arm(args, out) -> None:
 
 
 # --------------------------------------------------------------------------------------------------------------
-def profile_step(ts, steps: int = 2) -> dict:
+def profile_step(ts, steps: int = 2, one_stream: bool = False) -> dict:
     """Eager (no graph) passes with a CUDA event pair around every launch, recorded on the stream the launch goes to, in
     the SAME stream layout as the timed run (second trunk on its own stream, weight gradients on the side stream). A
     spin kernel queued first keeps the GPU busy while the host enqueues the whole step, so no event interval contains
-    host launch latency. Per-kernel-family time, algorithmic FLOPs / bytes."""
+    host launch latency. Per-kernel-family time, algorithmic FLOPs / bytes. one_stream: every launch on one stream
+    (each kernel alone on the GPU: its isolated rate, not what it achieves while sharing SMs with the other streams)."""
     import torch
 
     from multimodal_siamese_cd_b200 import ops
     eng = ts.eng
+    saved = (eng.branch_streams, eng.wgrad_side)
+    if one_stream:
+        eng.branch_streams = eng.wgrad_side = False
     fam = {}
     l0 = ops.LAUNCHES
     for it in range(steps + 1):
@@ -229,6 +233,7 @@ def profile_step(ts, steps: int = 2) -> dict:
                 d["bytes"] += by
                 d["calls"] += 1
     ops.PROFILE = None
+    eng.branch_streams, eng.wgrad_side = saved
     fam["_launches_per_step"] = (ops.LAUNCHES - l0) // (steps + 1)
     for d in fam.values():
         if not isinstance(d, dict):
@@ -468,6 +473,43 @@ class Bench:
         return parity, cpu
 
     # ------------------------------------------------------------------------------------------------------
+    def eval_throughput(self, cfgname: str, tile: int = 1024) -> dict:
+        """Inference as utils/evaluation.py:7-23 runs it: net.eval(), no_grad, one whole tile per call (batch 1),
+        through the drop-in module, HBM-resident input. Both numerics modes."""
+        torch = self.torch
+        from multimodal_siamese_cd_b200 import networks
+        from multimodal_siamese_cd_b200.config import synthetic_cfg
+        mtype, cin, _, _, _, _, yaml = CONFIGS[cfgname]
+        cfg = synthetic_cfg(mtype, in_channels=cin)
+        torch.manual_seed(cfg.SEED)
+        net = networks.create_network(cfg).to(self.dev).eval()
+        xc = 6 if mtype in TWO_STREAM else cin
+        g = torch.Generator(device=self.dev).manual_seed(7)
+        x1 = torch.rand(1, xc, tile, tile, device=self.dev, generator=g)
+        x2 = torch.rand(1, xc, tile, tile, device=self.dev, generator=g)
+        out = {"what": f"{yaml}: {mtype}.eval(), one {tile}x{tile} tile per call (batch 1), logits returned on the device",
+               "unit": "tiles/s"}
+        with torch.no_grad():
+            for mode in ("fast", "precise"):
+                net.module.set_precision(mode)
+                for _ in range(3):
+                    net(x1, x2)
+                torch.cuda.synchronize()
+                n = 10
+                self.e0.record()
+                for _ in range(n):
+                    z = net(x1, x2)
+                self.e1.record()
+                torch.cuda.synchronize()
+                ms = self.e0.elapsed_time(self.e1) / n
+                eng = next(iter(net.module._engines.values()))
+                out[mode] = {"value": 1e3 / ms, "ms_per_tile": ms, "launches_per_tile": eng.launches_per_step()["forward"],
+                             "logit_checksum": float(z.double().sum())}
+                net.module.release_engines()
+                torch.cuda.empty_cache()
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
     def library_baseline(self, cfgname: str, B: int) -> dict:
         """Stock PyTorch eager on this B200 running the reference's own modules (cuDNN / cuBLAS; none of this repo's
         kernels): fp32 with TF32 off, TF32 on, bf16 autocast + channels_last. Falls back to the oracle port on cuda when
@@ -567,6 +609,7 @@ def main() -> None:
     if bn.rank == 0:
         # ---- roofline of the dominant kernel + per-family breakdown (rank 0; same streams as the timed run) -----
         fam = profile_step(ts)
+        fam_iso = profile_step(ts, one_stream=True)
     net.module.release_engines()
     del ts, net
     torch.cuda.empty_cache()
@@ -611,13 +654,24 @@ def main() -> None:
                  "launches_per_step": d["calls"], "ms_per_step": d["ms"],
                  "timing": "CUDA event pair per launch on the launching stream, eager, same stream layout as `value` "
                            "(two trunk streams + weight-gradient side stream), whole step enqueued behind a spin kernel"})
+    fam_iso.pop("_launches_per_step")
+    di = fam_iso[dom]
+    roof["isolated"] = {"achieved": (di["flops"] / di["ms"] / 1e9) if dom in tensor_fams else (di["bytes"] / di["ms"] / 1e6),
+                        "ms_per_step": di["ms"], "sum_of_all_kernels_ms": sum(v["ms"] for v in fam_iso.values()),
+                        "what": "the same launches on ONE stream (each kernel alone on the GPU)"}
+    roof["isolated"]["frac"] = roof["isolated"]["achieved"] / roof["peak"]
     breakdown = {}
     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
         b = {"ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "calls": v["calls"]}
+        vi = fam_iso.get(k)
         if k in tensor_fams:
             b["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
+            if vi:
+                b["isolated_ms"], b["isolated_tflops"] = round(vi["ms"], 4), round(vi["flops"] / vi["ms"] / 1e9, 1)
         else:
             b["gbs"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+            if vi:
+                b["isolated_ms"], b["isolated_gbs"] = round(vi["ms"], 4), round(vi["bytes"] / vi["ms"] / 1e6, 1)
         breakdown[k] = b
 
     cpu = parity = None
@@ -629,6 +683,12 @@ def main() -> None:
             lib = bn.library_baseline(args.config, main_res["batch_per_gpu"])
         except Exception as e:  # noqa: BLE001
             lib = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    evl = None
+    if bn.world == 1 and not args.no_configs:
+        try:
+            evl = bn.eval_throughput(args.config)
+        except Exception as e:  # noqa: BLE001
+            evl = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     def mode_row(r):
         row = {"value": r["value"], "ms_per_step": r["ms_per_step"], "steps": K if r is main_res else min(K, 50),
@@ -659,6 +719,7 @@ def main() -> None:
                           "(see parity), 'precise' is the mode built to meet it" % args.precision},
         "parity": parity,
         "configs": cfg_rows,
+        "extra": {"eval": evl},
         "kernel_breakdown": breakdown,
         "step_roofline": main_res["step_roofline"],
         "loss": main_res["loss"],
