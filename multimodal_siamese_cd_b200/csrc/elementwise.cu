@@ -471,20 +471,49 @@ __global__ void __launch_bounds__(256) bn_stats_fused_kernel(const float2* __res
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;  // whole warp
   float rm = running_mean[c], rv = running_var[c];
+  // The kernel sits on the critical path between a convolution and its apply pass and moves a few hundred KB: it is
+  // pure latency. All partial rows of BOTH stat-groups are requested before anything is summed (rows <= 320: ten
+  // independent loads per lane and group in flight), so the launch costs one memory round trip instead of ten.
+  constexpr int kMaxK = 10;
+  const bool all_at_once = rows <= 32 * kMaxK && G <= 2;
+  float2 pre[2][kMaxK];
+  if (all_at_once) {
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const float2* base = partial + static_cast<long long>(gi) * rows * ld + c;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) {
+        const int r = lane + 32 * k;
+        pre[gi][k] = (gi < G && r < rows) ? __ldg(base + static_cast<long long>(r) * ld) : make_float2(0.f, 0.f);
+      }
+    }
+  }
   for (int gi = 0; gi < G; ++gi) {
     const int g = order_rev ? G - 1 - gi : gi;
     const float2* base = partial + static_cast<long long>(g) * rows * ld + c;
     double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0;
-    int r = lane;
-    for (; r + 32 < rows; r += 64) {
-      const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
-      const float2 v1 = __ldg(base + static_cast<long long>(r + 32) * ld);
-      s += v0.x; q += v0.y;
-      s1 += v1.x; q1 += v1.y;
-    }
-    if (r < rows) {
-      const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
-      s += v0.x; q += v0.y;
+    if (all_at_once) {
+      // same pairing of rows as the streaming loop below (rows l, l + 64, ... in one chain, l + 32, l + 96, ... in the
+      // other), so both paths give bit-identical statistics
+#pragma unroll
+      for (int k = 0; k < kMaxK; k += 2) {
+        const float2 v0 = g == 0 ? pre[0][k] : pre[1][k];          // static register indices
+        const float2 v1 = g == 0 ? pre[0][k + 1] : pre[1][k + 1];
+        s += v0.x; q += v0.y;
+        s1 += v1.x; q1 += v1.y;
+      }
+    } else {
+      int r = lane;
+      for (; r + 32 < rows; r += 64) {
+        const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
+        const float2 v1 = __ldg(base + static_cast<long long>(r + 32) * ld);
+        s += v0.x; q += v0.y;
+        s1 += v1.x; q1 += v1.y;
+      }
+      if (r < rows) {
+        const float2 v0 = __ldg(base + static_cast<long long>(r) * ld);
+        s += v0.x; q += v0.y;
+      }
     }
     s += s1;
     q += q1;

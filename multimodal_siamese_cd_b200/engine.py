@@ -983,7 +983,9 @@ class StepEngine:
         # (op_begin, op_end, grad_lo, grad_hi); drop empty segments
         return [c for c in cuts if c[1] > c[0]]
 
-    def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False) -> None:
+    def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False, inner_graphs: bool = True) -> None:
+        """inner_graphs=False: every segment runs eagerly (the caller is capturing the whole step, collectives
+        included, into ONE graph)."""
         import torch.distributed as dist
         if self._dp_plan is None:
             self._dp_plan = self.plan_buckets(nbuckets)
@@ -994,7 +996,7 @@ class StepEngine:
         for f in self.pack_bwd:
             f()
         for bi, (o0, o1, g0, g1) in enumerate(self._dp_plan):
-            if self.use_graphs and self._dp_runs >= 1:
+            if self.use_graphs and inner_graphs and self._dp_runs >= 1:
                 if self._dp_graphs[bi] is None:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()

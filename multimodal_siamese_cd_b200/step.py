@@ -24,6 +24,10 @@ from .engine import StepEngine
 
 
 _DEBUG_SKIP_ALLREDUCE = __import__("os").environ.get("B200CD_DEBUG_SKIP_ALLREDUCE", "0") == "1"
+# Data-parallel step as ONE CUDA graph (NCCL only): forward, loss sums, their all-reduce, loss backward, the bucketed
+# backward and its gradient all-reduces are captured together, so the host launches one graph per step instead of
+# 3 + 2 x buckets graphs with eager collectives in between. B200CD_DP_GRAPH=0 keeps the segmented replay.
+_DP_GRAPH = __import__("os").environ.get("B200CD_DP_GRAPH", "1") != "0"
 
 
 @dataclass
@@ -105,6 +109,11 @@ class TrainStep:
         elif dp_group is not None:
             self.dp = dp_group
         self.grad_buckets = max(1, int(__import__("os").environ.get("B200CD_GRAD_BUCKETS", grad_buckets)))
+        self._g_dp = None
+        self._dp_graph_ok = False
+        if self.dp is not None and _DP_GRAPH:
+            import torch.distributed as dist
+            self._dp_graph_ok = dist.get_backend(self.dp) == "nccl"   # host-side backends (gloo) cannot be captured
 
     # ------------------------------------------------------------------------------------------------
     def _target_of(self, term: _Term) -> torch.Tensor:
@@ -165,9 +174,28 @@ class TrainStep:
                 self.weights.copy_(torch.tensor(w, dtype=torch.float32))
             self.rowmask.copy_(lab.to(torch.uint8), non_blocking=True)
 
+    def _dp_step_eager(self) -> None:
+        import torch.distributed as dist
+        eng = self.eng
+        eng._run_fwd_eager()
+        self._loss_fwd()
+        dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.dp)
+        self._loss_bwd()
+        eng.backward_dp(self.dp, self.grad_buckets, skip_allreduce=_DEBUG_SKIP_ALLREDUCE, inner_graphs=False)
+
     def run(self) -> torch.Tensor:
         """fwd + loss + bwd on the staged batch. Returns the 0-d loss tensor (device)."""
         eng = self.eng
+        if self.dp is not None and self._dp_graph_ok and eng.use_graphs and self._steps >= 2:
+            if self._g_dp is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._dp_step_eager()
+                self._g_dp = g
+            self._g_dp.replay()
+            self._steps += 1
+            return (self.losses * self.weights).sum()
         eng.forward_static()
         self._graphed("_g_loss_fwd", self._loss_fwd)
         if self.dp is not None:

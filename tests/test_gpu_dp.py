@@ -57,7 +57,10 @@ def _worker(rank: int, port: int, path: str, q, backend: str = "nccl", precision
             grads = {n: p.grad.detach().cpu() for n, p in net.module.named_parameters() if p.grad is not None}
         elif path == "fused":
             ts = TrainStep(net.module, rows.stop - rows.start, HW, HW, kind="supervised", device=dev)
-            loss = ts(x1, x2, y_change=y)
+            sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+            for _ in range(4):          # the same step four times: eager, eager, then graph capture and replay
+                net.load_state_dict(sd0)
+                loss = ts(x1, x2, y_change=y)
             logits = ts.eng.output_tensors()[0].detach().cpu()
             g = ts.eng.grads
             grads = {n: g.views[n].detach().cpu() for n, _ in g.params if n not in g.skip}
