@@ -269,6 +269,10 @@ class Bench:
             dist.init_process_group("nccl", device_id=self.dev)
             from multimodal_siamese_cd_b200 import parallel
             parallel.enable_data_parallel()
+            if os.environ.get("B200CD_NATIVE_COMM", "1") != "0":
+                # gradient buckets / loss sums all-reduced by libb200cd's own NCCL communicator (b200cd_comm_init);
+                # torch.distributed stays the bootstrap and the barrier
+                parallel.enable_native_comm()
         self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier(self):

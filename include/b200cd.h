@@ -306,6 +306,41 @@ int b200cd_adamw_step(const b200cd_adamw_job* jobs_dev, int njobs, int64_t total
                       double beta2, double eps, double weight_decay, int64_t step_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Workspace queries: every entry point takes caller-allocated workspaces; this returns the bytes each needs (or -1).
+ *   B200CD_WS_BN_BWD      d = {n_img, H, W, C, G}                         fp32 workspace of b200cd_bn_bwd*
+ *   B200CD_WS_CONV_STATS  d = {mode, out_mode, flags, n_img, H, W, ka, N}  statistics side output of b200cd_conv_gemm
+ *   B200CD_WS_WGRAD       d = {splits, taps, cu, cv}                       split partials of b200cd_wgrad_gemm*
+ *   B200CD_WS_COLSUM      d = {nblk, C}                                    block partials of b200cd_colsum*
+ *   B200CD_WS_PJ          d = {nblk}                                       block partials of b200cd_pj_fwd
+ *   B200CD_WS_BN_STATS    d = {spl, G, C}                                  second-stage partials of b200cd_bn_stats
+ * ------------------------------------------------------------------------------------------------- */
+#define B200CD_WS_BN_BWD 1
+#define B200CD_WS_CONV_STATS 2
+#define B200CD_WS_WGRAD 3
+#define B200CD_WS_COLSUM 4
+#define B200CD_WS_PJ 5
+#define B200CD_WS_BN_STATS 6
+int64_t b200cd_query_workspace(int op, const int64_t* dims, int ndims);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU: a library-owned NCCL communicator, one process per GPU — replaces the gather / reduce-add of
+ * nn.DataParallel (utils/networks.py:27). NCCL is resolved with dlopen at run time (the copy already loaded in the
+ * process, e.g. torch's, or `libnccl_path`); streams and buffers stay the caller's.
+ *   rank 0: b200cd_comm_unique_id(id) -> ship the 128 bytes to the other ranks by any means
+ *   all:    b200cd_comm_init(id, rank, nranks)  (CUDA device = the caller's current device)
+ *   b200cd_allreduce_bucket: in-place SUM of a fp32 gradient bucket on `stream` (asynchronous, graph-capturable)
+ *   b200cd_allreduce_f64:    in-place SUM of the power-Jaccard partial sums (3 per loss term)
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_comm_load(const char* libnccl_path);
+int b200cd_comm_version(void);
+int b200cd_comm_unique_id(void* id128);
+int b200cd_comm_init(const void* id128, int rank, int nranks);
+int b200cd_comm_size(void);
+int b200cd_allreduce_bucket(float* buf, int64_t count, void* stream);
+int b200cd_allreduce_f64(double* buf, int64_t count, void* stream);
+int b200cd_comm_destroy(void);
+
+/* ---------------------------------------------------------------------------------------------------
  * Training-time augmentation + packing (next-row N2) — replaces the per-sample numpy transforms of
  * utils/augmentations.py:6-142 as composed by utils/datasets.py:111-181: crop (UniformCrop / ImportanceRandomCrop
  * :105-142) -> RandomFlip :44-62 -> RandomRotate :65-72 -> ColorShift :75-86 -> GammaCorrection :89-101 ->

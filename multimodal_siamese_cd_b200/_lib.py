@@ -65,6 +65,15 @@ SIGNATURES = {
     "b200cd_confusion_counts": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "b200cd_adamw_step": (_i, [_vp, _i, _i64, _d, _d, _d, _d, _d, _i64, _vp]),
     "b200cd_pj_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i64, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "b200cd_query_workspace": (_i64, [_i, C.POINTER(C.c_int64), _i]),
+    "b200cd_comm_load": (_i, [C.c_char_p]),
+    "b200cd_comm_version": (_i, []),
+    "b200cd_comm_unique_id": (_i, [_vp]),
+    "b200cd_comm_init": (_i, [_vp, _i, _i]),
+    "b200cd_comm_size": (_i, []),
+    "b200cd_allreduce_bucket": (_i, [_vp, _i64, _vp]),
+    "b200cd_allreduce_f64": (_i, [_vp, _i64, _vp]),
+    "b200cd_comm_destroy": (_i, []),
     "b200cd_augment": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b200cd_bn_eval_affine_batched": (_i, [_vp, _i, _i, _vp]),
     "b200cd_conv_gemm_affine": (_i, [_i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp]),

@@ -17,7 +17,7 @@ ROOT = PKG.parent
 LIB = PKG / "libb200cd.so"
 STAMP = PKG / ".libb200cd.stamp"
 
-SOURCES = ["abi.cu", "gemm_fprop.cu", "gemm_fprop2.cu", "gemm_wgrad.cu", "elementwise.cu", "elementwise_hp.cu"]
+SOURCES = ["abi.cu", "gemm_fprop.cu", "gemm_fprop2.cu", "gemm_wgrad.cu", "elementwise.cu", "elementwise_hp.cu", "comm.cu"]
 HEADERS = [CSRC / "kernels.h", CSRC / "ptx.cuh", ROOT / "include" / "b200cd.h"]
 
 NVCC_FLAGS = [
@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         raise RuntimeError("nvcc compilation of libb200cd failed")
     link = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-            "-o", str(LIB), *map(str, objs)]
+            "-o", str(LIB), *map(str, objs), "-ldl"]
     subprocess.run(link, check=True)
     STAMP.write_text(digest)
     return LIB

@@ -136,6 +136,7 @@ bool chan_ok(int C) { return C >= 64 && C % 64 == 0 && 256 % (C / 8) == 0; }
 }  // namespace
 
 namespace b200cd {
+void set_last_error(const char* msg) { g_last_error = msg; }
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("B200CD_PDL");
@@ -688,6 +689,32 @@ int b200cd_augment(const b200cd_augment_job* jobs_dev, int n, int crop, int cout
   CUDA_TRY(b200cd::launch_augment(reinterpret_cast<const b200cd::AugmentJob*>(jobs_dev), n, crop, cout, out,
                                   reinterpret_cast<cudaStream_t>(stream)));
   return 0;
+}
+
+int64_t b200cd_query_workspace(int op, const int64_t* d, int nd) {
+  // bytes of caller-allocated workspace / side-output buffers, per op (see include/b200cd.h for the dims of each op)
+  if (d == nullptr) return -1;
+  switch (op) {
+    case B200CD_WS_BN_BWD:        // n_img, H, W, C, G -> fp32 workspace of b200cd_bn_bwd*
+      return nd == 5 ? static_cast<int64_t>(4 * b200cd_bn_bwd_ws_floats((int)d[0], (int)d[1], (int)d[2], (int)d[3], (int)d[4])) : -1;
+    case B200CD_WS_CONV_STATS: {  // mode, out_mode, flags, n_img, H, W, ka, N -> fp32 [groups][rows][N][2] statistics buffer
+      if (nd != 8) return -1;
+      const int rows = b200cd_conv_gemm_stat_rows((int)d[0], (int)d[1], (int)d[2], (int)d[3], (int)d[4], (int)d[5], (int)d[6], (int)d[7]);
+      if (rows < 0) return -1;
+      const int groups = ((int)d[2] & 8) ? (((int)d[2] >> 8) & 0xff) : 1;
+      return static_cast<int64_t>(groups) * rows * d[7] * 2 * 4;
+    }
+    case B200CD_WS_WGRAD:         // splits, taps, cu, cv -> fp32 split partials of b200cd_wgrad_gemm*
+      return nd == 4 ? 4 * d[0] * d[1] * d[2] * d[3] : -1;
+    case B200CD_WS_COLSUM:        // nblk, C -> fp32 block partials of b200cd_colsum*
+      return nd == 2 ? 4 * d[0] * d[1] : -1;
+    case B200CD_WS_PJ:            // nblk -> fp64 block partials of b200cd_pj_fwd
+      return nd == 1 ? 8 * 3 * d[0] : -1;
+    case B200CD_WS_BN_STATS:      // spl, G, C -> fp64 second-stage partials of b200cd_bn_stats
+      return nd == 3 ? 8 * 2 * d[0] * d[1] * d[2] : -1;
+    default:
+      return -1;
+  }
 }
 
 int b200cd_reduce_job_parts(int splits, int d1, int taps) {

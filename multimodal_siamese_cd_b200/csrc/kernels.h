@@ -9,6 +9,9 @@
 
 namespace b200cd {
 
+// thread-local message behind b200cd_last_error (abi.cu); other translation units report through it
+void set_last_error(const char* msg);
+
 // Launch helper. With B200CD_PDL=1 in the environment kernels are launched with the programmatic-dependent-launch
 // attribute (see ptx.cuh: pdl_wait); by default they are plain stream-ordered launches and the kernels'
 // griddepcontrol instructions are no-ops (measured on B200: PDL does not shorten the graph-replayed step).

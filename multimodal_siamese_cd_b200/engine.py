@@ -20,7 +20,7 @@ from typing import Callable, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, parallel
 
 BF16 = torch.bfloat16
 
@@ -1014,7 +1014,10 @@ class StepEngine:
             if skip_allreduce:   # measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1): wrong gradients
                 continue
             with torch.cuda.stream(comm):
-                dist.all_reduce(self.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=group)
+                if parallel.native_comm():     # the library's own NCCL communicator (b200cd_allreduce_bucket)
+                    parallel.allreduce_sum_(self.grads.flat[g0:g1])
+                else:
+                    dist.all_reduce(self.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=group)
         main.wait_stream(comm)
         self._dp_runs += 1
         self._runs += 1

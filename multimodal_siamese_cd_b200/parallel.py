@@ -44,7 +44,66 @@ def enable_data_parallel(group=None, mode: str = "sharded") -> None:
     loss_functions.set_data_parallel_group(("default" if group is None else group) if mode == "sharded" else None)
 
 
+def _nccl_path() -> bytes:
+    import glob
+    import os
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+    return cands[0].encode() if cands else b""
+
+
+def enable_native_comm() -> bool:
+    """Create the LIBRARY-owned NCCL communicator (b200cd_comm_init, include/b200cd.h) over the ranks of the enabled
+    data-parallel group: rank 0 draws the NCCL unique id and the 128 bytes travel through the existing
+    torch.distributed group once. Afterwards gradient buckets and loss sums are all-reduced by libb200cd itself
+    (b200cd_allreduce_bucket / _f64) on the caller's streams — capturable into the step's CUDA graph — and
+    torch.distributed is only the bootstrap. Returns False (and changes nothing) when the group is not NCCL-backed."""
+    import torch.distributed as dist
+
+    from . import _lib
+    if not _STATE["enabled"] or dist.get_backend(_STATE["group"]) != "nccl":
+        return False
+    if _STATE.get("native"):
+        return True
+    lib = _lib.load()
+    _lib.check(lib.b200cd_comm_load(_nccl_path()))
+    rank, world = rank_world()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        import ctypes as C
+        buf = (C.c_char * 128)()
+        _lib.check(lib.b200cd_comm_unique_id(buf))
+        idt.copy_(torch.tensor(list(bytes(buf)), dtype=torch.uint8))
+    src = dist.get_global_rank(_STATE["group"], 0) if _STATE["group"] is not None else 0
+    dist.broadcast(idt, src=src, group=_STATE["group"])
+    host = bytes(idt.cpu().numpy().tobytes())
+    _lib.check(lib.b200cd_comm_init(host, rank, world))
+    _STATE["native"] = True
+    return True
+
+
+def native_comm() -> bool:
+    return bool(_STATE.get("native"))
+
+
+def allreduce_sum_(t: torch.Tensor) -> None:
+    """In-place SUM all-reduce of a contiguous fp32 / fp64 CUDA tensor on the current stream: the library's own NCCL
+    communicator when it exists, else torch.distributed."""
+    if _STATE.get("native"):
+        from . import _lib
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.float64)
+        fn = _lib.load().b200cd_allreduce_bucket if t.dtype == torch.float32 else _lib.load().b200cd_allreduce_f64
+        _lib.check(fn(t.data_ptr(), t.numel(), torch.cuda.current_stream().cuda_stream))
+    else:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_STATE["group"])
+
+
 def disable_data_parallel() -> None:
+    if _STATE.get("native"):
+        from . import _lib
+        _lib.load().b200cd_comm_destroy()
+        _STATE["native"] = False
     _STATE["enabled"] = False
     _STATE["group"] = None
     _STATE["mode"] = "sharded"
@@ -96,8 +155,7 @@ class GatherRows(torch.autograd.Function):
 def allreduce_gradients(flat: torch.Tensor) -> None:
     """SUM all-reduce of a flat gradient buffer across the data-parallel group (no-op when disabled)."""
     if _STATE["enabled"]:
-        import torch.distributed as dist
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_STATE["group"])
+        allreduce_sum_(flat)
 
 
 def shard_rows(batch_size: int, rank: int, world: int) -> slice:

@@ -179,9 +179,18 @@ class TrainStep:
         eng = self.eng
         eng._run_fwd_eager()
         self._loss_fwd()
-        dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.dp)
+        self._allreduce_sums()
         self._loss_bwd()
         eng.backward_dp(self.dp, self.grad_buckets, skip_allreduce=_DEBUG_SKIP_ALLREDUCE, inner_graphs=False)
+
+    def _allreduce_sums(self) -> None:
+        import torch.distributed as dist
+
+        from . import parallel
+        if parallel.native_comm() and self.dp is dist.group.WORLD:
+            parallel.allreduce_sum_(self.sums)
+        else:
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.dp)
 
     def run(self) -> torch.Tensor:
         """fwd + loss + bwd on the staged batch. Returns the 0-d loss tensor (device)."""
@@ -199,8 +208,7 @@ class TrainStep:
         eng.forward_static()
         self._graphed("_g_loss_fwd", self._loss_fwd)
         if self.dp is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.dp)
+            self._allreduce_sums()
         self._graphed("_g_loss_bwd", self._loss_bwd)
         if self.dp is not None:
             eng.backward_dp(self.dp, self.grad_buckets, skip_allreduce=_DEBUG_SKIP_ALLREDUCE)

@@ -38,7 +38,11 @@ def _worker(rank: int, port: int, path: str, q, backend: str = "nccl", precision
     else:
         dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     try:
+        native = path.endswith("_native")
+        path = path.replace("_native", "")
         parallel.enable_data_parallel(mode="gather" if path == "gather" else "sharded")
+        if native:      # the library's own NCCL communicator (b200cd_comm_init / b200cd_allreduce_bucket)
+            assert parallel.enable_native_comm() and parallel.native_comm()
         cfg = synthetic_cfg(MTYPE, in_channels=CIN, topology=TOPO)
         torch.manual_seed(7)
         net = networks.create_network(cfg).to(dev).train()
@@ -75,6 +79,7 @@ def _worker(rank: int, port: int, path: str, q, backend: str = "nccl", precision
         q.put((rank, loss.item(), logits.numpy(), {k: v.numpy() for k, v in grads.items()}))
         dist.barrier()
     finally:
+        parallel.disable_data_parallel()
         dist.destroy_process_group()
 
 
@@ -122,7 +127,7 @@ def _run_world(path: str, backend: str, precision: str):
         assert torch.equal(got[0][2][k], got[1][2][k]), k                                    # identical on all ranks
 
 
-@pytest.mark.parametrize("path", ["fused", "dropin", "gather"])
+@pytest.mark.parametrize("path", ["fused", "dropin", "gather", "fused_native", "gather_native"])
 def test_two_gpu_data_parallel_matches_dataparallel_semantics(path):
     if not torch.cuda.is_available() or torch.cuda.device_count() < WORLD:
         pytest.skip("needs 2 CUDA devices")
