@@ -120,9 +120,10 @@ def _run_world(path: str, backend: str, precision: str):
             d, nn_ = (grads[k].double() - r.double()).norm().item(), r.double().norm().item()
             num, den = num + d * d, den + nn_ * nn_
             worst = max(worst, d / max(nn_, 1e-30))
-        # SUM-reduced gradients, globally and per parameter (fast: bf16 noise floor; precise: ~5 x the fp32 floor)
-        assert (num / den) ** 0.5 <= (5e-3 if prec else 0.25), (num / den) ** 0.5
-        assert worst <= (2e-2 if prec else 0.8), worst
+        # SUM-reduced gradients, globally and per parameter: the same envelopes as the single-GPU step tests
+        # (tests/test_gpu_e2e.py: fast = bf16 noise floor; precise = the split-storage format floor)
+        assert (num / den) ** 0.5 <= (3e-2 if prec else 0.25), (num / den) ** 0.5
+        assert worst <= (8e-2 if prec else 0.8), worst
     for k in got[0][2]:
         assert torch.equal(got[0][2][k], got[1][2][k]), k                                    # identical on all ranks
 
