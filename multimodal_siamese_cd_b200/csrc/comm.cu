@@ -118,14 +118,16 @@ int b200cd_comm_size(void) { return g_comm != nullptr ? g_nranks : 0; }
 
 int b200cd_allreduce_bucket(float* buf, int64_t count, void* stream) {
   if (g_comm == nullptr) return comm_fail(B200CD_ERR_SHAPE, "allreduce_bucket: b200cd_comm_init has not been called");
-  if (buf == nullptr || count < 1) return comm_fail(B200CD_ERR_SHAPE, "allreduce_bucket: empty buffer");
+  if (count == 0) return 0;  // an empty bucket (a backward segment that completes no gradient) is a no-op on every rank
+  if (buf == nullptr || count < 0) return comm_fail(B200CD_ERR_SHAPE, "allreduce_bucket: NULL buffer / negative count");
   return nccl_check(g_nccl.all_reduce(buf, buf, static_cast<size_t>(count), kNcclFloat32, kNcclSum, g_comm,
                                       reinterpret_cast<cudaStream_t>(stream)), "ncclAllReduce(f32)");
 }
 
 int b200cd_allreduce_f64(double* buf, int64_t count, void* stream) {
   if (g_comm == nullptr) return comm_fail(B200CD_ERR_SHAPE, "allreduce_f64: b200cd_comm_init has not been called");
-  if (buf == nullptr || count < 1) return comm_fail(B200CD_ERR_SHAPE, "allreduce_f64: empty buffer");
+  if (count == 0) return 0;
+  if (buf == nullptr || count < 0) return comm_fail(B200CD_ERR_SHAPE, "allreduce_f64: NULL buffer / negative count");
   return nccl_check(g_nccl.all_reduce(buf, buf, static_cast<size_t>(count), kNcclFloat64, kNcclSum, g_comm,
                                       reinterpret_cast<cudaStream_t>(stream)), "ncclAllReduce(f64)");
 }

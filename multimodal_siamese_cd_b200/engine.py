@@ -1011,8 +1011,8 @@ class StepEngine:
             ev = torch.cuda.Event()
             ev.record(main)
             comm.wait_event(ev)
-            if skip_allreduce:   # measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1): wrong gradients
-                continue
+            if skip_allreduce or g1 <= g0:   # skip: measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1), wrong gradients
+                continue                     # g1 == g0: the segment completed no gradient (same on every rank)
             with torch.cuda.stream(comm):
                 if parallel.native_comm():     # the library's own NCCL communicator (b200cd_allreduce_bucket)
                     parallel.allreduce_sum_(self.grads.flat[g0:g1])

@@ -30,6 +30,24 @@ from . import loss_functions
 
 _STATE = {"enabled": False, "group": None, "mode": "sharded"}
 
+# Objects that hold CUDA graphs with captured NCCL collectives (step.TrainStep). ncclCommDestroy — torch's
+# destroy_process_group as well as b200cd_comm_destroy — waits until every graph that references the communicator has
+# been destroyed, so the graphs are dropped in disable_data_parallel() before any communicator goes away.
+_GRAPH_HOLDERS = __import__("weakref").WeakSet()
+
+
+def register_graph_holder(obj) -> None:
+    """`obj.release_comm_graphs()` is called by disable_data_parallel()."""
+    _GRAPH_HOLDERS.add(obj)
+
+
+def release_comm_graphs() -> None:
+    holders = list(_GRAPH_HOLDERS)
+    if holders and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for h in holders:
+        h.release_comm_graphs()
+
 
 def enable_data_parallel(group=None, mode: str = "sharded") -> None:
     import torch.distributed as dist
@@ -100,6 +118,8 @@ def allreduce_sum_(t: torch.Tensor) -> None:
 
 
 def disable_data_parallel() -> None:
+    """Call before torch.distributed.destroy_process_group(): graphs with captured collectives are released first."""
+    release_comm_graphs()
     if _STATE.get("native"):
         from . import _lib
         _lib.load().b200cd_comm_destroy()

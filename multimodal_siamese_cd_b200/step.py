@@ -202,6 +202,8 @@ class TrainStep:
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._dp_step_eager()
                 self._g_dp = g
+                from . import parallel
+                parallel.register_graph_holder(self)
             self._g_dp.replay()
             self._steps += 1
             return (self.losses * self.weights).sum()
@@ -216,6 +218,11 @@ class TrainStep:
             eng.backward_static()
         self._steps += 1
         return (self.losses * self.weights).sum()
+
+    def release_comm_graphs(self) -> None:
+        """Drop the whole-step graph (it holds captured NCCL collectives; the communicator cannot be destroyed while it
+        exists). The next run() captures again."""
+        self._g_dp = None
 
     def __call__(self, x_t1, x_t2, is_labeled=None, **targets) -> torch.Tensor:
         self.set_inputs(x_t1, x_t2, is_labeled=is_labeled, **targets)
