@@ -983,9 +983,11 @@ class StepEngine:
         # (op_begin, op_end, grad_lo, grad_hi); drop empty segments
         return [c for c in cuts if c[1] > c[0]]
 
-    def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False, inner_graphs: bool = True) -> None:
+    def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False, inner_graphs: bool = True,
+                    timeline: Optional[list] = None) -> None:
         """inner_graphs=False: every segment runs eagerly (the caller is capturing the whole step, collectives
-        included, into ONE graph)."""
+        included, into ONE graph). timeline: a list that receives (label, timing event) pairs — segment ends on the
+        compute stream, all-reduce start / end on the communication stream (tools/dp_timeline.py)."""
         import torch.distributed as dist
         if self._dp_plan is None:
             self._dp_plan = self.plan_buckets(nbuckets)
@@ -1008,16 +1010,26 @@ class StepEngine:
                 self._dp_graphs[bi].replay()
             else:
                 self.run_bwd_range(o0, o1)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=timeline is not None)
             ev.record(main)
             comm.wait_event(ev)
+            if timeline is not None:
+                timeline.append((f"seg{bi}_done", ev))
             if skip_allreduce or g1 <= g0:   # skip: measurement aid only (B200CD_DEBUG_SKIP_ALLREDUCE=1), wrong gradients
                 continue                     # g1 == g0: the segment completed no gradient (same on every rank)
             with torch.cuda.stream(comm):
+                if timeline is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(comm)
+                    timeline.append((f"ar{bi}_start[{4 * (g1 - g0)} B]", e))
                 if parallel.native_comm():     # the library's own NCCL communicator (b200cd_allreduce_bucket)
                     parallel.allreduce_sum_(self.grads.flat[g0:g1])
                 else:
                     dist.all_reduce(self.grads.flat[g0:g1], op=dist.ReduceOp.SUM, group=group)
+                if timeline is not None:
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(comm)
+                    timeline.append((f"ar{bi}_end", e))
         main.wait_stream(comm)
         self._dp_runs += 1
         self._runs += 1

@@ -215,7 +215,7 @@ class B200Net(nn.Module):
         super().__init__()
         self.cfg = cfg
         self._engines: "OrderedDict[tuple, StepEngine]" = OrderedDict()
-        self.use_cuda_graphs = True
+        self.use_cuda_graphs = os.environ.get("B200CD_CUDA_GRAPHS", "1") != "0"
         # "fast": single-bf16 storage / operands (the throughput mode). "precise": split-bf16 storage and three-MMA
         # products, which meets the reference-fp32 tolerance. Default from B200CD_PRECISION.
         self.precision = os.environ.get("B200CD_PRECISION", "fast")

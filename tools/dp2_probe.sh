@@ -1,13 +1,42 @@
-set -x
-timeout 900 python -m pytest tests/test_gpu_dp.py -q -x > gpurun_out/pytest_dp2_r02.log 2>&1; tail -15 gpurun_out/pytest_dp2_r02.log | cut -c1-600
-for combo in "1 1" "0 1" "1 0" "0 0"; do
-  set -- $combo
-  B200CD_DP_GRAPH=$1 B200CD_NATIVE_COMM=$2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 60 --warmup 10 --no-configs > gpurun_out/bench_n2_graph$1_native$2.json 2> gpurun_out/bench_n2_graph$1_native$2.err
-  python -c "
-import json,sys
+# Two-GPU probe (gpurun --gpus 2): NCCL data-parallel tests, the same box's N=1 and N=2 bench values, what the gradient
+# all-reduce costs (skip-all-reduce upper bound, NCCL CTA caps) and the device timeline of one data-parallel step.
+TAG=${1:-r02}
+N=${2:-2}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_dp.py -q > gpurun_out/${TAG}_pytest_dp.log 2>&1
+echo "pytest dp rc=$?"; tail -4 gpurun_out/${TAG}_pytest_dp.log | cut -c1-400
+FLAGS="--steps 60 --warmup 10 --no-configs --no-cpu-baseline --no-library-baseline --no-e2e"
+run() {  # name, nproc, env...
+  name=$1; np=$2; shift 2
+  if [ "$np" = "1" ]; then
+    env "$@" timeout 300 python bench.py --gpus 1 $FLAGS > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+  else
+    env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 \
+      --master-port 29511 bench.py --gpus $np $FLAGS > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+  fi
+  python - <<EOF
+import json
 try:
-    d=json.load(open('gpurun_out/bench_n2_graph$1_native$2.json')); print('graph$1 native$2', d['value'], d['ms_per_step'], d['e2e']['value'], d['loss'])
-except Exception as e: print('graph$1 native$2 FAILED', e)
-"
-  tail -3 gpurun_out/bench_n2_graph$1_native$2.err | cut -c1-300
+    d = json.load(open('gpurun_out/${TAG}_${name}.json'))
+    print('${name}', 'value', round(d['value'], 1), 'ms', round(d['ms_per_step'], 4), 'loss', d['loss'])
+except Exception as e:
+    print('${name} FAILED', e)
+EOF
+}
+run n1 1 A=1
+run n${N}_default $N A=1
+run n${N}_skip_allreduce $N B200CD_DEBUG_SKIP_ALLREDUCE=1
+run n${N}_maxctas4 $N NCCL_MAX_CTAS=4
+run n${N}_maxctas8 $N NCCL_MAX_CTAS=8
+run n${N}_torchdist $N B200CD_NATIVE_COMM=0
+for v in "default A=1" "maxctas4 NCCL_MAX_CTAS=4"; do
+  set -- $v
+  env $2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port 29533 tools/dp_timeline.py dualstream > gpurun_out/${TAG}_dp_timeline_n${N}_$1.json 2> gpurun_out/${TAG}_dp_timeline_n${N}_$1.err
+  echo "timeline $1 rc=$?"; head -c 1500 gpurun_out/${TAG}_dp_timeline_n${N}_$1.json; echo
 done
+timeout 300 python tools/dp_timeline.py dualstream > gpurun_out/${TAG}_dp_timeline_n1.json 2> gpurun_out/${TAG}_dp_timeline_n1.err
+head -c 600 gpurun_out/${TAG}_dp_timeline_n1.json; echo
+du -sh gpurun_out
+timeout 300 python tools/tiny_kernel_probe.py > gpurun_out/${TAG}_tiny_kernels.json 2> gpurun_out/${TAG}_tiny_kernels.err
+cat gpurun_out/${TAG}_tiny_kernels.json; tail -3 gpurun_out/${TAG}_tiny_kernels.err
