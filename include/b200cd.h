@@ -341,6 +341,17 @@ int b200cd_allreduce_f64(double* buf, int64_t count, void* stream);
 int b200cd_comm_destroy(void);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Plan graphs: a step's launches, captured by the caller into a cudaGraph_t (any capture API; the Python host layer
+ * uses torch.cuda.graph), instantiated and launched by the library so that the per-node stream priorities recorded at
+ * capture time are honoured (cudaGraphInstantiateFlagUseNodePriority): the plan's dependent chain runs on
+ * high-priority streams, the weight-gradient GEMMs on a default-priority one. The caller keeps ownership of the
+ * cudaGraph_t and of every buffer the graph touches; the executable graph is the library's until destroyed.
+ * ------------------------------------------------------------------------------------------------- */
+int b200cd_graph_instantiate(void* cuda_graph, int use_node_priority, void** exec_out);
+int b200cd_graph_launch(void* graph_exec, void* stream);
+int b200cd_graph_exec_destroy(void* graph_exec);
+
+/* ---------------------------------------------------------------------------------------------------
  * Training-time augmentation + packing (next-row N2) — replaces the per-sample numpy transforms of
  * utils/augmentations.py:6-142 as composed by utils/datasets.py:111-181: crop (UniformCrop / ImportanceRandomCrop
  * :105-142) -> RandomFlip :44-62 -> RandomRotate :65-72 -> ColorShift :75-86 -> GammaCorrection :89-101 ->

@@ -74,6 +74,9 @@ SIGNATURES = {
     "b200cd_allreduce_bucket": (_i, [_vp, _i64, _vp]),
     "b200cd_allreduce_f64": (_i, [_vp, _i64, _vp]),
     "b200cd_comm_destroy": (_i, []),
+    "b200cd_graph_instantiate": (_i, [_vp, _i, C.POINTER(C.c_void_p)]),
+    "b200cd_graph_launch": (_i, [_vp, _vp]),
+    "b200cd_graph_exec_destroy": (_i, [_vp]),
     "b200cd_augment": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "b200cd_bn_eval_affine_batched": (_i, [_vp, _i, _i, _vp]),
     "b200cd_conv_gemm_affine": (_i, [_i, _i, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _vp, _vp, _vp, _i, _vp]),

@@ -717,6 +717,27 @@ int64_t b200cd_query_workspace(int op, const int64_t* d, int nd) {
   }
 }
 
+int b200cd_graph_instantiate(void* cuda_graph, int use_node_priority, void** exec_out) {
+  if (cuda_graph == nullptr || exec_out == nullptr) return fail(B200CD_ERR_SHAPE, "graph_instantiate: NULL graph / output");
+  cudaGraphExec_t exec = nullptr;
+  const unsigned long long flags = use_node_priority ? cudaGraphInstantiateFlagUseNodePriority : 0ull;
+  CUDA_TRY(cudaGraphInstantiateWithFlags(&exec, reinterpret_cast<cudaGraph_t>(cuda_graph), flags));
+  *exec_out = exec;
+  return 0;
+}
+
+int b200cd_graph_launch(void* graph_exec, void* stream) {
+  if (graph_exec == nullptr) return fail(B200CD_ERR_SHAPE, "graph_launch: NULL executable graph");
+  CUDA_TRY(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200cd_graph_exec_destroy(void* graph_exec) {
+  if (graph_exec == nullptr) return 0;
+  CUDA_TRY(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+  return 0;
+}
+
 int b200cd_reduce_job_parts(int splits, int d1, int taps) {
   return (splits < 1 || d1 < 4 || taps < 1) ? -1 : b200cd::reduce_job_parts(splits, d1, taps);
 }

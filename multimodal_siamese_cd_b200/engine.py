@@ -45,6 +45,61 @@ _BRANCH_MODE = __import__("os").environ.get("B200CD_BRANCH_STREAMS", "1")
 BRANCH_STREAMS = _BRANCH_MODE != "0"
 BRANCH_MAX_PIXELS = 4 << 20
 WGRAD_SIDE_STREAM = __import__("os").environ.get("B200CD_WGRAD_SIDE_STREAM", "1") != "0"
+# Stream priorities: the dependent chain of a plan (convolutions, BatchNorm passes, input gradients — both trunk
+# streams) runs on HIGH-priority streams, the weight-gradient GEMMs that only have to finish by the end of a backward
+# segment on a default-priority one, so whenever both have a kernel ready the chain's CTAs are dispatched first. The
+# priorities are kernel-node attributes inside the captured graphs too.
+# tail flush of the split-K reduction when at most 1 / TAIL_FLUSH_DIV of the weight-gradient volume is left (0 = off)
+TAIL_FLUSH_DIV = int(__import__("os").environ.get("B200CD_TAIL_FLUSH_DIV", "24"))
+STREAM_PRIO = __import__("os").environ.get("B200CD_STREAM_PRIO", "1") != "0"
+# one weight-gradient side stream per trunk of a two-trunk plan (else both trunks' weight gradients share one)
+WGRAD_SIDE_PER_BRANCH = __import__("os").environ.get("B200CD_WGRAD_SIDE_PER_BRANCH", "0") != "0"
+_PRIO_WGRAD_HIGH = __import__("os").environ.get("B200CD_STREAM_PRIO", "1") == "2"   # experiment: the reverse assignment
+# Graphs instantiated and launched by libb200cd (b200cd_graph_instantiate, include/b200cd.h) with
+# cudaGraphInstantiateFlagUseNodePriority, so the stream priorities above survive inside a replayed plan: torch's own
+# instantiate passes no such flag and every node would run at the launch stream's priority.
+GRAPH_NODE_PRIO = __import__("os").environ.get("B200CD_GRAPH_NODE_PRIO", "1") != "0"
+
+
+class PlanGraph:
+    """One captured plan: torch.cuda.graph captures (thread_local error mode: a DataLoader pin-memory thread calling
+    cudaHostAlloc / event functions during a global-mode capture would invalidate it), the library instantiates and
+    launches when node priorities are wanted; else torch replays."""
+
+    def __init__(self, fn):
+        import ctypes as C
+
+        from . import _lib
+        self._exec = None
+        native = GRAPH_NODE_PRIO and STREAM_PRIO
+        torch.cuda.synchronize()
+        try:
+            self.g = torch.cuda.CUDAGraph(keep_graph=True) if native else torch.cuda.CUDAGraph()
+        except TypeError:                      # a torch without keep_graph: torch instantiates and replays
+            native = False
+            self.g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g, capture_error_mode="thread_local"):
+            fn()
+        if native:
+            out = C.c_void_p()
+            _lib.check(_lib.load().b200cd_graph_instantiate(C.c_void_p(int(self.g.raw_cuda_graph())), 1, C.byref(out)))
+            self._exec = out.value
+
+    def replay(self) -> None:
+        if self._exec is not None:
+            from . import _lib
+            _lib.check(_lib.load().b200cd_graph_launch(self._exec, torch.cuda.current_stream().cuda_stream))
+        else:
+            self.g.replay()
+
+    def __del__(self):
+        if getattr(self, "_exec", None) is not None:
+            try:
+                from . import _lib
+                _lib.load().b200cd_graph_exec_destroy(self._exec)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+            self._exec = None
 # transposed-conv bias gradient from the per-CTA channel sums of the dgrad launch that writes the concat-buffer gradient
 UP_BIAS_FROM_STATS = __import__("os").environ.get("B200CD_UP_BIAS_FROM_STATS", "1") != "0"
 FUSE_BN_BWD_MIN_PIXELS = int(__import__("os").environ.get("B200CD_FUSE_BN_BWD_MIN_PIXELS", 32768))
@@ -201,12 +256,15 @@ class StepEngine:
         self.heads: list[Head] = []
         self.fwd_ops: list[Callable[[], None]] = []
         self.bwd_ops: list[Callable[[], None]] = []
-        self._side_stream = None
-        self._side_dirty = False
+        self._side_streams: dict = {}             # weight-gradient side stream per executing trunk (0 / 1)
+        self._side_dirty: set = set()
+        self._exec_branch = 0                     # trunk whose op is being enqueued (_run_ops)
         self._cur_branch = 0                      # trunk being built (0, or 1 for the second stream's trunk)
         self.fwd_branch: list[int] = []           # per forward op: 0 / 1 = trunk, -1 = needs both trunks (heads)
         self.bwd_branch: list[int] = []
         self._branch_stream = None
+        self._chain_stream = None
+        self._in_chain = False
         self._branch_main = None
         self._branch_active = False
         self.branch_streams = BRANCH_STREAMS      # bench.profile_step turns both off to time launches one by one
@@ -618,12 +676,15 @@ class StepEngine:
                 self_inner.ctx = None
                 if eng.device.type != "cuda" or not eng.wgrad_side:
                     return
-                if eng._side_stream is None:
-                    eng._side_stream = torch.cuda.Stream(device=eng.device)
-                eng._side_stream.wait_stream(torch.cuda.current_stream())
-                self_inner.ctx = torch.cuda.stream(eng._side_stream)
+                key = eng._exec_branch if WGRAD_SIDE_PER_BRANCH else 0
+                side = eng._side_streams.get(key)
+                if side is None:
+                    side = eng._side_streams[key] = torch.cuda.Stream(device=eng.device,
+                                                                      priority=-1 if _PRIO_WGRAD_HIGH else 0)
+                side.wait_stream(torch.cuda.current_stream())
+                self_inner.ctx = torch.cuda.stream(side)
                 self_inner.ctx.__enter__()
-                eng._side_dirty = True
+                eng._side_dirty.add(key)
 
             def __exit__(self_inner, *exc):
                 if self_inner.ctx is not None:
@@ -634,9 +695,9 @@ class StepEngine:
 
     def _join_side(self) -> None:
         """The current stream waits for everything launched on the side stream so far."""
-        if self._side_stream is not None and self._side_dirty:
-            torch.cuda.current_stream().wait_stream(self._side_stream)
-            self._side_dirty = False
+        for key in sorted(self._side_dirty):
+            torch.cuda.current_stream().wait_stream(self._side_streams[key])
+        self._side_dirty.clear()
 
     def _ws_region(self, floats: int) -> int:
         """Every layer owns a region of the split workspace: the per-split partial weight gradients of a whole
@@ -839,6 +900,20 @@ class StepEngine:
                     k += 1
         if flush_after[-1] != specs[-1][0]:
             flush_after.append(specs[-1][0])
+        # Tail flush: backward ends with the shallow encoder layers — the longest-running convolutions of the plan with
+        # the smallest weight gradients (64 / 128 channels). A flush right before them completes all but a few MB of
+        # the gradient buffer ~1.5 ms before the plan ends, so a data-parallel caller's last exposed all-reduce is tiny
+        # (plan_buckets cuts there; measured: tools/dp_timeline.py).
+        self._tail_mark = None
+        rest = 0
+        for i in range(len(specs) - 1, 0, -1):
+            rest += specs[i][2].numel()
+            if (rest + specs[i - 1][2].numel()) * TAIL_FLUSH_DIV > total:
+                if i < len(specs) - 1 and specs[i - 1][0] not in flush_after and rest * TAIL_FLUSH_DIV <= total:
+                    flush_after.append(specs[i - 1][0])
+                    flush_after.sort()
+                    self._tail_mark = specs[i - 1][0]
+                break
         self._flush_groups = []
         lo = 0
         for fi, last_op in enumerate(flush_after):
@@ -891,13 +966,15 @@ class StepEngine:
                 f()
             return
         if self._branch_stream is None:
-            self._branch_stream = torch.cuda.Stream(device=self.device)
+            self._branch_stream = torch.cuda.Stream(device=self.device,
+                                                    priority=-1 if STREAM_PRIO and not _PRIO_WGRAD_HIGH else 0)
         main, side = torch.cuda.current_stream(), self._branch_stream
         self._branch_main = main
         side.wait_stream(main)                       # fork: everything queued so far is visible to both trunks
         self._branch_active = True
         try:
             for b, f in zip(branches, ops_list):
+                self._exec_branch = 1 if b in (1, 10) else 0
                 if b == 1 or b == 10:
                     if b == 10:                      # consumes what the main stream has produced so far
                         side.wait_stream(main)
@@ -914,6 +991,7 @@ class StepEngine:
                     side.wait_stream(main)
         finally:
             self._branch_active = False
+            self._exec_branch = 0
         main.wait_stream(side)                       # join
 
     def run_bwd_range(self, o0: int, o1: int) -> None:
@@ -921,15 +999,37 @@ class StepEngine:
         self._run_ops(self.bwd_ops[o0:o1], self.bwd_branch[o0:o1])
         self._join_side()
 
+    def _on_chain_stream(self, fn) -> None:
+        """Run `fn` on the plan's high-priority stream (forked from / joined into the current stream) when
+        B200CD_STREAM_PRIO is on; else right here."""
+        if not STREAM_PRIO or self.device.type != "cuda" or self._in_chain:
+            fn()
+            return
+        if self._chain_stream is None:
+            self._chain_stream = torch.cuda.Stream(device=self.device, priority=0 if _PRIO_WGRAD_HIGH else -1)
+        cur = torch.cuda.current_stream()
+        self._chain_stream.wait_stream(cur)
+        self._in_chain = True
+        try:
+            with torch.cuda.stream(self._chain_stream):
+                fn()
+        finally:
+            self._in_chain = False
+        cur.wait_stream(self._chain_stream)
+
     def _run_fwd_eager(self) -> None:
-        for f in self.pack_fwd:
-            f()
-        self._run_ops(self.fwd_ops, self.fwd_branch)
+        def body():
+            for f in self.pack_fwd:
+                f()
+            self._run_ops(self.fwd_ops, self.fwd_branch)
+        self._on_chain_stream(body)
 
     def _run_bwd_eager(self) -> None:
-        for f in self.pack_bwd:
-            f()
-        self.run_bwd_range(0, len(self.bwd_ops))
+        def body():
+            for f in self.pack_bwd:
+                f()
+            self.run_bwd_range(0, len(self.bwd_ops))
+        self._on_chain_stream(body)
 
     def forward(self, x_t1: torch.Tensor, x_t2: torch.Tensor) -> None:
         """Copies the inputs into the static buffers and runs the forward plan; logits land in head.logits."""
@@ -940,11 +1040,7 @@ class StepEngine:
     def forward_static(self) -> None:
         if self.use_graphs and self._runs >= 1:
             if self._g_fwd is None:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._run_fwd_eager()
-                self._g_fwd = g
+                self._g_fwd = PlanGraph(self._run_fwd_eager)
             self._g_fwd.replay()
         else:
             self._run_fwd_eager()
@@ -954,11 +1050,7 @@ class StepEngine:
         """Runs the backward plan from the dz buffers of the heads; gradients land in self.grads.flat."""
         if self.use_graphs and self._runs >= 2:
             if self._g_bwd is None:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._run_bwd_eager()
-                self._g_bwd = g
+                self._g_bwd = PlanGraph(self._run_bwd_eager)
             self._g_bwd.replay()
         else:
             self._run_bwd_eager()
@@ -980,8 +1072,15 @@ class StepEngine:
             i = max(i, cuts[-1][1] if cuts else 0)
             cuts.append((cuts[-1][1] if cuts else 0, i + 1, lo, marks[i]))
             lo = marks[i]
-        # (op_begin, op_end, grad_lo, grad_hi); drop empty segments
-        return [c for c in cuts if c[1] > c[0]]
+        cuts = [c for c in cuts if c[1] > c[0]]     # (op_begin, op_end, grad_lo, grad_hi); empty segments dropped
+        # the tail flush (see _plan_reduce_flushes) splits the last bucket: everything but the shallow layers' few MB
+        # goes out while those layers still run
+        tm = getattr(self, "_tail_mark", None)
+        if tm is not None and cuts:
+            o0, o1, g0, g1 = cuts[-1]
+            if o0 <= tm < o1 - 1 and g0 < marks[tm] < g1:
+                cuts[-1:] = [(o0, tm + 1, g0, marks[tm]), (tm + 1, o1, marks[tm], g1)]
+        return cuts
 
     def backward_dp(self, group, nbuckets: int = 4, skip_allreduce: bool = False, inner_graphs: bool = True,
                     timeline: Optional[list] = None) -> None:
@@ -1000,16 +1099,11 @@ class StepEngine:
         for bi, (o0, o1, g0, g1) in enumerate(self._dp_plan):
             if self.use_graphs and inner_graphs and self._dp_runs >= 1:
                 if self._dp_graphs[bi] is None:
-                    torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    # thread_local: a DataLoader pin-memory thread calling cudaHostAlloc / event functions during a
-                    # global-mode capture would invalidate it
-                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                        self.run_bwd_range(o0, o1)   # forks / joins the second trunk's stream inside the segment
-                    self._dp_graphs[bi] = g
+                    # forks / joins the second trunk's stream inside the segment
+                    self._dp_graphs[bi] = PlanGraph(lambda o0=o0, o1=o1: self._on_chain_stream(lambda: self.run_bwd_range(o0, o1)))
                 self._dp_graphs[bi].replay()
             else:
-                self.run_bwd_range(o0, o1)
+                self._on_chain_stream(lambda o0=o0, o1=o1: self.run_bwd_range(o0, o1))
             ev = torch.cuda.Event(enable_timing=timeline is not None)
             ev.record(main)
             comm.wait_event(ev)

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .engine import StepEngine
+from .engine import PlanGraph, StepEngine
 
 
 _DEBUG_SKIP_ALLREDUCE = __import__("os").environ.get("B200CD_DEBUG_SKIP_ALLREDUCE", "0") == "1"
@@ -141,10 +141,7 @@ class TrainStep:
             return
         g = getattr(self, attr)
         if g is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                fn()
+            g = PlanGraph(fn)
             setattr(self, attr, g)
         g.replay()
 
@@ -197,11 +194,7 @@ class TrainStep:
         eng = self.eng
         if self.dp is not None and self._dp_graph_ok and eng.use_graphs and self._steps >= 2:
             if self._g_dp is None:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._dp_step_eager()
-                self._g_dp = g
+                self._g_dp = PlanGraph(self._dp_step_eager)
                 from . import parallel
                 parallel.register_graph_holder(self)
             self._g_dp.replay()
