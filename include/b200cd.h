@@ -109,6 +109,10 @@ int b200cd_pack_weights_batched(const b200cd_pack_job* jobs_dev, int njobs, int6
  *          bit 2 (every mode; out_mode 1 only with mode 1) = CTA-pair kernel: two SMs compute one 256-pixel tile with cta_group::2 MMAs,
  *          each loading half of the weight tile; persistent, weights resident in shared memory when they fit
  *          (same result bit for bit).
+ *          bits 5..6 (with bit 2) = N tile of the CTA-pair kernel chosen by the caller: 1 = 64, 2 = 128, 3 = 256 output
+ *          channels per work item (0 = the library's own rule: the widest tile that divides N and leaves >= 48 items);
+ *          ignored when it does not divide N. The statistics row count depends on it: pass the same flags to
+ *          b200cd_conv_gemm_stat_rows. Same math; per-CTA statistics rows are summed in a different grouping.
  *   requires ka % 64 == 0, N % 64 == 0, a_ld % 8 == 0, out_ld % 8 == 0.
  * ------------------------------------------------------------------------------------------------- */
 int b200cd_conv_gemm(int mode, int out_mode, int flags, const void* A, int64_t a_ld, int n_img, int H, int W, int ka,

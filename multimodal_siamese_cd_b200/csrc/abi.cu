@@ -253,6 +253,13 @@ static ConvPlan plan_conv(int mode, int out_mode, int flags, int n_img, int H, i
     const int items256 = ((c.num_tiles + 1) / 2) * (N / 256);
     c.bn = items256 >= 48 ? 256 : 128;
   }
+  // flags bits 5..6: the caller's choice of N tile for the CTA-pair kernel (1 = 64, 2 = 128, 3 = 256; measured per layer
+  // shape, multimodal_siamese_cd_b200/tuning.py). Ignored when it does not divide N.
+  const int want = (flags >> 5) & 3;
+  if (c.pair && want != 0) {
+    const int w = 32 << want;
+    if (N % w == 0) c.bn = w;
+  }
   c.stat_groups = (c.pair && (flags & 8)) ? ((flags >> 8) & 0xff) : 0;
   return c;
 }

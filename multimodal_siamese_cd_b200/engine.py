@@ -744,7 +744,7 @@ class StepEngine:
                 if ps.n_img * ps.H * ps.W < FUSE_BN_BWD_MIN_PIXELS:
                     return None   # few work items per CTA pair: the longer epilogue is not hidden (measured)
                 if ps.bwd_sums is None:
-                    rows, per_cta = ops.conv_stat_rows(ps.n_img, ps.H, ps.W, ka, ps.cout, ps.G, mode=mode)
+                    rows, per_cta = ops.conv_stat_rows(ps.n_img, ps.H, ps.W, ka, ps.cout, ps.G, mode=mode, variant="bnbwd")
                     if not per_cta:
                         return None
                     ps.bwd_sum_rows = rows

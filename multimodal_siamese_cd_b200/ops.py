@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 
 import torch
 
-from . import _lib
+from . import _lib, tuning
 from ._lib import GradSrc
 
 
@@ -234,9 +234,10 @@ FPROP_WIDE_TILES = True     # 128 x 256 output tiles where N % 256 == 0 and the 
 FPROP_PAIR = True           # 3x3 convs on CTA pairs (cta_group::2, persistent, gemm_fprop2.cu)
 
 
-def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, stat_groups: int) -> int:
+def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, stat_groups: int, bn=None) -> int:
     """Tile policy (measured on B200, profiles/): 3x3 convs on CTA pairs; otherwise 128x256 tiles where N % 256 == 0,
-    the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels)."""
+    the halo variant when the N tile is 64 wide or the K loop is long (>= 8 chunks of 64 channels). bn: N tile of the
+    CTA-pair kernel (64 / 128 / 256; None = the library's rule) — tuning.py holds the measured per-shape choices."""
     pair_ok = out_mode == 0 or mode == 1
     if pair is None:
         pair = FPROP_PAIR and pair_ok and halo is None and wide is None
@@ -248,15 +249,19 @@ def _conv_flags(mode: int, out_mode: int, N: int, ka: int, halo, wide, pair, sta
         halo = mode == 0 and not wide and (pol == "all" or (pol in ("n64", "auto") and N % 128 != 0) or
                                            (pol == "auto" and ka >= 512))
     if pair:
-        return 4 | ((8 | (stat_groups << 8)) if stat_groups > 0 else 0)
+        return 4 | ((8 | (stat_groups << 8)) if stat_groups > 0 else 0) | tuning.flag_bits(bn)
     return (1 if (halo and mode == 0) else 0) | (2 if wide else 0)
 
 
 def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int, mode: int = 0,
-                   prec: bool = False) -> tuple[int, bool]:
+                   prec: bool = False, variant: str = "stats", bn=-1) -> tuple[int, bool]:
     """(rows per stat-group of the statistics buffer a 3x3 conv of this shape writes, per-CTA layout?). With the
-    CTA-pair kernel the rows are per CTA and epilogue group (<= 296); otherwise one row per 128-pixel tile."""
-    flags = _conv_flags(mode, 0, N, ka, None, None, None, stat_groups) | (16 if prec else 0)
+    CTA-pair kernel the rows are per CTA and epilogue group (<= 296); otherwise one row per 128-pixel tile.
+    variant / bn: as the launch that will write the buffer ("stats": conv_gemm with statistics, "bnbwd":
+    conv_gemm_bnbwd; bn = -1: the tuned tile of that launch shape, None: the library's rule)."""
+    if bn == -1:
+        bn = tuning.tile(variant, mode, 0, n_img, H, W, ka, N, prec)
+    flags = _conv_flags(mode, 0, N, ka, None, None, None, stat_groups, bn) | (16 if prec else 0)
     rows = _lib.load().b200cd_conv_gemm_stat_rows(mode, 0, flags, n_img, H, W, ka, N)
     if rows < 0:
         raise _lib.B200CDError("conv_gemm_stat_rows: unsupported shape")
@@ -267,9 +272,10 @@ def conv_stat_rows(n_img: int, H: int, W: int, ka: int, N: int, stat_groups: int
 def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor,
               bias: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
               halo: Optional[bool] = None, wide: Optional[bool] = None, pair: Optional[bool] = None,
-              stat_groups: int = 0, prec: bool = False) -> None:
+              stat_groups: int = 0, prec: bool = False, bn=-1) -> None:
     """G1. A: NHWC view (mode 2: at 2x the GEMM resolution); out: NHWC view (out_mode 1: at 2x).
-    prec: A / out are split-bf16 views, Bw is the K-tripled [hi | lo | hi] operand."""
+    prec: A / out are split-bf16 views, Bw is the K-tripled [hi | lo | hi] operand.
+    bn: N tile of the CTA-pair kernel (-1: tuning.py's entry for this launch shape, None: the library's rule)."""
     _require_cuda(A, Bw, out)
     n, Ha, Wa, ka, a_ld = _nhwc(A)
     H, W = (Ha // 2, Wa // 2) if mode == 2 else (Ha, Wa)
@@ -283,7 +289,10 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
     else:
         assert (no, Ho, Wo, Co) == (n, H, W, N)
         cout = 0
-    flags = _conv_flags(mode, out_mode, N, ka, halo, wide, pair, stat_groups if stats is not None else 0)
+    sg = stat_groups if stats is not None else 0
+    if bn == -1:
+        bn = tuning.tile("stats" if sg > 0 else "plain", mode, out_mode, n, H, W, ka, N, prec)
+    flags = _conv_flags(mode, out_mode, N, ka, halo, wide, pair, sg, bn)
     if prec:
         assert flags & 4, "split-bf16 operands need the CTA-pair kernel"
         flags |= 16
@@ -297,7 +306,7 @@ def conv_gemm(mode: int, out_mode: int, A: torch.Tensor, Bw: torch.Tensor, out: 
 
 
 def conv_gemm_affine(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor],
-                     scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, prec: bool = False) -> None:
+                     scale: torch.Tensor, shift: torch.Tensor, relu: bool = True, prec: bool = False, bn=-1) -> None:
     """Inference: conv + folded BatchNorm (+ ReLU) in one launch, out = act((A * Bw + bias) * scale + shift)."""
     _require_cuda(A, Bw, out, scale, shift)
     n, H, W, ka, a_ld = _nhwc(A)
@@ -306,7 +315,9 @@ def conv_gemm_affine(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Te
     taps = 9 if mode == 0 else 1
     assert mode in (0, 1) and Bw.shape[1] == taps * ka * (3 if prec else 1) and (no, Ho, Wo, Co) == (n, H, W, N)
     assert scale.dtype == torch.float32 and scale.numel() >= N and shift.numel() >= N
-    flags = 4 | (16 if prec else 0)
+    if bn == -1:
+        bn = tuning.tile("affine", mode, 0, n, H, W, ka, N, prec)
+    flags = 4 | (16 if prec else 0) | tuning.flag_bits(bn)
     _count(1)
     fam = "fprop3x3" if mode == 0 else "gemm1tap"
     with _Prof(fam, 2.0 * n * H * W * N * taps * ka, _nbytes(A, out) * (2 if prec else 1) + _nbytes(Bw),
@@ -350,7 +361,7 @@ def bn_eval_affine_batched(table: torch.Tensor, njobs: int, blocks: int) -> None
 
 
 def conv_gemm_bnbwd(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Tensor, r: torch.Tensor, scale: torch.Tensor,
-                    shift: torch.Tensor, sums: torch.Tensor, stat_groups: int) -> None:
+                    shift: torch.Tensor, sums: torch.Tensor, stat_groups: int, bn=-1) -> None:
     """Input-gradient convolution (mode 0 with dgrad weights / mode 2) whose epilogue also accumulates the
     BatchNorm-backward sums of the gradient it stores (see include/b200cd.h: b200cd_conv_gemm_bnbwd)."""
     _require_cuda(A, Bw, out, r, sums)
@@ -362,7 +373,9 @@ def conv_gemm_bnbwd(mode: int, A: torch.Tensor, Bw: torch.Tensor, out: torch.Ten
     taps = 9 if mode == 0 else 4
     assert mode in (0, 2) and Bw.shape[1] == taps * ka and (no, Ho, Wo, Co) == (n, H, W, N) == (nr, Hr, Wr, Cr)
     assert sums.dtype == torch.float32 and scale.shape[-1] == N
-    flags = 4 | 8 | (stat_groups << 8)
+    if bn == -1:
+        bn = tuning.tile("bnbwd", mode, 0, n, H, W, ka, N, False)
+    flags = 4 | 8 | (stat_groups << 8) | tuning.flag_bits(bn)
     _count(1)
     # own profile families: these launches also do the BatchNorm-backward reduce pass of the gradient they store
     fam = "dgrad3x3_bnbwd" if mode == 0 else "convT_dgrad_bnbwd"

@@ -1,0 +1,68 @@
+"""Measured N-tile choices of the CTA-pair convolution kernel, per layer shape.
+
+The library's own rule (csrc/abi.cu: plan_conv) picks the widest tile that divides N and leaves at least 48 work items.
+That is right for long-K layers, where the 256-wide tile is the only tensor-bound one, but not for every shape the
+U-Nets produce: short-K layers with wide outputs (input gradients of the decoder's channel-reducing convolutions,
+k = 64 -> n = 256) stream nine 16 KB weight half-tiles per 36 MMAs and run at half the rate of the same layer cut into
+narrower tiles whose weights stay resident or are cheap to stream. `tools/tile_sweep.py` times every (shape, variant)
+of the BASELINE configs with each tile width on a B200 and writes the table below; `ops.conv_gemm*` look the launch
+shape up (flags bits 5..6 of b200cd_conv_gemm, include/b200cd.h) and `ops.conv_stat_rows` uses the same entry, so the
+statistics buffers match the launch. A static table keeps a run reproducible across processes: the per-CTA partial sums
+(BatchNorm statistics) depend on the work assignment, so a run-time autotuner would make the last bits of a step
+depend on timing noise.
+
+B200CD_TUNED_TILES=0 ignores the table (the library's rule everywhere).
+
+Key: (variant, mode, out_mode, n_img, H, W, ka, N, prec) with variant one of
+  "stats"  forward convolution writing per-CTA BatchNorm statistics (also the concat-gradient dgrad with channel sums)
+  "plain"  no statistics side output
+  "bnbwd"  input gradient with the fused BatchNorm-backward sums
+  "affine" inference convolution with the folded BatchNorm epilogue
+"""
+from __future__ import annotations
+
+import os
+
+ENABLED = os.environ.get("B200CD_TUNED_TILES", "1") != "0"
+
+# (variant, mode, out_mode, n_img, H, W, ka, N, prec) -> N tile. Written by tools/tile_sweep.py --emit (measured on
+# B200, profiles/r02_tile_sweep.json); only entries that beat the library's rule by more than 3 % are kept.
+TABLE: dict = {
+}
+
+_CODE = {64: 1, 128: 2, 256: 3}
+
+# every (key) looked up since LOG was set to a list (tools/tile_sweep.py collects the launch shapes of a plan this way)
+LOG = None
+
+
+def load_table(path: str) -> None:
+    """Replace TABLE by the entries of a JSON file ([[variant, mode, out_mode, n_img, H, W, ka, N, prec, bn], ...]) —
+    tools/tile_sweep.py writes one; B200CD_TILE_TABLE=<path> loads it at import (same-box A/B of a fresh sweep)."""
+    import json
+    TABLE.clear()
+    with open(path) as f:
+        for *key, bn in json.load(f):
+            key[0], key[-1] = str(key[0]), bool(key[-1])
+            TABLE[tuple(key)] = int(bn)
+
+
+def tile(variant: str, mode: int, out_mode: int, n_img: int, H: int, W: int, ka: int, N: int, prec: bool = False):
+    """The measured tile width for this launch shape, or None (library rule)."""
+    key = (variant, mode, out_mode, n_img, H, W, ka, N, bool(prec))
+    if LOG is not None:
+        LOG.append(key)
+    if not ENABLED:
+        return None
+    return TABLE.get(key)
+
+
+def flag_bits(bn) -> int:
+    """flags bits 5..6 of b200cd_conv_gemm for an N tile of `bn` channels (0 for None)."""
+    if bn is None:
+        return 0
+    return _CODE[int(bn)] << 5
+
+
+if os.environ.get("B200CD_TILE_TABLE"):
+    load_table(os.environ["B200CD_TILE_TABLE"])

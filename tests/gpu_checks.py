@@ -328,6 +328,64 @@ def check_dgrad_bnbwd(n=4, H=32, W=32, cin=64, cout=128, G=2, seed=66, mode=0) -
     return res
 
 
+def check_forced_tiles(n=4, H=32, W=32, cin=64, cout=256, G=2, seed=120) -> dict:
+    """The N tile of the CTA-pair kernel chosen by the caller (flags bits 5..6 of b200cd_conv_gemm, tuning.py): every
+    tile width that divides N must give the SAME output bit for bit as the library's own choice (the K loop runs in the
+    same order) — forward with per-CTA statistics, plain, the fused BatchNorm-backward dgrad and the transposed-conv
+    scatter epilogue — and statistics / sums whose column totals agree."""
+    g = _gen(seed)
+    x = bf16r(torch.randn(n, cin, H, W, device=DEV, generator=g))
+    w = bf16r(torch.randn(cout, cin, 3, 3, device=DEV, generator=g) / (3.0 * cin ** 0.5))
+    b = torch.randn(cout, device=DEV, generator=g)
+    A = nhwc(x).to(torch.bfloat16)
+    Bw = ops.pack_weights(0, w)
+    res = {"ok": True}
+    base = {}
+    for bn in [None] + [t for t in (64, 128, 256) if cout % t == 0]:
+        tag = "auto" if bn is None else str(bn)
+        rows, per_cta = ops.conv_stat_rows(n, H, W, cin, cout, G, bn=bn)
+        stats = torch.full((G, rows, cout, 2), float("nan"), device=DEV)
+        o_s = torch.empty(n, H, W, cout, device=DEV, dtype=torch.bfloat16)
+        o_p = torch.empty_like(o_s)
+        ops.conv_gemm(0, 0, A, Bw, o_s, bias=b, stats=stats, stat_groups=G, bn=bn)
+        ops.conv_gemm(0, 0, A, Bw, o_p, bias=b, bn=bn)
+        # fused BatchNorm-backward dgrad: A plays the gradient, the output has `cout` channels
+        r = bf16r(torch.randn(n, H, W, cout, device=DEV, generator=_gen(seed + 1))).to(torch.bfloat16)
+        sc = torch.rand(G, cout, device=DEV, generator=_gen(seed + 2)) + 0.5
+        sh = torch.randn(G, cout, device=DEV, generator=_gen(seed + 3)) * 0.3
+        rows_b, _ = ops.conv_stat_rows(n, H, W, cin, cout, G, variant="bnbwd", bn=bn)
+        sums = torch.full((G, rows_b, cout, 2), float("nan"), device=DEV)
+        o_b = torch.empty_like(o_s)
+        ops.conv_gemm_bnbwd(0, A, Bw, o_b, r, sc, sh, sums, G, bn=bn)
+        ops.device_status()
+        cur = {"stats_out": o_s, "plain_out": o_p, "bnbwd_out": o_b, "stat_tot": stats.double().sum(1), "sum_tot": sums.double().sum(1),
+               "finite": bool(torch.isfinite(stats).all().item() and torch.isfinite(sums).all().item())}
+        res[f"rows_{tag}"] = rows
+        if bn is None:
+            base = cur
+            res["ok"] = res["ok"] and per_cta and cur["finite"] and bool(torch.equal(o_s, o_p))
+            continue
+        same = all(bool(torch.equal(cur[k], base[k])) for k in ("stats_out", "plain_out", "bnbwd_out"))
+        st_rel = ((cur["stat_tot"] - base["stat_tot"]).norm() / base["stat_tot"].norm()).item()
+        su_rel = ((cur["sum_tot"] - base["sum_tot"]).norm() / base["sum_tot"].norm()).item()
+        res[f"same_{tag}"], res[f"stat_rel_{tag}"], res[f"sums_rel_{tag}"] = same, st_rel, su_rel
+        res["ok"] = res["ok"] and same and cur["finite"] and st_rel < 1e-6 and su_rel < 1e-5
+    # transposed-conv forward (single tap, scatter epilogue): N = 4 * c
+    c = cin
+    wt = bf16r(torch.randn(c, c, 2, 2, device=DEV, generator=g) / (2.0 * c ** 0.5))
+    bt = torch.randn(c, device=DEV, generator=g)
+    Bt = ops.pack_weights(3, wt)
+    outs = []
+    for bn in [None] + [t for t in (64, 128, 256) if (4 * c) % t == 0]:
+        cat = torch.zeros(n, 2 * H, 2 * W, 2 * c, device=DEV, dtype=torch.bfloat16)
+        ops.conv_gemm(1, 1, A, Bt, cat[..., c:], bias=bt, bn=bn)
+        ops.device_status()
+        outs.append(cat)
+    res["convt_same"] = all(bool(torch.equal(o, outs[0])) for o in outs[1:])
+    res["ok"] = res["ok"] and res["convt_same"]
+    return res
+
+
 def check_pad_copy(n=2, h=8, w_=10, c=64, H=9, W=11, top=0, left=0, seed=90) -> dict:
     """Up's centre pad (utils/networks.py:440-443): dense tensor placed in the upper half of a concat buffer."""
     g = _gen(seed)
@@ -849,6 +907,9 @@ ALL_CHECKS = {
     "conv3x3_cta_stats_G1_many": lambda: check_conv3x3_cta_stats(16, 64, 64, 64, 64, G=1, seed=49),
     "conv3x3_cta_stats_G2_512": lambda: check_conv3x3_cta_stats(4, 16, 16, 256, 512, G=2, seed=50),
     "conv3x3_cta_stats_odd_tiles": lambda: check_conv3x3_cta_stats(6, 8, 8, 128, 64, G=2, seed=51),
+    "forced_tiles_64_256": check_forced_tiles,
+    "forced_tiles_256_512_deep": lambda: check_forced_tiles(4, 16, 16, 256, 512, G=1, seed=121),
+    "forced_tiles_128_128_ragged": lambda: check_forced_tiles(2, 24, 40, 128, 128, G=2, seed=122),
     "dgrad_bnbwd_G2": check_dgrad_bnbwd,
     "dgrad_bnbwd_G1_many": lambda: check_dgrad_bnbwd(16, 64, 64, 64, 64, G=1, seed=67),
     "dgrad_bnbwd_256_512": lambda: check_dgrad_bnbwd(4, 16, 16, 256, 512, G=1, seed=68),
