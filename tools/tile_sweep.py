@@ -65,52 +65,63 @@ def time_key(key, reps: int, flush) -> dict:
         out = act(n, H, W, N)
     bias = torch.zeros(N, device=dev)
     G = 1
-    res = {}
     cands = [None] + [b for b in (64, 128, 256) if N % b == 0]
+    launches = {}
+    keep = []           # buffers of every candidate stay alive until all are timed
     for bn in cands:
-        kw = {}
         if variant in ("stats", "bnbwd"):
             rows, per_cta = ops.conv_stat_rows(n, H, W, ka, N, G, mode=mode, prec=prec, variant=variant, bn=bn)
             if not per_cta:
                 continue
             stats = torch.zeros(G * rows * N * 2, device=dev)
+            keep.append(stats)
         if variant == "bnbwd":
             r = act(n, H, W, N)
             sc = torch.rand(G, N, device=dev) + 0.5
             sh = torch.randn(G, N, device=dev) * 0.1
+            keep += [r, sc, sh]
 
-            def launch():
+            def launch(bn=bn, stats=stats, rows=rows, r=r, sc=sc, sh=sh):
                 ops.conv_gemm_bnbwd(mode, A, Bw, out, r, sc, sh, stats.view(G, rows, N, 2), G, bn=bn)
         elif variant == "stats":
-            def launch():
+            def launch(bn=bn, stats=stats):
                 ops.conv_gemm(mode, out_mode, A, Bw, out, bias=bias if out_mode == 0 else None, stats=stats, stat_groups=G,
                               prec=prec, bn=bn)
         elif variant == "affine":
             sc = torch.rand(N, device=dev) + 0.5
             sh = torch.randn(N, device=dev) * 0.1
+            keep += [sc, sh]
 
-            def launch():
+            def launch(bn=bn, sc=sc, sh=sh):
                 ops.conv_gemm_affine(mode, A, Bw, out, bias, sc, sh, True, prec=prec, bn=bn)
         else:
             b1 = torch.zeros(N // 4 if out_mode == 1 else N, device=dev)
+            keep.append(b1)
 
-            def launch():
+            def launch(bn=bn, b1=b1):
                 ops.conv_gemm(mode, out_mode, A, Bw, out, bias=b1, prec=prec, bn=bn)
+        launches["auto" if bn is None else str(bn)] = launch
+    for f in launches.values():
         for _ in range(3):
-            launch()
-        torch.cuda.synchronize()
-        ev = []
-        for _ in range(reps):
+            f()
+    torch.cuda.synchronize()
+    # candidates interleaved rep by rep (clock / thermal drift hits all of them alike), L2 flushed before every launch
+    ev = {k: [] for k in launches}
+    torch.cuda._sleep(int(6e7))   # ~40 ms spin kernel: the host enqueues every launch below before the first one runs,
+    for _ in range(reps):         # so no event interval holds host latency (tensor-map encoding, ctypes)
+        for k, f in launches.items():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            launch()
+            f()
             e1.record()
-            ev.append((e0, e1))
-        torch.cuda.synchronize()
-        ops.device_status()
-        t = sorted(a.elapsed_time(b) for a, b in ev)
-        res["auto" if bn is None else str(bn)] = round(t[len(t) // 2] * 1e3, 2)   # microseconds
+            ev[k].append((e0, e1))
+    torch.cuda.synchronize()
+    ops.device_status()
+    res = {}
+    for k, pairs in ev.items():
+        t = sorted(a.elapsed_time(b) for a, b in pairs)
+        res[k] = round(t[len(t) // 2] * 1e3, 2)   # microseconds (median)
     return res
 
 
@@ -118,7 +129,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="siamese,dualstream,dtsiamese,mmcr")
     ap.add_argument("--precise-configs", default="dualstream")
-    ap.add_argument("--reps", type=int, default=15)
+    ap.add_argument("--reps", type=int, default=21)
     ap.add_argument("--margin", type=float, default=0.03)
     ap.add_argument("--out", default="gpurun_out/tile_sweep.json")
     ap.add_argument("--emit", default="gpurun_out/tuned_tiles.json")
@@ -134,6 +145,9 @@ def main():
                 keys[k] = keys.get(k, 0) + 1
                 users.setdefault(k, set()).add(f"{c}/{prec}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2000):           # ~0.1 s of memsets: clocks settled before the first shape is timed
+        flush.zero_()
+    torch.cuda.synchronize()
     rows, emit = [], []
     for k in sorted(keys, key=lambda k: (k[8], k[0], k[1], -k[3] * k[4] * k[5], k[6], k[7])):
         t = time_key(k, a.reps, flush)
