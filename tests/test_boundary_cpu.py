@@ -182,3 +182,36 @@ def test_documented_knobs_exist_in_code():
     assert documented - {"B200CD_DEBUG_"} <= read | {"B200CD_NVCC_EXTRA"}, documented - read
     assert read - debug <= documented, read - debug - documented
 
+
+
+def test_tile_table_is_well_formed_and_reaches_the_flags(tmp_path):
+    """tuning.TABLE: every entry names a known variant, a tile that divides N and differs from nothing the kernels cannot
+    run; ops._conv_flags encodes it in bits 5..6 (include/b200cd.h); B200CD_TILE_TABLE-style JSON round-trips; the
+    committed table equals profiles/r02_tile_table_v3.json (the measured one)."""
+    import json
+    from multimodal_siamese_cd_b200 import ops, tuning
+    assert tuning.TABLE, "the measured table is committed"
+    for key, bn in tuning.TABLE.items():
+        variant, mode, out_mode, n, H, W, ka, N, prec = key
+        assert variant in ("stats", "plain", "bnbwd", "affine") and mode in (0, 1, 2) and out_mode in (0, 1)
+        assert bn in (64, 128, 256) and N % bn == 0 and ka % 64 == 0 and isinstance(prec, bool)
+        assert not (variant == "bnbwd" and prec), "the fused BatchNorm-backward dgrad is a bf16-storage kernel"
+        assert tuning.tile(*key) == bn
+        flags = ops._conv_flags(mode, out_mode, N, ka, None, None, None, 1 if variant in ("stats", "bnbwd") else 0, bn)
+        assert flags & 4 and ((flags >> 5) & 3) == {64: 1, 128: 2, 256: 3}[bn]
+    assert ops._conv_flags(0, 0, 256, 64, None, None, None, 0, None) == 4          # no entry: the library's own rule
+    root = Path(__file__).resolve().parent.parent
+    measured = json.loads((root / "profiles" / "r02_tile_table_v3.json").read_text())
+    assert {tuple(e[:8]) + (bool(e[8]),): e[9] for e in measured} == tuning.TABLE
+    saved = dict(tuning.TABLE)
+    try:
+        f = tmp_path / "t.json"
+        f.write_text(json.dumps([["plain", 0, 0, 2, 32, 32, 64, 256, 0, 128]]))
+        tuning.load_table(str(f))
+        assert tuning.TABLE == {("plain", 0, 0, 2, 32, 32, 64, 256, False): 128}
+        old, tuning.ENABLED = tuning.ENABLED, False
+        assert tuning.tile("plain", 0, 0, 2, 32, 32, 64, 256, False) is None         # B200CD_TUNED_TILES=0
+        tuning.ENABLED = old
+    finally:
+        tuning.TABLE.clear()
+        tuning.TABLE.update(saved)
