@@ -149,3 +149,23 @@ def test_reference_script_plain_cpu_smoke(tmp_path):
     got = merged(logged)
     assert 0.0 < got["loss"] <= 1.0 and {"training F1", "validation F1", "test F1"} <= set(got), got
     assert ck["step"] == 1 and "module.inc.conv.conv.0.weight" in ck["network"]
+
+
+def test_reference_dualtask_script_cannot_start_upstream(tmp_path):
+    """Why train_supervised_dualtask.py is not among the cases above: the reference snapshot's own script dies before
+    it builds a network — `experiment_manager.default_argument_parser` (train_supervised_dualtask.py:132) and
+    `datasets.SpaceNet7CDDataset` (:37) are defined nowhere in the tree. Its step body
+    (:75-85) is what `TrainStep(kind="dualtask")`, bench.py's e2e loop and the `dtsiamese*` parity cases run instead.
+    If this test ever fails the script has become runnable and belongs in CASES."""
+    ref = stage_reference.staged_root()
+    if ref is None:
+        pytest.skip("no reference tree")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([str(ROOT / "tests" / "stubs"), str(ROOT), env.get("PYTHONPATH", "")])
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "ref_runner.py"), str(ref), "train_supervised_dualtask.py", "-c",
+                        "dtsiamese", "-p", "test", "-o", str(tmp_path / "o"), "-d", str(tmp_path / "d")],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "default_argument_parser" in r.stderr, r.stderr[-2000:]
+    src = (Path(ref) / "utils" / "datasets.py").read_text()
+    assert "SpaceNet7CDDataset" not in src
