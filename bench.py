@@ -444,6 +444,27 @@ class Bench:
                   "tolerance": "north_star: logits and gradients rel 1e-3, loss 1e-4, identical masks; read against "
                                "the reference's own fp32-vs-fp64 floor (SURVEY App. C: gradients 8e-4 global, 3e-3 per "
                                "parameter at random init through train-mode BatchNorm)"}
+        def metrics(outs, loss_value: float, grad_of, names, skip, tag: str) -> dict:
+            """The tolerance's quantities against the CPU reference step: worst-output logits rel L2, |loss difference|,
+            gradient rel L2 over all parameters and for the worst one, thresholded-mask flips."""
+            num = den = 0.0
+            worst, worst_name = 0.0, ""
+            for name in names:
+                rg = ref["grads"].get(name)
+                if name in skip or rg is None or name.endswith((".conv.0.bias", ".conv.3.bias")):
+                    continue      # no gradient in the reference / analytically zero (pre-BN conv bias)
+                d = (grad_of(name).detach().double().cpu() - rg.double()).norm().item()
+                nn_ = rg.double().norm().item()
+                num, den = num + d * d, den + nn_ * nn_
+                if d / max(nn_, 1e-30) > worst:
+                    worst, worst_name = d / max(nn_, 1e-30), name
+            lg = max(((a.double() - b.double()).norm() / b.double().norm()).item() for a, b in zip(outs, ref["outs"]))
+            flips = int(((outs[0] > 0) != (ref["outs"][0] > 0)).sum())
+            flips3 = int((((outs[0] > 0) != (ref["outs"][0] > 0)) & (ref["outs"][0].abs() >= 1e-3)).sum())
+            return {"logits_x": lg, "loss_x": abs(loss_value - ref["loss"]), "grads_x_global": (num / max(den, 1e-60)) ** 0.5,
+                    "grads_x_max": worst, "grads_x_worst_param": worst_name, "mask_flips": flips,
+                    "mask_flips_outside_1e-3": flips3, "pixels": outs[0].numel(), "mode": tag}
+
         for mode in ("fast", "precise"):
             net.load_state_dict(sd0)
             net.module.set_precision(mode)
@@ -453,26 +474,46 @@ class Bench:
             torch.cuda.synchronize()
             outs = [o.detach().cpu() for o in ts.eng.output_tensors()]
             g = ts.eng.grads
-            num = den = 0.0
-            worst, worst_name = 0.0, ""
-            for name, p in g.params:
-                rg = ref["grads"].get(name)
-                if name in g.skip or rg is None or name.endswith((".conv.0.bias", ".conv.3.bias")):
-                    continue      # no gradient in the reference / analytically zero (pre-BN conv bias)
-                d = (g.views[name].detach().double().cpu() - rg.double()).norm().item()
-                nn_ = rg.double().norm().item()
-                num, den = num + d * d, den + nn_ * nn_
-                if d / max(nn_, 1e-30) > worst:
-                    worst, worst_name = d / max(nn_, 1e-30), name
-            lg = max(((a.double() - b.double()).norm() / b.double().norm()).item() for a, b in zip(outs, ref["outs"]))
-            flips = int(((outs[0] > 0) != (ref["outs"][0] > 0)).sum())
-            flips3 = int((((outs[0] > 0) != (ref["outs"][0] > 0)) & (ref["outs"][0].abs() >= 1e-3)).sum())
-            parity[mode] = {"logits_x": lg, "loss_x": abs(float(loss.item()) - ref["loss"]),
-                            "grads_x_global": (num / max(den, 1e-60)) ** 0.5, "grads_x_max": worst,
-                            "grads_x_worst_param": worst_name, "mask_flips": flips, "mask_flips_outside_1e-3": flips3,
-                            "pixels": outs[0].numel(), "mode": mode}
+            parity[mode] = metrics(outs, float(loss.item()), lambda name, g=g: g.views[name], [nm for nm, _ in g.params], g.skip,
+                                   mode)
             net.module.release_engines()
             del ts
+            torch.cuda.empty_cache()
+        del net
+        # The yardstick for those numbers: the reference's OWN modules on this GPU under stock PyTorch (cuDNN / cuBLAS, none
+        # of this repo's kernels) against the same CPU step — fp32 with TF32 off (another summation order of the same
+        # arithmetic: what "matching the fp32 path" can mean at best), TF32, bf16 autocast.
+        from oracle import ref_modules
+        mods = ref_modules.load()
+        if mods is not None and cpu["kind"] == "reference":
+            nets, losses = mods
+            torch.manual_seed(cfg.SEED)
+            rnet = nets.create_network(cfg).module
+            old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+            try:
+                rb = dict(gb)
+                rb["is_labeled"] = batch["is_labeled"]
+                for tag, tf32, autocast in (("library_fp32", False, False), ("library_tf32", True, False),
+                                            ("library_bf16_autocast", True, True)):
+                    rnet.load_state_dict(ref["state"])
+                    rnet.to(self.dev).train()
+                    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+                    try:
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                            outs, loss = ref_modules.train_step(rnet, losses, rb, kind, alpha)
+                        torch.cuda.synchronize()
+                        outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+                        grads = {k: q.grad for k, q in rnet.named_parameters()}
+                        parity[tag] = metrics([o.detach().float().cpu() for o in outs], float(loss),
+                                              lambda name, grads=grads: grads[name],
+                                              [k for k, v in grads.items() if v is not None], set(), tag)
+                    except Exception as e:  # noqa: BLE001  (report, keep the other legs)
+                        parity[tag] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+                parity["library_note"] = ("library_*: the reference's own modules on this GPU under stock PyTorch eager "
+                                          "(cuDNN, none of this repo's kernels) against the same CPU fp32 step")
+            finally:
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+            del rnet
             torch.cuda.empty_cache()
         return parity, cpu
 
